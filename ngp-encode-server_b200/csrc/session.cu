@@ -1,0 +1,794 @@
+// session.cu -- host runtime behind the C ABI (include/nes_gpu.h).
+//
+// A session is what one process_frame_thread of the reference owns
+// (/root/reference/src/encode.cpp:42-119, one per eye, main.cpp:274-282): a CUDA device,
+// three streams (H2D | kernels | D2H) and a ring of frame slots so that the upload of
+// frame f+1, the kernels of frame f and the download of frame f-1 overlap.  Per frame
+// the host does: pen arithmetic for the text runs (text.cc), one descriptor (DevJob),
+// at most one pinned staging memcpy each way (none when the caller's buffers are pinned),
+// and 1-3 kernel launches (kernels.cu).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "filter.h"
+#include "nes_gpu.h"
+#include "nes_internal.h"
+#include "text.h"
+
+using namespace nes;
+
+namespace {
+
+constexpr int kMaxBatch = 256;
+constexpr int kBatchRing = 8;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct FilterSet {  // device tables for one (W,H,Wd,Hd)
+  DevFilter hl{}, hc{}, vl{}, vc{};
+  FilterTable h_hl, h_hc, h_vl, h_vc;
+  void *blob = nullptr;
+  int half = 0, csW = 0;
+  int smem_need[2] = {0, 0};  // bpp 3 / 4
+};
+
+struct StagedCopy {  // pinned staging -> caller memory, done in wait()
+  uint8_t *dst;
+  const uint8_t *src;
+  size_t bytes;
+};
+
+struct Slot {
+  uint8_t *d_in = nullptr, *d_out = nullptr, *d_scratch = nullptr;
+  size_t d_in_cap = 0, d_out_cap = 0, d_scratch_cap = 0;
+  uint8_t *h_in = nullptr, *h_out = nullptr;
+  size_t h_in_cap = 0, h_out_cap = 0;
+  DevJob *h_job = nullptr, *d_job = nullptr;
+  DevPlaced *h_glyphs = nullptr, *d_glyphs = nullptr;
+  cudaEvent_t e_start = nullptr, e_in = nullptr, e_k0 = nullptr, e_k1 = nullptr, e_out = nullptr;
+  uint64_t ticket = 0;
+  bool busy = false;
+  int n_launches = 0;
+  std::vector<StagedCopy> staged;
+};
+
+struct BatchTables {
+  DevJob *h_jobs = nullptr, *d_jobs = nullptr;
+  DevPlaced *h_glyphs = nullptr, *d_glyphs = nullptr;
+  cudaEvent_t done = nullptr;
+  bool used = false;
+};
+
+}  // namespace
+
+struct nes_gpu_session {
+  nes_gpu_cfg cfg{};
+  std::mutex mu;
+  cudaStream_t st_in = nullptr, st_k = nullptr, st_out = nullptr;
+  std::vector<Slot> slots;
+  BatchTables batch[kBatchRing];
+  uint64_t batch_seq = 0;
+  uint64_t next_ticket = 1;
+  uint64_t launches = 0;
+  HostAtlas atlas;
+  uint8_t *d_atlas = nullptr;
+  std::map<std::tuple<int, int, int, int>, FilterSet> filters;
+  nes_timing last{};
+  std::string err;
+  int sticky = 0;
+  std::vector<nes_placed_glyph> scratch_placed;
+};
+
+namespace {
+
+#define CU_TRY(s, call)                                                                      \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      (s)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+      (s)->sticky = NES_ERR_CUDA;                                                            \
+      return NES_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+int ensure_dev(nes_gpu_session *s, uint8_t **p, size_t *cap, size_t need) {
+  if (need <= *cap) return NES_OK;
+  if (*p) CU_TRY(s, cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  need = align_up(need, 1 << 20);
+  CU_TRY(s, cudaMalloc((void **)p, need));
+  CU_TRY(s, cudaMemset(*p, 0, need));
+  *cap = need;
+  return NES_OK;
+}
+
+int ensure_host(nes_gpu_session *s, uint8_t **p, size_t *cap, size_t need) {
+  if (need <= *cap) return NES_OK;
+  if (*p) CU_TRY(s, cudaFreeHost(*p));
+  *p = nullptr;
+  *cap = 0;
+  need = align_up(need, 1 << 20);
+  CU_TRY(s, cudaHostAlloc((void **)p, need, cudaHostAllocDefault));
+  *cap = need;
+  return NES_OK;
+}
+
+bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int fmt_info(int fmt, int *bpp, int *base, int *a_off, bool *bgr) {
+  switch (fmt) {
+    case NES_PIX_RGB24: *bpp = 3; *base = 0; *a_off = -1; *bgr = false; return 0;
+    case NES_PIX_BGR24: *bpp = 3; *base = 0; *a_off = -1; *bgr = true; return 0;
+    case NES_PIX_RGBA: *bpp = 4; *base = 0; *a_off = 3; *bgr = false; return 0;
+    case NES_PIX_BGRA: *bpp = 4; *base = 0; *a_off = 3; *bgr = true; return 0;
+    case NES_PIX_ARGB: *bpp = 4; *base = 1; *a_off = 0; *bgr = false; return 0;
+    case NES_PIX_ABGR: *bpp = 4; *base = 1; *a_off = 0; *bgr = true; return 0;
+    default: return -1;
+  }
+}
+
+// shared memory the resize kernel needs for its worst tile (mirrors k_resize_tiles)
+int resize_smem_need(const FilterSet &fs, int W, int Wd, int Hd, int bpp) {
+  const int cdW = (Wd + 1) >> 1, cdH = (Hd + 1) >> 1;
+  (void)W;
+  int worst = 0;
+  for (int dy0 = 0; dy0 < Hd; dy0 += RS_TILE_H) {
+    const int dy1 = std::min(dy0 + RS_TILE_H, Hd);
+    const int cy0 = dy0 >> 1, cy1 = std::min((dy1 + 1) >> 1, cdH);
+    int lr0 = 1 << 30, lr1 = 0, cr0 = 1 << 30, cr1 = 0;
+    for (int i = dy0; i < dy1; i++) { lr0 = std::min(lr0, fs.h_vl.pos[i]); lr1 = std::max(lr1, fs.h_vl.pos[i] + fs.vl.size); }
+    for (int i = cy0; i < cy1; i++) { cr0 = std::min(cr0, fs.h_vc.pos[i]); cr1 = std::max(cr1, fs.h_vc.pos[i] + fs.vc.size); }
+    for (int dx0 = 0; dx0 < Wd; dx0 += RS_TILE_W) {
+      const int dx1 = std::min(dx0 + RS_TILE_W, Wd);
+      const int cx0 = dx0 >> 1, cx1 = std::min((dx1 + 1) >> 1, cdW);
+      int lc0 = 1 << 30, lc1 = 0, cc0 = 1 << 30, cc1 = 0;
+      for (int i = dx0; i < dx1; i++) { lc0 = std::min(lc0, fs.h_hl.pos[i]); lc1 = std::max(lc1, fs.h_hl.pos[i] + fs.hl.size); }
+      for (int i = cx0; i < cx1; i++) { cc0 = std::min(cc0, fs.h_hc.pos[i]); cc1 = std::max(cc1, fs.h_hc.pos[i] + fs.hc.size); }
+      const int pc0 = fs.half ? cc0 * 2 : cc0, pc1 = fs.half ? cc1 * 2 : cc1;
+      const int wx0 = std::min(lc0, pc0), wx1 = std::max(lc1, pc1);
+      const int wy0 = std::min(lr0, cr0), wy1 = std::max(lr1, cr1);
+      const int ww = wx1 - wx0, wh = wy1 - wy0, lw = lc1 - lc0, cw = cc1 - cc0, dw = dx1 - dx0, dcw = cx1 - cx0;
+      size_t need = (size_t)((wh * ww * bpp + 15) & ~15);
+      need += 2 * (size_t)(((lr1 - lr0) * lw + 7) & ~7);
+      need += 2 * 2 * (size_t)(((cr1 - cr0) * cw + 7) & ~7);
+      need += 2 * (size_t)(((lr1 - lr0) * dw + 7) & ~7);
+      need += 2 * 2 * (size_t)(((cr1 - cr0) * dcw + 7) & ~7);
+      need += HIT_CAP * 4 + 32;
+      worst = std::max(worst, (int)need);
+    }
+  }
+  return worst;
+}
+
+int get_filters(nes_gpu_session *s, int W, int H, int Wd, int Hd, FilterSet **out) {
+  auto key = std::make_tuple(W, H, Wd, Hd);
+  auto it = s->filters.find(key);
+  if (it != s->filters.end()) { *out = &it->second; return NES_OK; }
+  FilterSet fs;
+  const int cdW = (Wd + 1) >> 1, cdH = (Hd + 1) >> 1;
+  fs.half = (Wd >> 1) <= (W >> 1);
+  fs.csW = fs.half ? (W >> 1) : W;
+  if (build_filter(W, Wd, 1 << 14, &fs.h_hl) < 0 || build_filter(fs.csW, cdW, 1 << 14, &fs.h_hc) < 0 ||
+      build_filter(H, Hd, 1 << 12, &fs.h_vl) < 0 || build_filter(H, cdH, 1 << 12, &fs.h_vc) < 0)
+    return NES_ERR_INVALID_ARG;
+  const FilterTable *t[4] = {&fs.h_hl, &fs.h_hc, &fs.h_vl, &fs.h_vc};
+  DevFilter *d[4] = {&fs.hl, &fs.hc, &fs.vl, &fs.vc};
+  size_t total = 0, off[4][2];
+  for (int i = 0; i < 4; i++) {
+    off[i][0] = total; total = align_up(total + t[i]->coef.size() * 2 + 64, 256);  // +64: tap loops may over-read a row
+    off[i][1] = total; total = align_up(total + t[i]->pos.size() * 4, 256);
+  }
+  std::vector<uint8_t> host(total, 0);
+  for (int i = 0; i < 4; i++) {
+    std::memcpy(&host[off[i][0]], t[i]->coef.data(), t[i]->coef.size() * 2);
+    std::memcpy(&host[off[i][1]], t[i]->pos.data(), t[i]->pos.size() * 4);
+  }
+  CU_TRY(s, cudaMalloc(&fs.blob, total));
+  CU_TRY(s, cudaMemcpy(fs.blob, host.data(), total, cudaMemcpyHostToDevice));
+  for (int i = 0; i < 4; i++) {
+    d[i]->coef = (const int16_t *)((uint8_t *)fs.blob + off[i][0]);
+    d[i]->pos = (const int32_t *)((uint8_t *)fs.blob + off[i][1]);
+    d[i]->size = t[i]->size;
+  }
+  fs.smem_need[0] = resize_smem_need(fs, W, Wd, Hd, 3);
+  fs.smem_need[1] = resize_smem_need(fs, W, Wd, Hd, 4);
+  auto ins = s->filters.emplace(key, std::move(fs));
+  *out = &ins.first->second;
+  return NES_OK;
+}
+
+struct PlaneLayout {  // where one YUV420P image sits inside a linear buffer
+  size_t off[3];
+  size_t bytes[3];
+  size_t total;
+};
+
+PlaneLayout yuv_layout(const int32_t ls[3], int Hd, size_t base) {
+  PlaneLayout p;
+  const int cH = (Hd + 1) >> 1;
+  p.off[0] = base; p.bytes[0] = (size_t)ls[0] * Hd;
+  p.off[1] = p.off[0] + p.bytes[0]; p.bytes[1] = (size_t)ls[1] * cH;
+  p.off[2] = p.off[1] + p.bytes[1]; p.bytes[2] = (size_t)ls[2] * cH;
+  p.total = p.bytes[0] + p.bytes[1] + p.bytes[2];
+  return p;
+}
+
+int validate(const nes_gpu_session *s, const nes_frame_in *in, const nes_frame_out *out, int bpp) {
+  if (in->n_sources < 1 || in->n_sources > NES_MAX_SOURCES || in->n_sources > s->cfg.max_sources) return NES_ERR_INVALID_ARG;
+  const int W = in->width, H = in->height, Wd = out->width, Hd = out->height;
+  if (W < 4 || H < 4 || Wd < 4 || Hd < 4 || ((W | H | Wd | Hd) & 1)) return NES_ERR_INVALID_ARG;
+  if (W > s->cfg.max_width || H > s->cfg.max_height || Wd > s->cfg.max_width || Hd > s->cfg.max_height) return NES_ERR_TOO_LARGE;
+  if (in->mem != NES_MEM_HOST && in->mem != NES_MEM_DEVICE) return NES_ERR_INVALID_ARG;
+  if (out->mem != NES_MEM_HOST && out->mem != NES_MEM_DEVICE) return NES_ERR_INVALID_ARG;
+  const bool want_depth = out->depth[0] != nullptr;
+  for (int k = 0; k < in->n_sources; k++) {
+    const nes_source &sr = in->src[k];
+    if (!sr.rgb) return NES_ERR_INVALID_ARG;
+    const int64_t rs = sr.rgb_stride ? sr.rgb_stride : W * bpp;
+    if (rs < (int64_t)W * bpp) return NES_ERR_INVALID_ARG;
+    if (sr.rgb_bytes < (uint64_t)(rs * (H - 1) + (int64_t)W * bpp)) return NES_ERR_SHORT_BUFFER;
+    if (want_depth || in->n_sources > 1) {
+      if (!sr.depth) return NES_ERR_INVALID_ARG;
+      const int64_t ds = sr.depth_stride ? sr.depth_stride : W;
+      if (ds < W) return NES_ERR_INVALID_ARG;
+      if (sr.depth_bytes < (uint64_t)(ds * (H - 1) + W)) return NES_ERR_SHORT_BUFFER;
+    }
+  }
+  for (int p = 0; p < 3; p++) {
+    const int minls = p ? (Wd + 1) / 2 : Wd;
+    if (!out->scene[p] || out->scene_linesize[p] < minls) return NES_ERR_INVALID_ARG;
+    if (want_depth && (!out->depth[p] || out->depth_linesize[p] < minls)) return NES_ERR_INVALID_ARG;
+  }
+  return NES_OK;
+}
+
+bool aligned16(const void *p, int stride) { return (((uintptr_t)p | (uintptr_t)stride) & 15) == 0; }
+
+// Fill the colour / geometry part of a job.
+void job_common(DevJob *jb, const nes_frame_in *in, const nes_frame_out *out, int bpp, int base, int a_off, bool bgr) {
+  std::memset(jb, 0, sizeof(*jb));
+  jb->n_src = in->n_sources;
+  jb->bpp = bpp;
+  jb->rgb_base = base;
+  jb->a_off = a_off;
+  const int RY = 8414, GY = 16519, BY = 3208, RU = -4865, GU = -9528, BU = 14392, RV = 14392, GV = -12061, BV = -2332;
+  const int r = bgr ? 2 : 0, b = bgr ? 0 : 2;
+  jb->cy[r] = RY; jb->cy[1] = GY; jb->cy[b] = BY;
+  jb->cu[r] = RU; jb->cu[1] = GU; jb->cu[b] = BU;
+  jb->cv[r] = RV; jb->cv[1] = GV; jb->cv[b] = BV;
+  jb->W = in->width; jb->H = in->height; jb->Wd = out->width; jb->Hd = out->height;
+}
+
+void job_tiles(DevJob *jb, int tile_base) {
+  if (jb->W == jb->Wd && jb->H == jb->Hd) {
+    jb->tiles_x = (jb->W + TILE_W - 1) / TILE_W;
+    jb->tiles_y = (jb->H + TILE_H - 1) / TILE_H;
+  } else {
+    jb->tiles_x = (jb->Wd + RS_TILE_W - 1) / RS_TILE_W;
+    jb->tiles_y = (jb->Hd + RS_TILE_H - 1) / RS_TILE_H;
+  }
+  jb->tile_base = tile_base;
+}
+
+void job_alignment(DevJob *jb) {
+  bool iv = true;
+  for (int k = 0; k < jb->n_src; k++) {
+    iv = iv && aligned16(jb->src[k].rgb, jb->src[k].rgb_stride);
+    if (jb->src[k].depth) iv = iv && aligned16(jb->src[k].depth, jb->src[k].depth_stride);
+  }
+  bool ov = aligned16(jb->sy, jb->sys) && aligned16(jb->su, jb->sus) && aligned16(jb->sv, jb->svs);
+  if (jb->dy) ov = ov && aligned16(jb->dy, jb->dys) && aligned16(jb->du, jb->dus) && aligned16(jb->dv, jb->dvs);
+  jb->in_vec = iv;
+  jb->out_vec = ov;
+}
+
+// Text runs -> placed glyph descriptors at dst[0..].  Returns count or negative status.
+int place_text(nes_gpu_session *s, int W, int H, const nes_text_run *runs, int n_runs, DevPlaced *dst, int cap) {
+  if (n_runs <= 0) return 0;
+  if (!runs) return NES_ERR_INVALID_ARG;
+  if (!s->atlas.valid) return NES_ERR_NO_ATLAS;
+  s->scratch_placed.clear();
+  for (int r = 0; r < n_runs; r++) {
+    if (runs[r].len > 0 && !runs[r].text) return NES_ERR_INVALID_ARG;
+    layout_run(s->atlas, W, H, runs[r], &s->scratch_placed);
+  }
+  const int n = (int)s->scratch_placed.size();
+  if (n > cap) return NES_ERR_TOO_LARGE;
+  for (int i = 0; i < n; i++) {
+    const nes_placed_glyph &pg = s->scratch_placed[i];
+    const HostGlyph &g = s->atlas.glyph[pg.code];
+    dst[i] = DevPlaced{pg.x, pg.y, g.width, g.rows, g.pitch, g.offset};
+  }
+  return n;
+}
+
+int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, int n, cudaStream_t st) {
+  int l = 0;
+  l += launch_composite(d_jobs, h_jobs, n, st);
+  l += launch_frame_tiles(d_jobs, h_jobs, n, st);
+  const int r = launch_resize_tiles(d_jobs, h_jobs, n, st);
+  if (r > 0) l += r;
+  s->launches += (uint64_t)l;
+  return l;
+}
+
+}  // namespace
+
+// ============================================================================
+extern "C" {
+
+int nes_gpu_abi_version(void) { return NES_ABI_VERSION; }
+
+const char *nes_gpu_strerror(int st) {
+  switch (st) {
+    case NES_OK: return "ok";
+    case NES_ERR_INVALID_ARG: return "invalid argument";
+    case NES_ERR_SHORT_BUFFER: return "source buffer shorter than stride*height";
+    case NES_ERR_TOO_LARGE: return "frame or glyph list exceeds the session limits";
+    case NES_ERR_CUDA: return "CUDA error (see nes_gpu_session_error)";
+    case NES_ERR_NO_MEMORY: return "out of memory";
+    case NES_ERR_BAD_TICKET: return "unknown ticket";
+    case NES_ERR_PARSE: return "malformed RenderedFrame message";
+    case NES_ERR_NO_ATLAS: return "text submitted before a glyph atlas was set";
+    case NES_ERR_FREETYPE: return "FreeType unavailable or font could not be opened";
+    case NES_ERR_BUSY: return "frame ring full; wait on an older ticket";
+    default: return "unknown status";
+  }
+}
+
+const char *nes_gpu_session_error(nes_gpu_session *s) { return s ? s->err.c_str() : ""; }
+
+int nes_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int nes_gpu_session_create(const nes_gpu_cfg *cfg, nes_gpu_session **out) {
+  if (!cfg || !out) return NES_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (cfg->max_width < 4 || cfg->max_height < 4) return NES_ERR_INVALID_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return NES_ERR_CUDA; }
+  if (cfg->device < 0 || cfg->device >= ndev) return NES_ERR_INVALID_ARG;
+  nes_gpu_session *s = new (std::nothrow) nes_gpu_session();
+  if (!s) return NES_ERR_NO_MEMORY;
+  s->cfg = *cfg;
+  if (s->cfg.max_sources < 1) s->cfg.max_sources = 1;
+  if (s->cfg.max_sources > NES_MAX_SOURCES) s->cfg.max_sources = NES_MAX_SOURCES;
+  if (s->cfg.ring_depth < 1) s->cfg.ring_depth = 3;
+  if (s->cfg.max_glyphs < 1) s->cfg.max_glyphs = 8192;
+  auto fail = [&](int st) { nes_gpu_session_destroy(s); return st; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(NES_ERR_CUDA);
+  if (kernels_init() != 0) return fail(NES_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&s->st_in, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&s->st_k, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&s->st_out, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
+  s->slots.resize((size_t)s->cfg.ring_depth);
+  const size_t gl_bytes = (size_t)s->cfg.max_glyphs * sizeof(DevPlaced);
+  for (Slot &sl : s->slots) {
+    cudaEvent_t *ev[5] = {&sl.e_start, &sl.e_in, &sl.e_k0, &sl.e_k1, &sl.e_out};
+    for (cudaEvent_t *e : ev)
+      if (cudaEventCreate(e) != cudaSuccess) return fail(NES_ERR_CUDA);
+    if (cudaHostAlloc((void **)&sl.h_job, sizeof(DevJob), cudaHostAllocDefault) != cudaSuccess) return fail(NES_ERR_CUDA);
+    if (cudaMalloc((void **)&sl.d_job, sizeof(DevJob)) != cudaSuccess) return fail(NES_ERR_CUDA);
+    if (cudaHostAlloc((void **)&sl.h_glyphs, gl_bytes, cudaHostAllocDefault) != cudaSuccess) return fail(NES_ERR_CUDA);
+    if (cudaMalloc((void **)&sl.d_glyphs, gl_bytes) != cudaSuccess) return fail(NES_ERR_CUDA);
+  }
+  *out = s;
+  return NES_OK;
+}
+
+void nes_gpu_session_destroy(nes_gpu_session *s) {
+  if (!s) return;
+  cudaSetDevice(s->cfg.device);
+  if (s->st_in) cudaStreamSynchronize(s->st_in);
+  if (s->st_k) cudaStreamSynchronize(s->st_k);
+  if (s->st_out) cudaStreamSynchronize(s->st_out);
+  for (Slot &sl : s->slots) {
+    cudaFree(sl.d_in); cudaFree(sl.d_out); cudaFree(sl.d_scratch);
+    cudaFreeHost(sl.h_in); cudaFreeHost(sl.h_out);
+    cudaFreeHost(sl.h_job); cudaFree(sl.d_job);
+    cudaFreeHost(sl.h_glyphs); cudaFree(sl.d_glyphs);
+    cudaEvent_t ev[5] = {sl.e_start, sl.e_in, sl.e_k0, sl.e_k1, sl.e_out};
+    for (cudaEvent_t e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+  for (BatchTables &b : s->batch) {
+    cudaFreeHost(b.h_jobs); cudaFree(b.d_jobs); cudaFreeHost(b.h_glyphs); cudaFree(b.d_glyphs);
+    if (b.done) cudaEventDestroy(b.done);
+  }
+  for (auto &kv : s->filters) cudaFree(kv.second.blob);
+  cudaFree(s->d_atlas);
+  if (s->st_in) cudaStreamDestroy(s->st_in);
+  if (s->st_k) cudaStreamDestroy(s->st_k);
+  if (s->st_out) cudaStreamDestroy(s->st_out);
+  cudaGetLastError();
+  delete s;
+}
+
+void *nes_gpu_session_stream(nes_gpu_session *s) { return s ? (void *)s->st_k : nullptr; }
+uint64_t nes_gpu_session_launches(nes_gpu_session *s) { return s ? s->launches : 0; }
+
+int nes_gpu_host_alloc(size_t bytes, void **out) {
+  if (!out || bytes == 0) return NES_ERR_INVALID_ARG;
+  if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); *out = nullptr; return NES_ERR_CUDA; }
+  return NES_OK;
+}
+void nes_gpu_host_free(void *p) {
+  if (p) { cudaFreeHost(p); cudaGetLastError(); }
+}
+
+int nes_gpu_device_alloc(nes_gpu_session *s, size_t bytes, void **out) {
+  if (!s || !out || bytes == 0) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  CU_TRY(s, cudaSetDevice(s->cfg.device));
+  CU_TRY(s, cudaMalloc(out, bytes));
+  return NES_OK;
+}
+void nes_gpu_device_free(nes_gpu_session *s, void *p) {
+  if (!s || !p) return;
+  std::lock_guard<std::mutex> lk(s->mu);
+  cudaSetDevice(s->cfg.device);
+  cudaFree(p);
+  cudaGetLastError();
+}
+int nes_gpu_memcpy_h2d(nes_gpu_session *s, void *dst, const void *src, size_t bytes) {
+  if (!s || !dst || !src) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  CU_TRY(s, cudaSetDevice(s->cfg.device));
+  CU_TRY(s, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return NES_OK;
+}
+int nes_gpu_memcpy_d2h(nes_gpu_session *s, void *dst, const void *src, size_t bytes) {
+  if (!s || !dst || !src) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  CU_TRY(s, cudaSetDevice(s->cfg.device));
+  CU_TRY(s, cudaStreamSynchronize(s->st_k));
+  CU_TRY(s, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return NES_OK;
+}
+
+// ---- atlas ------------------------------------------------------------------
+static int upload_atlas(nes_gpu_session *s) {
+  CU_TRY(s, cudaSetDevice(s->cfg.device));
+  CU_TRY(s, cudaStreamSynchronize(s->st_k));
+  if (s->d_atlas) { CU_TRY(s, cudaFree(s->d_atlas)); s->d_atlas = nullptr; }
+  const size_t n = std::max<size_t>(s->atlas.coverage.size(), 16);
+  CU_TRY(s, cudaMalloc((void **)&s->d_atlas, n));
+  if (!s->atlas.coverage.empty())
+    CU_TRY(s, cudaMemcpy(s->d_atlas, s->atlas.coverage.data(), s->atlas.coverage.size(), cudaMemcpyHostToDevice));
+  s->atlas.valid = true;
+  return NES_OK;
+}
+
+int nes_gpu_atlas_set(nes_gpu_session *s, const nes_glyph *glyphs, int n) {
+  if (!s || (n > 0 && !glyphs) || n < 0) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  HostAtlas a;
+  for (int i = 0; i < n; i++) {
+    const nes_glyph &g = glyphs[i];
+    if (g.code < 0 || g.code > 255 || g.width < 0 || g.rows < 0) return NES_ERR_INVALID_ARG;
+    if (g.width > 0 && g.rows > 0 && (!g.coverage || g.pitch < g.width)) return NES_ERR_INVALID_ARG;
+    HostGlyph &h = a.glyph[g.code];
+    h.width = g.width; h.rows = g.rows; h.left = g.left; h.top = g.top; h.advance = g.advance;
+    h.pitch = g.width;
+    h.offset = (uint32_t)a.coverage.size();
+    for (int q = 0; q < g.rows; q++) a.coverage.insert(a.coverage.end(), g.coverage + (size_t)q * g.pitch, g.coverage + (size_t)q * g.pitch + g.width);
+  }
+  s->atlas = std::move(a);
+  return upload_atlas(s);
+}
+
+int nes_gpu_atlas_load_font(nes_gpu_session *s, const char *freetype_so, const char *font_path) {
+  if (!s || !font_path) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  HostAtlas a;
+  const int st = rasterise_font(freetype_so, font_path, &a, &s->err);
+  if (st != NES_OK) return st;
+  s->atlas = std::move(a);
+  return upload_atlas(s);
+}
+
+int nes_gpu_text_layout(nes_gpu_session *s, int frame_w, int frame_h, const nes_text_run *run, nes_placed_glyph *out, int cap) {
+  if (!s || !run || (cap > 0 && !out)) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (!s->atlas.valid) return NES_ERR_NO_ATLAS;
+  std::vector<nes_placed_glyph> v;
+  layout_run(s->atlas, frame_w, frame_h, *run, &v);
+  for (int i = 0; i < (int)v.size() && i < cap; i++) out[i] = v[i];
+  return (int)v.size();
+}
+
+int nes_gpu_filter_table(int src, int dst, int one, int16_t *coef, int coef_cap, int32_t *pos, int pos_cap) {
+  FilterTable t;
+  const int size = build_filter(src, dst, one, &t);
+  if (size < 0) return NES_ERR_INVALID_ARG;
+  if (coef) {
+    if ((size_t)coef_cap < t.coef.size()) return NES_ERR_TOO_LARGE;
+    std::memcpy(coef, t.coef.data(), t.coef.size() * 2);
+  }
+  if (pos) {
+    if ((size_t)pos_cap < t.pos.size()) return NES_ERR_TOO_LARGE;
+    std::memcpy(pos, t.pos.data(), t.pos.size() * 4);
+  }
+  return size;
+}
+
+// ---- the hot path -------------------------------------------------------------
+int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_run *runs, int n_runs,
+                   const nes_frame_out *out, uint64_t *ticket) {
+  if (!s || !in || !out || !ticket) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (s->sticky) return s->sticky;
+  int bpp, base, a_off; bool bgr;
+  if (fmt_info(in->pix_fmt, &bpp, &base, &a_off, &bgr)) return NES_ERR_INVALID_ARG;
+  int st = validate(s, in, out, bpp);
+  if (st) return st;
+  CU_TRY(s, cudaSetDevice(s->cfg.device));
+
+  Slot &sl = s->slots[s->next_ticket % s->slots.size()];
+  if (sl.busy) return NES_ERR_BUSY;
+  const int W = in->width, H = in->height, Wd = out->width, Hd = out->height;
+  const bool want_depth = out->depth[0] != nullptr;
+  const bool need_depth_in = want_depth || in->n_sources > 1;
+  const bool resize = (W != Wd) || (H != Hd);
+
+  // text -> placed glyphs (pinned)
+  const int n_gl = place_text(s, W, H, runs, n_runs, sl.h_glyphs, s->cfg.max_glyphs);
+  if (n_gl < 0) return n_gl;
+
+  DevJob *jb = sl.h_job;
+  job_common(jb, in, out, bpp, base, a_off, bgr);
+  jb->glyphs = sl.d_glyphs;
+  jb->atlas = s->d_atlas;
+  jb->n_glyphs = n_gl;
+
+  sl.staged.clear();
+  CU_TRY(s, cudaEventRecord(sl.e_start, s->st_in));
+
+  // ---- inputs ----
+  if (in->mem == NES_MEM_DEVICE) {
+    for (int k = 0; k < in->n_sources; k++) {
+      jb->src[k].rgb = in->src[k].rgb;
+      jb->src[k].rgb_stride = in->src[k].rgb_stride ? in->src[k].rgb_stride : W * bpp;
+      jb->src[k].depth = need_depth_in ? in->src[k].depth : nullptr;
+      jb->src[k].depth_stride = in->src[k].depth_stride ? in->src[k].depth_stride : W;
+    }
+  } else {
+    const size_t rs_dev = align_up((size_t)W * bpp, 16), ds_dev = align_up((size_t)W, 16);
+    const size_t rgb_sz = align_up(rs_dev * H, 256), dep_sz = need_depth_in ? align_up(ds_dev * H, 256) : 0;
+    const size_t need = (rgb_sz + dep_sz) * in->n_sources;
+    if ((st = ensure_dev(s, &sl.d_in, &sl.d_in_cap, need))) return st;
+    bool all_pinned = true;
+    for (int k = 0; k < in->n_sources; k++) {
+      all_pinned = all_pinned && is_pinned(in->src[k].rgb);
+      if (need_depth_in) all_pinned = all_pinned && is_pinned(in->src[k].depth);
+    }
+    if (!all_pinned && (st = ensure_host(s, &sl.h_in, &sl.h_in_cap, need))) return st;
+    for (int k = 0; k < in->n_sources; k++) {
+      const nes_source &sr = in->src[k];
+      const size_t o_rgb = (rgb_sz + dep_sz) * k, o_dep = o_rgb + rgb_sz;
+      const size_t rs = sr.rgb_stride ? sr.rgb_stride : (size_t)W * bpp;
+      const size_t ds = sr.depth_stride ? sr.depth_stride : (size_t)W;
+      jb->src[k].rgb = sl.d_in + o_rgb;
+      jb->src[k].rgb_stride = (int)rs_dev;
+      jb->src[k].depth = need_depth_in ? sl.d_in + o_dep : nullptr;
+      jb->src[k].depth_stride = (int)ds_dev;
+      if (all_pinned) {
+        if (rs == rs_dev) CU_TRY(s, cudaMemcpyAsync(sl.d_in + o_rgb, sr.rgb, rs * (H - 1) + (size_t)W * bpp, cudaMemcpyHostToDevice, s->st_in));
+        else CU_TRY(s, cudaMemcpy2DAsync(sl.d_in + o_rgb, rs_dev, sr.rgb, rs, (size_t)W * bpp, H, cudaMemcpyHostToDevice, s->st_in));
+        if (need_depth_in) {
+          if (ds == ds_dev) CU_TRY(s, cudaMemcpyAsync(sl.d_in + o_dep, sr.depth, ds * (H - 1) + W, cudaMemcpyHostToDevice, s->st_in));
+          else CU_TRY(s, cudaMemcpy2DAsync(sl.d_in + o_dep, ds_dev, sr.depth, ds, W, H, cudaMemcpyHostToDevice, s->st_in));
+        }
+      } else {
+        // the one host memcpy of the payload: caller memory -> pinned staging
+        if (rs == rs_dev) std::memcpy(sl.h_in + o_rgb, sr.rgb, rs * (H - 1) + (size_t)W * bpp);
+        else for (int y = 0; y < H; y++) std::memcpy(sl.h_in + o_rgb + y * rs_dev, sr.rgb + y * rs, (size_t)W * bpp);
+        if (need_depth_in) {
+          if (ds == ds_dev) std::memcpy(sl.h_in + o_dep, sr.depth, ds * (H - 1) + W);
+          else for (int y = 0; y < H; y++) std::memcpy(sl.h_in + o_dep + y * ds_dev, sr.depth + y * ds, W);
+        }
+      }
+    }
+    if (!all_pinned) CU_TRY(s, cudaMemcpyAsync(sl.d_in, sl.h_in, need, cudaMemcpyHostToDevice, s->st_in));
+  }
+
+  // ---- outputs ----
+  PlaneLayout ps{}, pd{};
+  if (out->mem == NES_MEM_DEVICE) {
+    jb->sy = out->scene[0]; jb->su = out->scene[1]; jb->sv = out->scene[2];
+    if (want_depth) { jb->dy = out->depth[0]; jb->du = out->depth[1]; jb->dv = out->depth[2]; }
+  } else {
+    ps = yuv_layout(out->scene_linesize, Hd, 0);
+    pd = yuv_layout(out->depth_linesize, Hd, align_up(ps.total, 256));
+    const size_t need = pd.off[0] + (want_depth ? pd.total : 0);
+    if ((st = ensure_dev(s, &sl.d_out, &sl.d_out_cap, need))) return st;
+    jb->sy = sl.d_out + ps.off[0]; jb->su = sl.d_out + ps.off[1]; jb->sv = sl.d_out + ps.off[2];
+    if (want_depth) { jb->dy = sl.d_out + pd.off[0]; jb->du = sl.d_out + pd.off[1]; jb->dv = sl.d_out + pd.off[2]; }
+  }
+  jb->sys = out->scene_linesize[0]; jb->sus = out->scene_linesize[1]; jb->svs = out->scene_linesize[2];
+  jb->dys = out->depth_linesize[0]; jb->dus = out->depth_linesize[1]; jb->dvs = out->depth_linesize[2];
+
+  if (resize) {
+    FilterSet *fs;
+    if ((st = get_filters(s, W, H, Wd, Hd, &fs))) return st;
+    if (fs->smem_need[bpp - 3] > 200 * 1024) return NES_ERR_TOO_LARGE;  // scale ratio beyond what one tile can stage
+    jb->hl = fs->hl; jb->hc = fs->hc; jb->vl = fs->vl; jb->vc = fs->vc;
+    jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need[bpp - 3];
+    if (in->n_sources > 1) {
+      const size_t need = (size_t)W * H * (bpp + 1);
+      if ((st = ensure_dev(s, &sl.d_scratch, &sl.d_scratch_cap, need))) return st;
+      jb->scratch_rgb = sl.d_scratch;
+      jb->scratch_depth = sl.d_scratch + (size_t)W * H * bpp;
+    }
+  }
+  job_tiles(jb, 0);
+  job_alignment(jb);
+
+  if (n_gl > 0) CU_TRY(s, cudaMemcpyAsync(sl.d_glyphs, sl.h_glyphs, (size_t)n_gl * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
+  CU_TRY(s, cudaMemcpyAsync(sl.d_job, sl.h_job, sizeof(DevJob), cudaMemcpyHostToDevice, s->st_in));
+  CU_TRY(s, cudaEventRecord(sl.e_in, s->st_in));
+
+  // ---- kernels ----
+  CU_TRY(s, cudaStreamWaitEvent(s->st_k, sl.e_in, 0));
+  CU_TRY(s, cudaEventRecord(sl.e_k0, s->st_k));
+  sl.n_launches = run_kernels(s, sl.d_job, sl.h_job, 1, s->st_k);
+  CU_TRY(s, cudaGetLastError());
+  CU_TRY(s, cudaEventRecord(sl.e_k1, s->st_k));
+
+  // ---- download ----
+  CU_TRY(s, cudaStreamWaitEvent(s->st_out, sl.e_k1, 0));
+  if (out->mem == NES_MEM_HOST) {
+    const size_t total = pd.off[0] + (want_depth ? pd.total : 0);
+    const int nimg = want_depth ? 2 : 1;
+    bool direct = true;
+    for (int im = 0; im < nimg; im++) {
+      uint8_t *const *pl = im ? out->depth : out->scene;
+      const PlaneLayout &L = im ? pd : ps;
+      const bool contiguous = pl[1] == pl[0] + L.bytes[0] && pl[2] == pl[1] + L.bytes[1];
+      direct = direct && contiguous && is_pinned(pl[0]);
+    }
+    if (direct) {
+      CU_TRY(s, cudaMemcpyAsync(out->scene[0], sl.d_out + ps.off[0], ps.total, cudaMemcpyDeviceToHost, s->st_out));
+      if (want_depth) CU_TRY(s, cudaMemcpyAsync(out->depth[0], sl.d_out + pd.off[0], pd.total, cudaMemcpyDeviceToHost, s->st_out));
+    } else {
+      if ((st = ensure_host(s, &sl.h_out, &sl.h_out_cap, total))) return st;
+      CU_TRY(s, cudaMemcpyAsync(sl.h_out, sl.d_out, total, cudaMemcpyDeviceToHost, s->st_out));
+      for (int im = 0; im < nimg; im++) {
+        uint8_t *const *pl = im ? out->depth : out->scene;
+        const PlaneLayout &L = im ? pd : ps;
+        for (int p = 0; p < 3; p++) sl.staged.push_back(StagedCopy{pl[p], sl.h_out + L.off[p], L.bytes[p]});
+      }
+    }
+  }
+  CU_TRY(s, cudaEventRecord(sl.e_out, s->st_out));
+
+  sl.busy = true;
+  sl.ticket = s->next_ticket++;
+  *ticket = sl.ticket;
+  return NES_OK;
+}
+
+int nes_gpu_wait(nes_gpu_session *s, uint64_t ticket) {
+  if (!s) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  Slot *sl = nullptr;
+  for (Slot &c : s->slots)
+    if (c.busy && c.ticket == ticket) sl = &c;
+  if (!sl) return NES_ERR_BAD_TICKET;
+  CU_TRY(s, cudaSetDevice(s->cfg.device));
+  CU_TRY(s, cudaEventSynchronize(sl->e_out));
+  for (const StagedCopy &c : sl->staged) std::memcpy(c.dst, c.src, c.bytes);
+  sl->staged.clear();
+  float h2d = 0, k = 0, d2h = 0, tot = 0;
+  cudaEventElapsedTime(&h2d, sl->e_start, sl->e_in);
+  cudaEventElapsedTime(&k, sl->e_k0, sl->e_k1);
+  cudaEventElapsedTime(&d2h, sl->e_k1, sl->e_out);
+  cudaEventElapsedTime(&tot, sl->e_start, sl->e_out);
+  s->last.h2d_us = h2d * 1000.f; s->last.kernels_us = k * 1000.f; s->last.d2h_us = d2h * 1000.f; s->last.total_us = tot * 1000.f;
+  s->last.n_launches = sl->n_launches;
+  sl->busy = false;
+  CU_TRY(s, cudaGetLastError());
+  return NES_OK;
+}
+
+int nes_gpu_convert(nes_gpu_session *s, const nes_frame_in *in, const nes_text_run *runs, int n_runs, const nes_frame_out *out) {
+  uint64_t t;
+  const int st = nes_gpu_submit(s, in, runs, n_runs, out, &t);
+  if (st) return st;
+  return nes_gpu_wait(s, t);
+}
+
+int nes_gpu_last_timing(nes_gpu_session *s, nes_timing *t) {
+  if (!s || !t) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  *t = s->last;
+  return NES_OK;
+}
+
+int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_frame_in *in, const nes_text_run *const *runs,
+                                 const int *n_runs, const nes_frame_out *out, int sync) {
+  if (!s || !in || !out || n_frames < 1 || n_frames > kMaxBatch) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (s->sticky) return s->sticky;
+  CU_TRY(s, cudaSetDevice(s->cfg.device));
+  BatchTables &bt = s->batch[s->batch_seq++ % kBatchRing];
+  const size_t gl_bytes = (size_t)s->cfg.max_glyphs * sizeof(DevPlaced);
+  if (!bt.h_jobs) {
+    CU_TRY(s, cudaHostAlloc((void **)&bt.h_jobs, sizeof(DevJob) * kMaxBatch, cudaHostAllocDefault));
+    CU_TRY(s, cudaMalloc((void **)&bt.d_jobs, sizeof(DevJob) * kMaxBatch));
+    CU_TRY(s, cudaHostAlloc((void **)&bt.h_glyphs, gl_bytes, cudaHostAllocDefault));
+    CU_TRY(s, cudaMalloc((void **)&bt.d_glyphs, gl_bytes));
+    CU_TRY(s, cudaEventCreateWithFlags(&bt.done, cudaEventDisableTiming));
+  }
+  if (bt.used) CU_TRY(s, cudaEventSynchronize(bt.done));  // tables still referenced by an older batch
+  int tile_base = 0, gl_used = 0;
+  for (int f = 0; f < n_frames; f++) {
+    int bpp, base, a_off; bool bgr;
+    if (fmt_info(in[f].pix_fmt, &bpp, &base, &a_off, &bgr)) return NES_ERR_INVALID_ARG;
+    if (in[f].mem != NES_MEM_DEVICE || out[f].mem != NES_MEM_DEVICE) return NES_ERR_INVALID_ARG;
+    int st = validate(s, &in[f], &out[f], bpp);
+    if (st) return st;
+    const int W = in[f].width, H = in[f].height;
+    if (W != out[f].width || H != out[f].height) {
+      if (in[f].n_sources > 1) return NES_ERR_INVALID_ARG;  // composite+resize needs a slot's scratch frame: use submit
+    }
+    const bool want_depth = out[f].depth[0] != nullptr;
+    DevJob *jb = &bt.h_jobs[f];
+    job_common(jb, &in[f], &out[f], bpp, base, a_off, bgr);
+    const int n_gl = place_text(s, W, H, runs ? runs[f] : nullptr, (runs && n_runs) ? n_runs[f] : 0, bt.h_glyphs + gl_used, s->cfg.max_glyphs - gl_used);
+    if (n_gl < 0) return n_gl;
+    jb->glyphs = bt.d_glyphs + gl_used;
+    jb->atlas = s->d_atlas;
+    jb->n_glyphs = n_gl;
+    gl_used += n_gl;
+    for (int k = 0; k < in[f].n_sources; k++) {
+      jb->src[k].rgb = in[f].src[k].rgb;
+      jb->src[k].rgb_stride = in[f].src[k].rgb_stride ? in[f].src[k].rgb_stride : W * bpp;
+      jb->src[k].depth = (want_depth || in[f].n_sources > 1) ? in[f].src[k].depth : nullptr;
+      jb->src[k].depth_stride = in[f].src[k].depth_stride ? in[f].src[k].depth_stride : W;
+    }
+    jb->sy = out[f].scene[0]; jb->su = out[f].scene[1]; jb->sv = out[f].scene[2];
+    jb->sys = out[f].scene_linesize[0]; jb->sus = out[f].scene_linesize[1]; jb->svs = out[f].scene_linesize[2];
+    if (want_depth) {
+      jb->dy = out[f].depth[0]; jb->du = out[f].depth[1]; jb->dv = out[f].depth[2];
+      jb->dys = out[f].depth_linesize[0]; jb->dus = out[f].depth_linesize[1]; jb->dvs = out[f].depth_linesize[2];
+    }
+    if (W != out[f].width || H != out[f].height) {
+      FilterSet *fs;
+      if ((st = get_filters(s, W, H, out[f].width, out[f].height, &fs))) return st;
+      if (fs->smem_need[bpp - 3] > 200 * 1024) return NES_ERR_TOO_LARGE;
+      jb->hl = fs->hl; jb->hc = fs->hc; jb->vl = fs->vl; jb->vc = fs->vc;
+      jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need[bpp - 3];
+    }
+    job_tiles(jb, tile_base);
+    tile_base += jb->tiles_x * jb->tiles_y;
+    job_alignment(jb);
+  }
+  if (gl_used > 0) CU_TRY(s, cudaMemcpyAsync(bt.d_glyphs, bt.h_glyphs, (size_t)gl_used * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_k));
+  CU_TRY(s, cudaMemcpyAsync(bt.d_jobs, bt.h_jobs, sizeof(DevJob) * n_frames, cudaMemcpyHostToDevice, s->st_k));
+  run_kernels(s, bt.d_jobs, bt.h_jobs, n_frames, s->st_k);
+  CU_TRY(s, cudaGetLastError());
+  CU_TRY(s, cudaEventRecord(bt.done, s->st_k));
+  bt.used = true;
+  if (sync) CU_TRY(s, cudaStreamSynchronize(s->st_k));
+  return NES_OK;
+}
+
+}  // extern "C"
