@@ -210,6 +210,12 @@ NES_API int nes_gpu_atlas_set(nes_gpu_session *s, const nes_glyph *glyphs, int n
  * 0..255 and call nes_gpu_atlas_set. */
 NES_API int nes_gpu_atlas_load_font(nes_gpu_session *s, const char *freetype_so, const char *font_path);
 
+/* Host-only half of the above (no session, no GPU): fills glyphs[0..255]; their coverage
+ * pointers point into `coverage` (pitch == width).  Returns 0, NES_ERR_FREETYPE, or
+ * NES_ERR_TOO_LARGE when coverage_cap is too small (*coverage_used = bytes needed). */
+NES_API int nes_font_rasterise(const char *freetype_so, const char *font_path, nes_glyph *glyphs,
+                               uint8_t *coverage, uint64_t coverage_cap, uint64_t *coverage_used);
+
 /* ---- the hot path -------------------------------------------------------- */
 /* Asynchronous: stage + enqueue H2D, kernels, D2H for one frame.  `runs` are the
  * render_string_to_frame calls to apply to the scene BEFORE conversion, in call

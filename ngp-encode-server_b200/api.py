@@ -91,7 +91,7 @@ ABI_SYMBOLS = [
     "nes_gpu_session_create", "nes_gpu_session_destroy", "nes_gpu_session_stream", "nes_gpu_session_launches",
     "nes_gpu_host_alloc", "nes_gpu_host_free", "nes_gpu_device_alloc", "nes_gpu_device_free",
     "nes_gpu_memcpy_h2d", "nes_gpu_memcpy_d2h", "nes_gpu_atlas_set", "nes_gpu_atlas_load_font",
-    "nes_gpu_submit", "nes_gpu_wait", "nes_gpu_convert", "nes_gpu_convert_batch_device", "nes_gpu_last_timing",
+    "nes_font_rasterise", "nes_gpu_submit", "nes_gpu_wait", "nes_gpu_convert", "nes_gpu_convert_batch_device", "nes_gpu_last_timing",
     "nes_gpu_filter_table", "nes_gpu_text_layout", "nes_unpack_rendered_frame",
 ]
 
@@ -129,6 +129,7 @@ def lib() -> C.CDLL:
     L.nes_gpu_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
     L.nes_gpu_atlas_set.argtypes = [vp, C.POINTER(nes_glyph), i32]
     L.nes_gpu_atlas_load_font.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.nes_font_rasterise.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(nes_glyph), vp, u64, C.POINTER(u64)]
     L.nes_gpu_submit.argtypes = [vp, C.POINTER(nes_frame_in), C.POINTER(nes_text_run), i32, C.POINTER(nes_frame_out), C.POINTER(u64)]
     L.nes_gpu_wait.argtypes = [vp, u64]
     L.nes_gpu_convert.argtypes = [vp, C.POINTER(nes_frame_in), C.POINTER(nes_text_run), i32, C.POINTER(nes_frame_out)]
@@ -191,6 +192,27 @@ def unpack_rendered_frame(buf, prefix: bool = True) -> dict:
         "matrix": [u.matrix[i] for i in range(u.n_matrix)], "frame": (u.frame_off, u.frame_len), "depth": (u.depth_off, u.depth_len),
         "consumed": u.consumed,
     }
+
+
+def font_rasterise(font_path: str, freetype_so: str | None = None):
+    """Rasterise codes 0..255 like RenderTextContext does per character (render_text.cc:12-32,88)
+    -> (metrics int32 [256,5] = width, rows, left, top, advance; bitmaps list of uint8 arrays)."""
+    ft = freetype_so or find_freetype()
+    arr = (nes_glyph * 256)()
+    cov = np.zeros(1 << 20, np.uint8)
+    used = C.c_uint64()
+    r = lib().nes_font_rasterise(ft.encode() if ft else None, font_path.encode(), arr, cov.ctypes.data, cov.size, C.byref(used))
+    if r:
+        raise NesGpuError(r, "nes_font_rasterise", strerror(r))
+    metrics = np.zeros((256, 5), np.int32)
+    bitmaps = []
+    for b in range(256):
+        g = arr[b]
+        metrics[b] = (g.width, g.rows, g.left, g.top, g.advance)
+        n = g.width * g.rows
+        off = (g.coverage - cov.ctypes.data) if g.coverage else 0
+        bitmaps.append(cov[off:off + n].copy())
+    return metrics, bitmaps
 
 
 def format_camera_matrix(matrix) -> bytes:

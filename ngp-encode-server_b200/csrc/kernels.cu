@@ -180,7 +180,7 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs) {
 
   int tile;
   const DevJob *jp = find_job(jobs, n_jobs, blockIdx.x, &tile);
-  if (jp->bpp != BPP || jp->W != jp->Wd || jp->H != jp->Hd) return;  // other template / resize job
+  if (jp->bpp != BPP || jp->general) return;  // other template / general-path job
   const DevJob &jb = *jp;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -380,7 +380,7 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs) {
 __global__ void __launch_bounds__(256) k_composite(const DevJob *__restrict__ jobs, int n_jobs) {
   for (int j = 0; j < n_jobs; j++) {
     const DevJob &jb = jobs[j];
-    if (jb.n_src <= 1 || !jb.scratch_rgb) continue;
+    if (jb.n_src <= 1 || !jb.scratch_rgb) continue;  // only general-path composites get a scratch frame
     const int W = jb.W, H = jb.H;
     const size_t n = (size_t)W * H;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256) k_resize_tiles(const DevJob *__restrict__
   extern __shared__ __align__(16) uint8_t smem[];
   int tile;
   const DevJob *jp = find_job(jobs, n_jobs, blockIdx.x, &tile);
-  if (jp->W == jp->Wd && jp->H == jp->Hd) return;
+  if (!jp->general) return;
   const DevJob &jb = *jp;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int tx = tile % jb.tiles_x, ty = tile / jb.tiles_x;
@@ -621,7 +621,7 @@ int launch_frame_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jo
   for (int j = 0; j < n_jobs; j++) {
     const DevJob &jb = jobs_host[j];
     total = jb.tile_base + jb.tiles_x * jb.tiles_y;
-    if (jb.W == jb.Wd && jb.H == jb.Hd) (jb.bpp == 3 ? any3 : any4) = true;
+    if (!jb.general) (jb.bpp == 3 ? any3 : any4) = true;
   }
   if (total == 0) return 0;
   int launches = 0;
@@ -651,7 +651,7 @@ int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_j
   for (int j = 0; j < n_jobs; j++) {
     const DevJob &jb = jobs_host[j];
     total = jb.tile_base + jb.tiles_x * jb.tiles_y;
-    if (jb.W != jb.Wd || jb.H != jb.Hd) { any = true; smem = jb.rs_smem > smem ? jb.rs_smem : smem; }
+    if (jb.general) { any = true; smem = jb.rs_smem > smem ? jb.rs_smem : smem; }
   }
   if (!any || total == 0) return 0;
   smem = (smem + 1023) & ~1023;

@@ -22,6 +22,9 @@ constexpr int HIT_CAP = 512;  // glyph rect tests per overlay chunk
 // Resize tile geometry (k_resize_tiles): destination pixels per CTA.
 constexpr int RS_TILE_W = 64;
 constexpr int RS_TILE_H = 16;
+// Below this source height libswscale's vertical chroma filter has fewer than 8 taps
+// (initFilter clamps the size to srcH-2), so the fused same-size kernel does not apply.
+constexpr int MIN_FUSED_H = 12;
 
 struct DevSource {
   const uint8_t *rgb;
@@ -68,7 +71,7 @@ struct DevJob {
   int32_t half;  // chroma horizontally pair-summed before the H pass
   int32_t csW;   // chroma source width fed to the H pass
   int32_t rs_smem;  // shared memory the resize kernel needs for this job's worst tile (host use)
-  int32_t pad0;
+  int32_t general;  // 1: k_resize_tiles (any size change, or H < 12 where libswscale's chroma filter is truncated)
   // composite scratch (resize of a composite goes through a scratch frame)
   uint8_t *scratch_rgb;
   uint8_t *scratch_depth;

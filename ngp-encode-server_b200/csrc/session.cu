@@ -274,7 +274,7 @@ void job_common(DevJob *jb, const nes_frame_in *in, const nes_frame_out *out, in
 }
 
 void job_tiles(DevJob *jb, int tile_base) {
-  if (jb->W == jb->Wd && jb->H == jb->Hd) {
+  if (!jb->general) {
     jb->tiles_x = (jb->W + TILE_W - 1) / TILE_W;
     jb->tiles_y = (jb->H + TILE_H - 1) / TILE_H;
   } else {
@@ -504,6 +504,23 @@ int nes_gpu_atlas_load_font(nes_gpu_session *s, const char *freetype_so, const c
   return upload_atlas(s);
 }
 
+int nes_font_rasterise(const char *freetype_so, const char *font_path, nes_glyph *glyphs, uint8_t *coverage,
+                       uint64_t coverage_cap, uint64_t *coverage_used) {
+  if (!font_path || !glyphs) return NES_ERR_INVALID_ARG;
+  HostAtlas a;
+  std::string err;
+  const int st = rasterise_font(freetype_so, font_path, &a, &err);
+  if (st != NES_OK) return st;
+  if (coverage_used) *coverage_used = a.coverage.size();
+  if (a.coverage.size() > coverage_cap || (!coverage && !a.coverage.empty())) return NES_ERR_TOO_LARGE;
+  if (!a.coverage.empty()) std::memcpy(coverage, a.coverage.data(), a.coverage.size());
+  for (int c = 0; c < 256; c++) {
+    const HostGlyph &g = a.glyph[c];
+    glyphs[c] = nes_glyph{c, g.width, g.rows, g.left, g.top, g.advance, g.width, 0, (g.width > 0 && g.rows > 0) ? coverage + g.offset : nullptr};
+  }
+  return NES_OK;
+}
+
 int nes_gpu_text_layout(nes_gpu_session *s, int frame_w, int frame_h, const nes_text_run *run, nes_placed_glyph *out, int cap) {
   if (!s || !run || (cap > 0 && !out)) return NES_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(s->mu);
@@ -546,7 +563,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   const int W = in->width, H = in->height, Wd = out->width, Hd = out->height;
   const bool want_depth = out->depth[0] != nullptr;
   const bool need_depth_in = want_depth || in->n_sources > 1;
-  const bool resize = (W != Wd) || (H != Hd);
+  const bool resize = (W != Wd) || (H != Hd) || H < MIN_FUSED_H;
 
   // text -> placed glyphs (pinned)
   const int n_gl = place_text(s, W, H, runs, n_runs, sl.h_glyphs, s->cfg.max_glyphs);
@@ -625,6 +642,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   jb->sys = out->scene_linesize[0]; jb->sus = out->scene_linesize[1]; jb->svs = out->scene_linesize[2];
   jb->dys = out->depth_linesize[0]; jb->dus = out->depth_linesize[1]; jb->dvs = out->depth_linesize[2];
 
+  jb->general = resize;
   if (resize) {
     FilterSet *fs;
     if ((st = get_filters(s, W, H, Wd, Hd, &fs))) return st;
@@ -746,9 +764,8 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
     int st = validate(s, &in[f], &out[f], bpp);
     if (st) return st;
     const int W = in[f].width, H = in[f].height;
-    if (W != out[f].width || H != out[f].height) {
-      if (in[f].n_sources > 1) return NES_ERR_INVALID_ARG;  // composite+resize needs a slot's scratch frame: use submit
-    }
+    const bool general = W != out[f].width || H != out[f].height || H < MIN_FUSED_H;
+    if (general && in[f].n_sources > 1) return NES_ERR_INVALID_ARG;  // composite+resize needs a slot's scratch frame: use submit
     const bool want_depth = out[f].depth[0] != nullptr;
     DevJob *jb = &bt.h_jobs[f];
     job_common(jb, &in[f], &out[f], bpp, base, a_off, bgr);
@@ -770,7 +787,8 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
       jb->dy = out[f].depth[0]; jb->du = out[f].depth[1]; jb->dv = out[f].depth[2];
       jb->dys = out[f].depth_linesize[0]; jb->dus = out[f].depth_linesize[1]; jb->dvs = out[f].depth_linesize[2];
     }
-    if (W != out[f].width || H != out[f].height) {
+    jb->general = general;
+    if (general) {
       FilterSet *fs;
       if ((st = get_filters(s, W, H, out[f].width, out[f].height, &fs))) return st;
       if (fs->smem_need[bpp - 3] > 200 * 1024) return NES_ERR_TOO_LARGE;

@@ -7,6 +7,7 @@
 // render_text.cc:12-32) into an atlas that lives in device memory; per frame the host
 // only runs the pen arithmetic of render_text.cc:47-110 and emits a list of placed
 // glyph rectangles that the kernels stamp inside their shared-memory tiles.
+#include <dirent.h>
 #include <dlfcn.h>
 
 #include <cstdint>
@@ -98,17 +99,38 @@ struct FtFace {
 };
 constexpr int kFtLoadRender = 1 << 2;
 constexpr unsigned char kFtPixelModeGray = 2;
+
+// A wheel-bundled libfreetype (pillow.libs/) names its dependencies by hashed sonames
+// that live next to it and carries no RUNPATH: load those siblings first.
+void preload_siblings(const char *so_path) {
+  const std::string path(so_path);
+  const size_t slash = path.rfind('/');
+  if (slash == std::string::npos) return;
+  const std::string dir = path.substr(0, slash);
+  DIR *d = opendir(dir.c_str());
+  if (!d) return;
+  std::vector<std::string> names;
+  while (dirent *e = readdir(d)) names.push_back(e->d_name);
+  closedir(d);
+  for (const char *prefix : {"libbrotlicommon", "libbrotlidec", "libpng16"})
+    for (const std::string &n : names)
+      if (n.compare(0, strlen(prefix), prefix) == 0) dlopen((dir + "/" + n).c_str(), RTLD_NOW | RTLD_GLOBAL);
+  dlerror();
+}
 }  // namespace
 
 int rasterise_font(const char *freetype_so, const char *font_path, HostAtlas *atlas, std::string *err) {
   const char *candidates[] = {freetype_so, getenv("NES_FREETYPE_SO"), "libfreetype.so.6", "libfreetype.so"};
   void *h = nullptr;
+  std::string why = "not found";
   for (const char *c : candidates) {
     if (!c || !*c) continue;
-    h = dlopen(c, RTLD_NOW | RTLD_LOCAL);
+    preload_siblings(c);
+    h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
     if (h) break;
+    if (const char *e = dlerror()) why = e;
   }
-  if (!h) { *err = std::string("cannot dlopen FreeType: ") + (dlerror() ? dlerror() : "not found"); return NES_ERR_FREETYPE; }
+  if (!h) { *err = "cannot dlopen FreeType: " + why; return NES_ERR_FREETYPE; }
   auto init = (int (*)(void **))dlsym(h, "FT_Init_FreeType");
   auto new_face = (int (*)(void *, const char *, long, FtFace **))dlsym(h, "FT_New_Face");
   auto set_size = (int (*)(FtFace *, long, long, unsigned, unsigned))dlsym(h, "FT_Set_Char_Size");

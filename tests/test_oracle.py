@@ -203,3 +203,20 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cc", ".h", ".hpp", "Makefile")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt and "libnes_ref" not in txt, f
+
+
+def test_product_font_rasterise_matches_golden_glyphs(N, glyphs):
+    """The product's FreeType loader (csrc/text.cc) yields the same 256 glyphs as the golden table
+    (made with the oracle's shim over the same FreeType 2.14.3)."""
+    if N.find_freetype() is None:
+        pytest.skip("no FreeType binary in this image")
+    metrics, bitmaps = N.font_rasterise(FONT)
+    for b in range(256):
+        if glyphs.metrics[b][0] * glyphs.metrics[b][1] == 0:
+            assert bitmaps[b].size == 0 and metrics[b][4] == glyphs.metrics[b][4], b
+        else:
+            assert metrics[b].tolist() == glyphs.metrics[b].tolist(), b
+            assert np.array_equal(bitmaps[b], glyphs.bitmaps[b]), b
+    with pytest.raises(N.NesGpuError) as e:
+        N.font_rasterise("/nonexistent/font.ttf")
+    assert e.value.status == N.NES_ERR_FREETYPE
