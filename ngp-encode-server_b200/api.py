@@ -378,6 +378,30 @@ class Session:
         self._check(self.L.nes_gpu_convert_batch_device(self.h, n, a_in, a_runs, a_n, a_out, 1 if sync else 0), "nes_gpu_convert_batch_device")
         return (a_in, a_out, made)  # keep-alive for async callers
 
+    def prepare_batch(self, fins, runs_list, fouts):
+        """Build the ctypes argument arrays of convert_batch_device once (a streaming caller
+        re-submits the same descriptors every step)."""
+        n = len(fins)
+        a_in = (nes_frame_in * n)(*fins)
+        a_out = (nes_frame_out * n)(*fouts)
+        made = [self.make_runs(r) for r in runs_list] if runs_list else None
+        a_runs = (C.POINTER(nes_text_run) * n)(*[C.cast(m[0], C.POINTER(nes_text_run)) for m in made]) if made else None
+        a_n = (C.c_int * n)(*[m[1] for m in made]) if made else None
+        return (n, a_in, a_runs, a_n, a_out, made, runs_list)
+
+    def run_batch(self, prepared, sync: bool = False):
+        n, a_in, a_runs, a_n, a_out = prepared[:5]
+        r = self.L.nes_gpu_convert_batch_device(self.h, n, a_in, a_runs, a_n, a_out, 1 if sync else 0)
+        if r:
+            self._check(r, "nes_gpu_convert_batch_device")
+
+    def submit_prepared(self, fin, runs_made, fout) -> int:
+        t = C.c_uint64()
+        r = self.L.nes_gpu_submit(self.h, C.byref(fin), runs_made[0], runs_made[1], C.byref(fout), C.byref(t))
+        if r:
+            self._check(r, "nes_gpu_submit")
+        return t.value
+
     def last_timing(self) -> dict:
         t = nes_timing()
         self._check(self.L.nes_gpu_last_timing(self.h, C.byref(t)), "nes_gpu_last_timing")

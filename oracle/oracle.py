@@ -145,6 +145,8 @@ class Port:
         L.nes_oracle_gray_to_yuv420p.restype = C.c_int
         L.nes_oracle_render_string.argtypes = [C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.POINTER(_Glyph)]
         L.nes_oracle_render_string.restype = C.c_long
+        L.nes_oracle_render_string4.argtypes = [C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.POINTER(_Glyph), C.c_int]
+        L.nes_oracle_render_string4.restype = C.c_long
         L.nes_oracle_composite.argtypes = [C.c_int, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), C.c_int]
         L.nes_oracle_composite.restype = None
 
@@ -185,6 +187,12 @@ class Port:
         h, w = surface.shape[:2]
         assert surface.flags["C_CONTIGUOUS"] and surface.shape[2] == 3
         return self.L.nes_oracle_render_string(_u8p(surface), w, h, position, text, len(text), glyphs._arr)
+
+    def render_string4(self, surface: np.ndarray, position: int, text: bytes, glyphs: GlyphTable, fmt: str) -> int:
+        """surface: uint8 [H, W, 4] contiguous, colour bytes stamped white, alpha untouched."""
+        h, w = surface.shape[:2]
+        assert surface.flags["C_CONTIGUOUS"] and surface.shape[2] == 4
+        return self.L.nes_oracle_render_string4(_u8p(surface), w, h, position, text, len(text), glyphs._arr, 1 if PIXFMT[fmt][4] == 0 else 0)
 
     def composite(self, rgbs: list, depths: list, fmt: str):
         """rgbs[k]: uint8 [H,W,bpp]; depths[k]: uint8 [H,W] -> (rgb, depth)"""
@@ -244,6 +252,8 @@ class Ref:
         L.nes_ref_freetype_version.argtypes = [C.c_void_p]
         L.nes_ref_text_render.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_int]
         L.nes_ref_text_render.restype = C.c_long
+        L.nes_ref_text_render4.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.c_int]
+        L.nes_ref_text_render4.restype = C.c_long
         L.nes_ref_text_glyph.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.c_int]
         L.nes_ref_swscale_version.restype = C.c_uint
         self.have_sws = False
@@ -287,6 +297,11 @@ class Ref:
         h, w = surface.shape[:2]
         assert surface.flags["C_CONTIGUOUS"] and surface.shape[2] == 3
         return self.L.nes_ref_text_render(t, _u8p(surface), w, h, position, text, len(text))
+
+    def text_render4(self, t, surface: np.ndarray, position: int, text: bytes, fmt: str) -> int:
+        h, w = surface.shape[:2]
+        assert surface.flags["C_CONTIGUOUS"] and surface.shape[2] == 4
+        return self.L.nes_ref_text_render4(t, _u8p(surface), w, h, position, text, len(text), 1 if PIXFMT[fmt][4] == 0 else 0)
 
     def glyph_table(self, t) -> GlyphTable:
         metrics = np.zeros((256, 5), np.int32)

@@ -24,6 +24,8 @@
  */
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
 
 #define NES_ORACLE_API __attribute__((visibility("default")))
 
@@ -41,9 +43,8 @@ typedef struct {
 enum { POS_LEFT_TOP = 0, POS_LEFT_BOTTOM = 1, POS_RIGHT_TOP = 2, POS_RIGHT_BOTTOM = 3, POS_CENTER = 4 };
 
 /* glyphs: 256 entries indexed by (unsigned char)ch.  Returns pixels stamped. */
-NES_ORACLE_API long nes_oracle_render_string(uint8_t *surface, uint32_t width, uint32_t height,
-                                             int position, const char *content, int len,
-                                             const nes_oracle_glyph *glyphs) {
+static long render_string_bpp(uint8_t *surface, uint32_t width, uint32_t height, int position, const char *content,
+                              int len, const nes_oracle_glyph *glyphs, int bpp, int c_off) {
   int pen_x, pen_y;
   const int x_box = 300, y_box = 100, margin = 50; /* render_text.cc:48-50 */
   long stamped = 0;
@@ -67,7 +68,7 @@ NES_ORACLE_API long nes_oracle_render_string(uint8_t *surface, uint32_t width, u
       for (i = pen_x + g->left, p = 0; i < x_max; i++, p++) {
         if (i < 0 || j < 0 || (uint32_t)i >= width || (uint32_t)j >= height) continue;
         if (g->buffer[q * g->width + p]) {
-          uint8_t *px = surface + ((size_t)j * width + (size_t)i) * 3;
+          uint8_t *px = surface + ((size_t)j * width + (size_t)i) * bpp + c_off;
           px[0] = 255; px[1] = 255; px[2] = 255;
           stamped++;
         }
@@ -76,6 +77,21 @@ NES_ORACLE_API long nes_oracle_render_string(uint8_t *surface, uint32_t width, u
     pen_x += g->advance;
   }
   return stamped;
+}
+
+/* render_text.cc:35-111 as written: tightly packed RGB24 surface */
+NES_ORACLE_API long nes_oracle_render_string(uint8_t *surface, uint32_t width, uint32_t height,
+                                             int position, const char *content, int len,
+                                             const nes_oracle_glyph *glyphs) {
+  return render_string_bpp(surface, width, height, position, content, len, glyphs, 3, 0);
+}
+
+/* the same stamp on a 4-byte pixel surface (colour bytes at c_off..c_off+2, alpha untouched):
+ * the reference only ever sees RGB24 (server.cpp:193); BASELINE configs 2/5 feed RGBA */
+NES_ORACLE_API long nes_oracle_render_string4(uint8_t *surface, uint32_t width, uint32_t height,
+                                              int position, const char *content, int len,
+                                              const nes_oracle_glyph *glyphs, int c_off) {
+  return render_string_bpp(surface, width, height, position, content, len, glyphs, 4, c_off);
 }
 
 /*
@@ -88,24 +104,38 @@ NES_ORACLE_API void nes_oracle_composite(int n, const uint8_t *const *rgb, const
                                          int a_off, const uint8_t *const *depth, const int *depth_stride,
                                          int W, int H, uint8_t *out_rgb, int out_rgb_stride,
                                          uint8_t *out_depth, int out_depth_stride) {
+  /* row-wise "running best" form of the per-pixel definition above (same result: a source
+   * replaces the current winner only when strictly nearer, so ties keep the lowest index);
+   * written so a plain C compiler vectorises it -- this is the CPU baseline's composite. */
+  int16_t *best = (int16_t *)malloc(sizeof(int16_t) * (size_t)W);
   for (int y = 0; y < H; y++) {
-    for (int x = 0; x < W; x++) {
-      int best = -1, best_d = 256;
-      for (int k = 0; k < n; k++) {
-        const uint8_t *p = rgb[k] + (size_t)y * rgb_stride[k] + (size_t)x * bpp;
-        const int valid = (bpp == 3) ? 1 : (p[a_off] != 0);
-        const int d = depth[k][(size_t)y * depth_stride[k] + x];
-        if (valid && d < best_d) { best = k; best_d = d; }
-      }
-      uint8_t *o = out_rgb + (size_t)y * out_rgb_stride + (size_t)x * bpp;
-      if (best < 0) {
-        for (int c = 0; c < bpp; c++) o[c] = 0;
-        out_depth[(size_t)y * out_depth_stride + x] = 255;
+    uint8_t *restrict o = out_rgb + (size_t)y * out_rgb_stride;
+    memset(o, 0, (size_t)W * bpp);
+    for (int x = 0; x < W; x++) best[x] = 256;
+    for (int k = 0; k < n; k++) {
+      const uint8_t *restrict p = rgb[k] + (size_t)y * rgb_stride[k];
+      const uint8_t *restrict d = depth[k] + (size_t)y * depth_stride[k];
+      if (bpp == 4) {
+        const uint32_t *restrict p4 = (const uint32_t *)p;
+        uint32_t *restrict o4 = (uint32_t *)o;
+        if (((uintptr_t)p4 | (uintptr_t)o4) & 3) {
+          for (int x = 0; x < W; x++)
+            if (p[4 * x + a_off] != 0 && d[x] < best[x]) { best[x] = d[x]; memcpy(o + 4 * x, p + 4 * x, 4); }
+        } else {
+          const int sh = 8 * a_off; /* little-endian host */
+          for (int x = 0; x < W; x++) {
+            const int take = (((p4[x] >> sh) & 255u) != 0) & (d[x] < best[x]);
+            best[x] = take ? d[x] : best[x];
+            o4[x] = take ? p4[x] : o4[x];
+          }
+        }
       } else {
-        const uint8_t *p = rgb[best] + (size_t)y * rgb_stride[best] + (size_t)x * bpp;
-        for (int c = 0; c < bpp; c++) o[c] = p[c];
-        out_depth[(size_t)y * out_depth_stride + x] = (uint8_t)best_d;
+        for (int x = 0; x < W; x++)
+          if (d[x] < best[x]) { best[x] = d[x]; o[3 * x] = p[3 * x]; o[3 * x + 1] = p[3 * x + 1]; o[3 * x + 2] = p[3 * x + 2]; }
       }
     }
+    uint8_t *restrict od = out_depth + (size_t)y * out_depth_stride;
+    for (int x = 0; x < W; x++) od[x] = (uint8_t)(best[x] > 255 ? 255 : best[x]);
   }
+  free(best);
 }

@@ -187,8 +187,8 @@ NES_REF_API int nes_ref_freetype_version(void *ctx) {
 }
 
 /* render_text.cc:35-111; returns the number of pixels stamped */
-NES_REF_API long nes_ref_text_render(void *ctx, uint8_t *surface, uint32_t width, uint32_t height, int opt,
-                                     const char *content, int len) {
+static long text_render_bpp(void *ctx, uint8_t *surface, uint32_t width, uint32_t height, int opt,
+                            const char *content, int len, int bpp, int c_off) {
   nes_ref_text *t = (nes_ref_text *)ctx;
   FT_GlyphSlotRec_m *slot = t->face->glyph;
   int pen_x, pen_y;
@@ -214,9 +214,9 @@ NES_REF_API long nes_ref_text_render(void *ctx, uint8_t *surface, uint32_t width
       for (i = pen_x + slot->bitmap_left, p = 0; i < x_max; i++, p++) {
         if (i < 0 || j < 0 || (uint32_t)i >= width || (uint32_t)j >= height) continue;
         if (slot->bitmap.buffer[q * slot->bitmap.width + p]) {
-          surface[(j * width + i) * 3] = 255;
-          surface[(j * width + i) * 3 + 1] = 255;
-          surface[(j * width + i) * 3 + 2] = 255;
+          surface[(j * width + i) * bpp + c_off] = 255;
+          surface[(j * width + i) * bpp + c_off + 1] = 255;
+          surface[(j * width + i) * bpp + c_off + 2] = 255;
           stamped++;
         }
       }
@@ -224,6 +224,17 @@ NES_REF_API long nes_ref_text_render(void *ctx, uint8_t *surface, uint32_t width
     pen_x += slot->advance.x >> 6;
   }
   return stamped;
+}
+
+NES_REF_API long nes_ref_text_render(void *ctx, uint8_t *surface, uint32_t width, uint32_t height, int opt,
+                                     const char *content, int len) {
+  return text_render_bpp(ctx, surface, width, height, opt, content, len, 3, 0);
+}
+
+/* same loop on a 4-byte pixel surface (BASELINE configs 2/5 feed RGBA; the reference itself is RGB24 only) */
+NES_REF_API long nes_ref_text_render4(void *ctx, uint8_t *surface, uint32_t width, uint32_t height, int opt,
+                                      const char *content, int len, int c_off) {
+  return text_render_bpp(ctx, surface, width, height, opt, content, len, 4, c_off);
 }
 
 /*
