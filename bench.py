@@ -298,8 +298,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record(stream)
+    h0 = time.perf_counter()
     for _ in range(args.steps):
         step_dev()
+    host_issue_ms = 1000.0 * (time.perf_counter() - h0)
     e1.record(stream)
     e1.synchronize()
     torch.cuda.synchronize()
@@ -401,7 +403,8 @@ def main():
             "config": dict(config, frames_per_step=B, l2="inputs larger than L2: ring of %d distinct frames, %.0f MB touched per step" % (B, B * (in_bytes + out_bytes) / 1e6)),
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "p50_frame_latency_ms": None if lat_p50 is None else round(lat_p50, 3),
-            "single_frame_launch_fps": None if single is None else round(single, 1)}
+            "single_frame_launch_fps": None if single is None else round(single, 1),
+            "host_issue_ms_per_step": round(host_issue_ms / args.steps, 4)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         s.close()

@@ -22,356 +22,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "device_common.cuh"
 #include "nes_internal.h"
 
 namespace nes {
-
-// BT.601 limited range, 15-bit
-// Y = (RY*R + GY*G + BY*B + (32<<14) + (1<<8)) >> 9  -> 14 bit; *2 -> 15 bit;
-// 8-bit out = (y15 + 64) >> 7.  Folded: Y = (S + (32<<14) + (1<<8) + (64<<8)) >> 15
-// (nested floors; the low bit cleared by "*2" cannot carry because 64 is even;
-// no clip is needed: 16 <= Y <= 251).
-constexpr int Y_BIAS = (32 << 14) + (1 << 8) + (64 << 8);
-// chroma of a horizontal pixel pair: u14 = (RU*r2 + GU*g2 + BU*b2 + (256<<15) + (1<<9)) >> 10,
-// u15 = 2*u14 = (S >> 9) & ~1 (S > 0 always; 2*u14 <= 30720 so min(.,32767) never fires).
-constexpr int C_BIAS = (256 << 15) + (1 << 9);
-// per-pixel chroma (resize path without pair sum): (..., + (256<<14) + (1<<8)) >> 9
-constexpr int C1_BIAS = (256 << 14) + (1 << 8);
-// GRAY8 -> limited range luma: ((((d<<7)*14071 + 33561472) >> 14) + 64) >> 7
-//   == (d*1801088 + 34610048) >> 21  (nested floors)
-constexpr int G_MUL = 14071 << 7;
-constexpr int G_ADD = 33561472 + (64 << 14);
-
-__device__ __forceinline__ uint32_t byte_at(uint32_t w, int p) { return __byte_perm(w, 0u, 0x4440u | (uint32_t)p); }
-__device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
-__device__ __forceinline__ uint32_t gray_y(uint32_t d) { return (d * (uint32_t)G_MUL + (uint32_t)G_ADD) >> 21; }
-__device__ __forceinline__ uint32_t gray_y4(uint32_t w) {
-  return gray_y(w & 255u) | (gray_y((w >> 8) & 255u) << 8) | (gray_y((w >> 16) & 255u) << 16) | (gray_y(w >> 24) << 24);
-}
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
-__device__ __forceinline__ const DevJob *find_job(const DevJob *jobs, int n_jobs, int bid, int *tile) {
-  int j = 0;
-  // jobs are few (<= a few hundred); tile_base is a prefix sum
-  int lo = 0, hi = n_jobs - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].tile_base <= bid) lo = mid; else hi = mid - 1;
-  }
-  j = lo;
-  *tile = bid - jobs[j].tile_base;
-  return jobs + j;
-}
-
-// ---------------------------------------------------------------------------
-// depth-select composite of one pixel (self-defined semantics, DESIGN.md §composite;
-// oracle/overlay_port.c nes_oracle_composite): among valid sources (bpp 4: alpha != 0;
-// bpp 3: always) the smallest depth wins, ties to the lowest source index; no valid
-// source -> pixel bytes 0, depth 255.
-// ---------------------------------------------------------------------------
-template <int BPP>
-__device__ __forceinline__ void composite_px(const DevJob &jb, int x, int y, uint8_t *out_px, uint32_t *out_d) {
-  int best = -1;
-  uint32_t best_d = 256;
-  for (int k = 0; k < jb.n_src; k++) {
-    const uint8_t *p = jb.src[k].rgb + (size_t)y * jb.src[k].rgb_stride + (size_t)x * BPP;
-    const uint32_t d = jb.src[k].depth ? jb.src[k].depth[(size_t)y * jb.src[k].depth_stride + x] : 0u;
-    const bool valid = (BPP == 3) ? true : (p[jb.a_off] != 0);
-    if (valid && d < best_d) { best = k; best_d = d; }
-  }
-  if (best < 0) {
-#pragma unroll
-    for (int c = 0; c < BPP; c++) out_px[c] = 0;
-    *out_d = 255;
-  } else {
-    const uint8_t *p = jb.src[best].rgb + (size_t)y * jb.src[best].rgb_stride + (size_t)x * BPP;
-#pragma unroll
-    for (int c = 0; c < BPP; c++) out_px[c] = p[c];
-    *out_d = best_d;
-  }
-}
-
-// 4 pixels of RGBA-family sources at once (aligned fast path).
-__device__ __forceinline__ void composite_px4(const DevJob &jb, int x, int y, uint4 *out_px, uint32_t *out_d4) {
-  uint4 best_px = make_uint4(0, 0, 0, 0);
-  uint32_t bd0 = 256, bd1 = 256, bd2 = 256, bd3 = 256;
-  const int ash = jb.a_off * 8;
-  for (int k = 0; k < jb.n_src; k++) {
-    const uint4 p = __ldg((const uint4 *)(jb.src[k].rgb + (size_t)y * jb.src[k].rgb_stride + (size_t)x * 4));
-    const uint32_t dw = __ldg((const uint32_t *)(jb.src[k].depth + (size_t)y * jb.src[k].depth_stride + x));
-    const uint32_t d0 = dw & 255u, d1 = (dw >> 8) & 255u, d2 = (dw >> 16) & 255u, d3 = dw >> 24;
-    if (((p.x >> ash) & 255u) && d0 < bd0) { bd0 = d0; best_px.x = p.x; }
-    if (((p.y >> ash) & 255u) && d1 < bd1) { bd1 = d1; best_px.y = p.y; }
-    if (((p.z >> ash) & 255u) && d2 < bd2) { bd2 = d2; best_px.z = p.z; }
-    if (((p.w >> ash) & 255u) && d3 < bd3) { bd3 = d3; best_px.w = p.w; }
-  }
-  *out_px = best_px;
-  *out_d4 = min(bd0, 255u) | (min(bd1, 255u) << 8) | (min(bd2, 255u) << 16) | (min(bd3, 255u) << 24);
-}
-
-// ---------------------------------------------------------------------------
-// glyph stamp into a shared-memory pixel tile.  Reference semantics
-// (render_text.cc:94-106): every bitmap pixel with coverage != 0 that falls inside the
-// frame becomes (255,255,255).  All stamps write the same value, so overlapping glyphs
-// and concurrent warps are order-free.
-//   tile origin (ox, oy) in frame coordinates, tile extent cols [cx0,cx1) rows [ry0,ry1)
-// ---------------------------------------------------------------------------
-template <int BPP>
-__device__ __forceinline__ void stamp_glyphs(const DevJob &jb, uint8_t *s_px, int row_bytes, int ox, int oy, int cx0,
-                                             int cx1, int ry0, int ry1, int *s_hits, int *s_nhits) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nwarps = blockDim.x >> 5;
-  for (int base = 0; base < jb.n_glyphs; base += HIT_CAP) {
-    if (tid == 0) *s_nhits = 0;
-    __syncthreads();
-    for (int g = base + tid; g < min(base + HIT_CAP, jb.n_glyphs); g += blockDim.x) {
-      const DevPlaced pg = jb.glyphs[g];
-      if (pg.x < cx1 && pg.x + pg.w > cx0 && pg.y < ry1 && pg.y + pg.h > ry0) s_hits[atomicAdd(s_nhits, 1)] = g;
-    }
-    __syncthreads();
-    const int nh = *s_nhits;
-    for (int h = warp; h < nh; h += nwarps) {
-      const DevPlaced pg = jb.glyphs[s_hits[h]];
-      const uint8_t *cov = jb.atlas + pg.atlas_off;
-      const int q0 = max(0, ry0 - pg.y), q1 = min(pg.h, ry1 - pg.y);
-      const int p0 = max(0, cx0 - pg.x), p1 = min(pg.w, cx1 - pg.x);
-      for (int q = q0; q < q1; q++) {
-        for (int p = p0 + lane; p < p1; p += 32) {
-          if (cov[q * pg.pitch + p]) {
-            uint8_t *px = s_px + (pg.y + q - oy) * row_bytes + (pg.x + p - ox) * BPP + (BPP == 4 ? jb.rgb_base : 0);
-            px[0] = 255; px[1] = 255; px[2] = 255;
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// ---------------------------------------------------------------------------
-// k_frame_tiles: same-size fused path.
-// shared memory: s_in  [TILE_ROWS][TILE_W*BPP] packed pixels (tile + halo rows)
-//                s_uv  [TILE_ROWS][TILE_W/2]   u15 | v15<<16 per (source row, chroma col)
-//                s_hits[HIT_CAP], s_nhits
-// ---------------------------------------------------------------------------
-template <int BPP>
-struct FrameTileSmem {
-  static constexpr int ROWB = TILE_W * BPP;
-  static constexpr int IN_BYTES = TILE_ROWS * ROWB;
-  static constexpr int UV_BYTES = TILE_ROWS * (TILE_W / 2) * 4;
-  static constexpr int HIT_BYTES = HIT_CAP * 4 + 16;
-  static constexpr int TOTAL = IN_BYTES + UV_BYTES + HIT_BYTES;
-};
-
-template <int BPP>
-__global__ void __launch_bounds__(CTA_THREADS, (BPP == 3 ? 4 : 3))
-k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  using L = FrameTileSmem<BPP>;
-  uint8_t *s_in = smem;
-  uint32_t *s_uv = (uint32_t *)(smem + L::IN_BYTES);
-  int *s_hits = (int *)(smem + L::IN_BYTES + L::UV_BYTES);
-  int *s_nhits = s_hits + HIT_CAP;
-
-  int tile;
-  const DevJob *jp = find_job(jobs, n_jobs, blockIdx.x, &tile);
-  if (jp->bpp != BPP || jp->general) return;  // other template / general-path job
-  const DevJob &jb = *jp;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = tile % jb.tiles_x, ty = tile / jb.tiles_x;
-  const int W = jb.W, H = jb.H;
-  const int x0 = tx * TILE_W, y0 = ty * TILE_H;
-  const int tw = min(TILE_W, W - x0), th = min(TILE_H, H - y0);
-  const int oy = y0 - HALO;                       // frame row of tile row 0
-  const int ya = max(oy, 0), yb = min(y0 + th + HALO, H);  // rows actually present
-  const bool composite = jb.n_src > 1;
-  const bool vec_in = jb.in_vec != 0, vec_out = jb.out_vec != 0;
-
-  // ---- stage 1: packed pixels of the tile (+halo) into shared memory ----------
-  if (!composite) {
-    const uint8_t *src = jb.src[0].rgb;
-    const int stride = jb.src[0].rgb_stride;
-    const int nbytes = tw * BPP;
-    for (int y = ya + warp; y < yb; y += CTA_THREADS / 32) {
-      const uint8_t *g = src + (size_t)y * stride + (size_t)x0 * BPP;
-      uint8_t *s = s_in + (y - oy) * L::ROWB;
-      if (vec_in) {
-        const int nvec = nbytes >> 4;
-        for (int i = lane; i < nvec; i += 32) cp_async16(s + i * 16, g + i * 16);
-        for (int i = (nvec << 4) + lane; i < nbytes; i += 32) s[i] = g[i];
-      } else {
-        for (int i = lane; i < nbytes; i += 32) s[i] = g[i];
-      }
-    }
-    // depth stream is pointwise: do it while the cp.async traffic is in flight
-    if (jb.dy) {
-      const uint8_t *dsrc = jb.src[0].depth;
-      const int dstride = jb.src[0].depth_stride;
-      for (int r = warp; r < th; r += CTA_THREADS / 32) {
-        const int y = y0 + r;
-        const uint8_t *g = dsrc + (size_t)y * dstride + x0;
-        uint8_t *o = jb.dy + (size_t)y * jb.dys + x0;
-        const int x = lane * 8;
-        if (vec_in && vec_out && x + 8 <= tw) {
-          const uint2 d = __ldg((const uint2 *)(g + x));
-          *(uint2 *)(o + x) = make_uint2(gray_y4(d.x), gray_y4(d.y));
-        } else {
-          for (int i = x; i < min(x + 8, tw); i++) o[i] = (uint8_t)gray_y(g[i]);
-        }
-      }
-    }
-    cp_async_wait_all();
-  } else {
-    // composite: select per pixel among the sources, keep the winner's bytes in the
-    // tile and convert the winner's depth on the fly (core rows only).
-    for (int y = ya + warp; y < yb; y += CTA_THREADS / 32) {
-      uint8_t *s = s_in + (y - oy) * L::ROWB;
-      const bool core = (y >= y0) && (y < y0 + th);
-      if (BPP == 4 && vec_in && vec_out && (tw & 3) == 0) {
-        for (int x = lane * 4; x < tw; x += 128) {
-          uint4 px; uint32_t d4;
-          composite_px4(jb, x0 + x, y, &px, &d4);
-          *(uint4 *)(s + x * 4) = px;
-          if (core && jb.dy) *(uint32_t *)(jb.dy + (size_t)y * jb.dys + x0 + x) = gray_y4(d4);
-        }
-      } else {
-        for (int x = lane; x < tw; x += 32) {
-          uint32_t d;
-          composite_px<BPP>(jb, x0 + x, y, s + x * BPP, &d);
-          if (core && jb.dy) jb.dy[(size_t)y * jb.dys + x0 + x] = (uint8_t)gray_y(d);
-        }
-      }
-    }
-  }
-  // depth chroma planes are constant 128
-  if (jb.dy) {
-    for (int r = warp; r < (th >> 1); r += CTA_THREADS / 32) {
-      const int ci = (y0 >> 1) + r;
-      uint8_t *ou = jb.du + (size_t)ci * jb.dus + (x0 >> 1);
-      uint8_t *ov = jb.dv + (size_t)ci * jb.dvs + (x0 >> 1);
-      const int c = lane * 4;
-      if (vec_out && c + 4 <= (tw >> 1)) {
-        *(uint32_t *)(ou + c) = 0x80808080u;
-        *(uint32_t *)(ov + c) = 0x80808080u;
-      } else {
-        for (int i = c; i < min(c + 4, tw >> 1); i++) { ou[i] = 128; ov[i] = 128; }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- stage 2: text overlay, stamped into the shared tile ---------------------
-  if (jb.n_glyphs > 0) stamp_glyphs<BPP>(jb, s_in, L::ROWB, x0, oy, x0, x0 + tw, ya, yb, s_hits, s_nhits);
-
-  // ---- stage 3: per source row: Y out, pair-summed chroma to s_uv -------------
-  {
-    const int cy0 = jb.cy[0], cy1 = jb.cy[1], cy2 = jb.cy[2];
-    const int cu0 = jb.cu[0], cu1 = jb.cu[1], cu2 = jb.cu[2];
-    const int cv0 = jb.cv[0], cv1 = jb.cv[1], cv2 = jb.cv[2];
-    const int rb = jb.rgb_base;
-    const int x = lane * 8;
-    if (x < tw) {
-      for (int y = ya + warp; y < yb; y += CTA_THREADS / 32) {
-        const int tr = y - oy;
-        uint32_t c[8][3];
-        if (BPP == 3) {
-          const uint2 *p = (const uint2 *)(s_in + tr * L::ROWB + lane * 24);
-          const uint2 a = p[0], b = p[1], d = p[2];
-          const uint32_t w[6] = {a.x, a.y, b.x, b.y, d.x, d.y};
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) c[k][j] = byte_at(w[(3 * k + j) >> 2], (3 * k + j) & 3);
-        } else {
-          const uint4 *p = (const uint4 *)(s_in + tr * L::ROWB + lane * 32);
-          const uint4 a = p[0], b = p[1];
-          const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) c[k][j] = byte_at(w[k], rb + j);
-        }
-        if (y >= y0 && y < y0 + th) {
-          uint32_t yv[8];
-#pragma unroll
-          for (int k = 0; k < 8; k++)
-            yv[k] = (uint32_t)(cy0 * (int)c[k][0] + cy1 * (int)c[k][1] + cy2 * (int)c[k][2] + Y_BIAS) >> 15;
-          uint8_t *o = jb.sy + (size_t)y * jb.sys + x0 + x;
-          if (vec_out && x + 8 <= tw) {
-            uint2 v;
-            v.x = yv[0] | (yv[1] << 8) | (yv[2] << 16) | (yv[3] << 24);
-            v.y = yv[4] | (yv[5] << 8) | (yv[6] << 16) | (yv[7] << 24);
-            *(uint2 *)o = v;
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-              if (x + k < tw) o[k] = (uint8_t)yv[k];
-          }
-        }
-        uint32_t uv[4];
-#pragma unroll
-        for (int p2 = 0; p2 < 4; p2++) {
-          const int s0 = (int)(c[2 * p2][0] + c[2 * p2 + 1][0]);
-          const int s1 = (int)(c[2 * p2][1] + c[2 * p2 + 1][1]);
-          const int s2 = (int)(c[2 * p2][2] + c[2 * p2 + 1][2]);
-          const uint32_t u = ((uint32_t)(cu0 * s0 + cu1 * s1 + cu2 * s2 + C_BIAS) >> 9) & 0xFFFEu;
-          const uint32_t v = ((uint32_t)(cv0 * s0 + cv1 * s1 + cv2 * s2 + C_BIAS) >> 9) & 0xFFFEu;
-          uv[p2] = u | (v << 16);
-        }
-        *(uint4 *)(s_uv + tr * (TILE_W / 2) + lane * 4) = make_uint4(uv[0], uv[1], uv[2], uv[3]);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- stage 4: 8-tap vertical bicubic on chroma (edge taps fold = clamped rows) --
-  // T = [-58,-172,492,1786,1786,492,-172,-58]/4096, symmetric: pair the taps first (the
-  // packed u|v words add without carry: 2*32767 < 65536).
-  {
-    const int c = lane * 4;  // chroma column inside the tile
-    if (c < (tw >> 1)) {
-      for (int r = warp; r < (th >> 1); r += CTA_THREADS / 32) {
-        const int ci = (y0 >> 1) + r;
-        uint32_t t[8][4];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int sr = min(max(2 * ci - 3 + j, 0), H - 1) - oy;
-          const uint4 q = *(const uint4 *)(s_uv + sr * (TILE_W / 2) + c);
-          t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
-        }
-        uint32_t ub = 0, vb = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const uint32_t a07 = t[0][k] + t[7][k];
-          const uint32_t a16 = t[1][k] + t[6][k];
-          const uint32_t a25 = t[2][k] + t[5][k];
-          const uint32_t a34 = t[3][k] + t[4][k];
-          const int su = (64 << 12) + 1786 * (int)(a34 & 0xFFFFu) + 492 * (int)(a25 & 0xFFFFu) -
-                         172 * (int)(a16 & 0xFFFFu) - 58 * (int)(a07 & 0xFFFFu);
-          const int sv = (64 << 12) + 1786 * (int)(a34 >> 16) + 492 * (int)(a25 >> 16) - 172 * (int)(a16 >> 16) -
-                         58 * (int)(a07 >> 16);
-          ub |= (uint32_t)clip8(su >> 19) << (8 * k);
-          vb |= (uint32_t)clip8(sv >> 19) << (8 * k);
-        }
-        uint8_t *ou = jb.su + (size_t)ci * jb.sus + (x0 >> 1) + c;
-        uint8_t *ov = jb.sv + (size_t)ci * jb.svs + (x0 >> 1) + c;
-        if (vec_out && c + 4 <= (tw >> 1)) {
-          *(uint32_t *)ou = ub;
-          *(uint32_t *)ov = vb;
-        } else {
-          for (int k = 0; k < 4; k++)
-            if (c + k < (tw >> 1)) { ou[k] = (uint8_t)(ub >> (8 * k)); ov[k] = (uint8_t)(vb >> (8 * k)); }
-        }
-      }
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------
 // k_composite: composite N sources to a scratch frame (same pixel format + GRAY8).
@@ -605,35 +259,11 @@ static int g_resize_smem_cap = 0;
 
 int kernels_init() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_frame_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrameTileSmem<3>::TOTAL);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_frame_tiles<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FrameTileSmem<4>::TOTAL);
-  if (e != cudaSuccess) return (int)e;
+  if (int r = frame_tiles_init()) return r;
   g_resize_smem_cap = 200 * 1024;
   e = cudaFuncSetAttribute(k_resize_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, g_resize_smem_cap);
   if (e != cudaSuccess) return (int)e;
   return 0;
-}
-
-int launch_frame_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream) {
-  int total = 0;
-  bool any3 = false, any4 = false;
-  for (int j = 0; j < n_jobs; j++) {
-    const DevJob &jb = jobs_host[j];
-    total = jb.tile_base + jb.tiles_x * jb.tiles_y;
-    if (!jb.general) (jb.bpp == 3 ? any3 : any4) = true;
-  }
-  if (total == 0) return 0;
-  int launches = 0;
-  if (any3) {
-    k_frame_tiles<3><<<total, CTA_THREADS, FrameTileSmem<3>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs);
-    launches++;
-  }
-  if (any4) {
-    k_frame_tiles<4><<<total, CTA_THREADS, FrameTileSmem<4>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs);
-    launches++;
-  }
-  return launches;
 }
 
 int launch_composite(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream) {

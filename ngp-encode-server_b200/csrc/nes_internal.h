@@ -13,11 +13,12 @@ namespace nes {
 // TILE_W x TILE_H block of source pixels and loads 3 halo rows above and below
 // for the 8-tap vertical chroma filter.
 constexpr int TILE_W = 256;
-constexpr int TILE_H = 32;
+constexpr int TILE_H = 30;  // divides 720/1080/1440/2160: no ragged last tile row
 constexpr int HALO = 3;
 constexpr int TILE_ROWS = TILE_H + 2 * HALO;
 constexpr int CTA_THREADS = 256;
-constexpr int HIT_CAP = 512;  // glyph rect tests per overlay chunk
+constexpr int HIT_CAP = 256;  // glyph rect tests per overlay chunk
+constexpr int MASK_WORDS = 128;  // per-job bitmap of tiles touched by text (4096 tiles)
 
 // Resize tile geometry (k_resize_tiles): destination pixels per CTA.
 constexpr int RS_TILE_W = 64;
@@ -55,6 +56,9 @@ struct DevJob {
   int32_t rgb_base;  // byte offset of the first colour byte inside a pixel (0, or 1 for ARGB/ABGR)
   int32_t a_off;     // byte offset of alpha (bpp 4) or -1
   int32_t cy[3], cu[3], cv[3];  // BT.601 coefficients per colour byte position
+  // the same coefficients packed for dp2a on a pixel word (bytes 0,1 -> [0]; bytes 2,3 -> [1]),
+  // 16-bit signed halves; bytes that are not colour get 0
+  uint32_t ky[2], ku[2], kv[2];
   int32_t W, H, Wd, Hd;
   uint8_t *sy, *su, *sv;  // scene planes
   int32_t sys, sus, svs;
@@ -65,6 +69,10 @@ struct DevJob {
   const DevPlaced *glyphs;
   const uint8_t *atlas;
   int32_t n_glyphs;
+  int32_t tma_ok;     // single source, 16-byte aligned rows: tiles are staged with bulk async copies
+  int32_t use_mask;   // tile_mask valid (tiles_x*tiles_y <= 32*MASK_WORDS)
+  int32_t pad1;
+  uint32_t tile_mask[MASK_WORDS];  // bit t set: tile t (or its halo rows) intersects a placed glyph
   int32_t tiles_x, tiles_y, tile_base;
   // resize only
   DevFilter hl, hc, vl, vc;
@@ -82,6 +90,7 @@ int launch_frame_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jo
 int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
 int launch_composite(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
 int kernels_init();  // opt-in shared memory sizes; returns cudaError_t
+int frame_tiles_init();
 
 }  // namespace nes
 #endif

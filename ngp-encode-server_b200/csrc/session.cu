@@ -270,7 +270,39 @@ void job_common(DevJob *jb, const nes_frame_in *in, const nes_frame_out *out, in
   jb->cy[r] = RY; jb->cy[1] = GY; jb->cy[b] = BY;
   jb->cu[r] = RU; jb->cu[1] = GU; jb->cu[b] = BU;
   jb->cv[r] = RV; jb->cv[1] = GV; jb->cv[b] = BV;
+  // dp2a operands: 16-bit coefficient pairs for pixel-word bytes (0,1) and (2,3)
+  int cb[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+  for (int j = 0; j < 3; j++) { cb[0][base + j] = jb->cy[j]; cb[1][base + j] = jb->cu[j]; cb[2][base + j] = jb->cv[j]; }
+  uint32_t *k[3] = {jb->ky, jb->ku, jb->kv};
+  for (int c = 0; c < 3; c++) {
+    k[c][0] = ((uint32_t)cb[c][0] & 0xFFFFu) | ((uint32_t)cb[c][1] << 16);
+    k[c][1] = ((uint32_t)cb[c][2] & 0xFFFFu) | ((uint32_t)cb[c][3] << 16);
+  }
   jb->W = in->width; jb->H = in->height; jb->Wd = out->width; jb->Hd = out->height;
+}
+
+// Bitmap of the fused kernel's tiles (incl. their halo rows) that a placed glyph touches, so
+// that every other tile skips the overlay stage without looking at the glyph list.
+void job_tile_mask(DevJob *jb, const DevPlaced *placed) {
+  jb->use_mask = 0;
+  if (jb->general || jb->n_glyphs <= 0 || jb->tiles_x * jb->tiles_y > 32 * MASK_WORDS) return;
+  std::memset(jb->tile_mask, 0, sizeof(jb->tile_mask));
+  for (int g = 0; g < jb->n_glyphs; g++) {
+    const DevPlaced &p = placed[g];
+    const int x0 = std::max(p.x, 0), x1 = std::min(p.x + p.w, jb->W), y0 = std::max(p.y, 0), y1 = std::min(p.y + p.h, jb->H);
+    if (x0 >= x1 || y0 >= y1) continue;
+    const int tx0 = x0 / TILE_W, tx1 = (x1 - 1) / TILE_W;
+    const int ty0 = std::max((y0 - HALO) / TILE_H - 1, 0), ty1 = std::min((y1 + HALO) / TILE_H + 1, jb->tiles_y - 1);
+    for (int ty = ty0; ty <= ty1; ty++) {
+      const int ra = ty * TILE_H - HALO, rb = ty * TILE_H + TILE_H + HALO;  // rows the tile stages
+      if (y0 >= rb || y1 <= ra) continue;
+      for (int tx = tx0; tx <= tx1; tx++) {
+        const int t = ty * jb->tiles_x + tx;
+        jb->tile_mask[t >> 5] |= 1u << (t & 31);
+      }
+    }
+  }
+  jb->use_mask = 1;
 }
 
 void job_tiles(DevJob *jb, int tile_base) {
@@ -294,6 +326,7 @@ void job_alignment(DevJob *jb) {
   if (jb->dy) ov = ov && aligned16(jb->dy, jb->dys) && aligned16(jb->du, jb->dus) && aligned16(jb->dv, jb->dvs);
   jb->in_vec = iv;
   jb->out_vec = ov;
+  jb->tma_ok = iv && jb->n_src == 1 && (jb->W % 16) == 0;
 }
 
 // Text runs -> placed glyph descriptors at dst[0..].  Returns count or negative status.
@@ -658,6 +691,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   }
   job_tiles(jb, 0);
   job_alignment(jb);
+  job_tile_mask(jb, sl.h_glyphs);
 
   if (n_gl > 0) CU_TRY(s, cudaMemcpyAsync(sl.d_glyphs, sl.h_glyphs, (size_t)n_gl * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaMemcpyAsync(sl.d_job, sl.h_job, sizeof(DevJob), cudaMemcpyHostToDevice, s->st_in));
@@ -798,6 +832,7 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
     job_tiles(jb, tile_base);
     tile_base += jb->tiles_x * jb->tiles_y;
     job_alignment(jb);
+    job_tile_mask(jb, bt.h_glyphs + gl_used - n_gl);
   }
   if (gl_used > 0) CU_TRY(s, cudaMemcpyAsync(bt.d_glyphs, bt.h_glyphs, (size_t)gl_used * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_k));
   CU_TRY(s, cudaMemcpyAsync(bt.d_jobs, bt.h_jobs, sizeof(DevJob) * n_frames, cudaMemcpyHostToDevice, s->st_k));
