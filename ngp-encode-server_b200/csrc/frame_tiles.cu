@@ -85,6 +85,28 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// explicit shared-space accesses (32-bit shared addresses; keeps the hot loops off generic LD/ST)
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ int atoms_inc(uint32_t a) {
+  int v;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1   (a: signed 16-bit halves, b: unsigned bytes)
@@ -130,9 +152,9 @@ __device__ __forceinline__ int job_of_tile(const DevJob *jobs, int n_jobs, int t
 }  // namespace
 
 // One warp-wide grab from a shared work counter.
-__device__ __forceinline__ int grab(int *q, int lane) {
+__device__ __forceinline__ int grab(uint32_t q_addr, int lane) {
   int v = 0;
-  if (lane == 0) v = atomicAdd(q, 1);
+  if (lane == 0) v = atoms_inc(q_addr);
   return __shfl_sync(0xffffffffu, v, 0);
 }
 
@@ -185,6 +207,8 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = CTA_THREADS / 32;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t qA = smem_base + L::OFF_Q, qB = qA + 4, qF = qA + 8;
 
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
@@ -286,7 +310,7 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
 
       // ---- fill the tile ourselves when it was not staged by bulk copies ------------------
       if (!c.tma && !direct) {
-        for (int y = ya + grab(&s_q[2], lane); y < yb; y = ya + grab(&s_q[2], lane)) {
+        for (int y = ya + grab(qF, lane); y < yb; y = ya + grab(qF, lane)) {
           uint8_t *s = s_px + (y - oy) * L::ROWB;
           if (n_src == 1) {
             const uint8_t *g = c.rgb[0] + (size_t)y * c.rs[0];
@@ -324,14 +348,16 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
         const uint32_t kya = c.kya, kyb = c.kyb, kua = c.kua, kub = c.kub, kva = c.kva, kvb = c.kvb;
         uint8_t *const sy = c.sy;
         const size_t sys = (size_t)c.sys;
-        for (int y = ya + grab(&s_q[0], lane); y < yb; y = ya + grab(&s_q[0], lane)) {
-          uint8_t *row = s_px + (y - oy) * L::ROWB;
+        const uint32_t px_addr = smem_base + cur * L::PX_BYTES;
+        int y = ya + grab(qA, lane);
+        while (y < yb) {
+          const int y_next = ya + grab(qA, lane);  // overlaps the queue round trip with this row's arithmetic
+          const uint32_t row = px_addr + (y - oy) * L::ROWB;
           const bool core = (y >= y0) && (y < y0 + th);
           uint32_t p[8];  // pixel words: colour bytes of pixel k in the positions ky/ku/kv expect
           if (BPP == 3) {
             // lane owns pixels 8*lane .. 8*lane+7 (24 bytes; 8-byte loads at 24-byte stride are conflict free)
-            const uint2 *q = (const uint2 *)(row + lane * 24);
-            const uint2 a = q[0], b = q[1], d = q[2];
+            const uint2 a = lds64(row + lane * 24), b = lds64(row + lane * 24 + 8), d = lds64(row + lane * 24 + 16);
             p[0] = a.x;
             p[1] = __funnelshift_r(a.x, a.y, 24);
             p[2] = __funnelshift_r(a.y, b.x, 16);
@@ -352,7 +378,7 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
             }
           } else {
             // lane owns pixels 4*lane..+3 and 128+4*lane..+3 (16-byte loads at 16-byte stride)
-            const uint4 a = *(const uint4 *)(row + lane * 16), b = *(const uint4 *)(row + 512 + lane * 16);
+            const uint4 a = lds128(row + lane * 16), b = lds128(row + 512 + lane * 16);
             p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
             __syncwarp();
           }
@@ -366,10 +392,10 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
             uv[j] = (((uint32_t)su >> 9) & 0xFFFEu) | (((uint32_t)sv << 7) & 0xFFFE0000u);
           }
           if (BPP == 3) {
-            *(uint4 *)(row + lane * 16) = make_uint4(uv[0], uv[1], uv[2], uv[3]);  // chroma cols 4*lane..+3
+            sts128(row + lane * 16, uv[0], uv[1], uv[2], uv[3]);  // chroma cols 4*lane..+3
           } else {
-            *(uint2 *)(row + lane * 8) = make_uint2(uv[0], uv[1]);         // chroma cols 2*lane, 2*lane+1
-            *(uint2 *)(row + 256 + lane * 8) = make_uint2(uv[2], uv[3]);   // chroma cols 64+2*lane, +1
+            sts64(row + lane * 8, uv[0], uv[1]);         // chroma cols 2*lane, 2*lane+1
+            sts64(row + 256 + lane * 8, uv[2], uv[3]);   // chroma cols 64+2*lane, +1
           }
           if (core) {
             uint32_t yv[8];
@@ -401,6 +427,7 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
                   if (xb + k < tw) o[xb + k] = (uint8_t)yv[4 + k];
             }
           }
+          y = y_next;
         }
       }
       __syncthreads();
@@ -414,14 +441,18 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
         uint8_t *const su_ = c.su, *const sv_ = c.sv;
         const size_t sus = (size_t)c.sus, svs = (size_t)c.svs;
         const int crows = th >> 1;
-        for (int r = grab(&s_q[1], lane); r < crows; r = grab(&s_q[1], lane)) {
-          if (cc >= (tw >> 1)) continue;
+        const uint32_t px_addr = smem_base + cur * L::PX_BYTES + cc * 4;
+        int r = grab(qB, lane);
+        while (r < crows) {
+          const int r_next = grab(qB, lane);
           const int ci = (y0 >> 1) + r;
+          r = r_next;
+          if (cc >= (tw >> 1)) continue;
           uint32_t t[8][4];
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             const int sr = min(max(2 * ci - 3 + j, 0), H - 1) - oy;
-            const uint4 q = *(const uint4 *)(s_px + sr * L::ROWB + cc * 4);
+            const uint4 q = lds128(px_addr + sr * L::ROWB);
             t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
           }
           uint32_t ub = 0, vb = 0;

@@ -64,7 +64,7 @@ struct Slot {
 struct BatchTables {
   DevJob *h_jobs = nullptr, *d_jobs = nullptr;
   DevPlaced *h_glyphs = nullptr, *d_glyphs = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaEvent_t done = nullptr, up = nullptr;
   bool used = false;
 };
 
@@ -444,6 +444,7 @@ void nes_gpu_session_destroy(nes_gpu_session *s) {
   for (BatchTables &b : s->batch) {
     cudaFreeHost(b.h_jobs); cudaFree(b.d_jobs); cudaFreeHost(b.h_glyphs); cudaFree(b.d_glyphs);
     if (b.done) cudaEventDestroy(b.done);
+    if (b.up) cudaEventDestroy(b.up);
   }
   for (auto &kv : s->filters) cudaFree(kv.second.blob);
   cudaFree(s->d_atlas);
@@ -788,6 +789,7 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
     CU_TRY(s, cudaHostAlloc((void **)&bt.h_glyphs, gl_bytes, cudaHostAllocDefault));
     CU_TRY(s, cudaMalloc((void **)&bt.d_glyphs, gl_bytes));
     CU_TRY(s, cudaEventCreateWithFlags(&bt.done, cudaEventDisableTiming));
+    CU_TRY(s, cudaEventCreateWithFlags(&bt.up, cudaEventDisableTiming));
   }
   if (bt.used) CU_TRY(s, cudaEventSynchronize(bt.done));  // tables still referenced by an older batch
   int tile_base = 0, gl_used = 0;
@@ -834,8 +836,11 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
     job_alignment(jb);
     job_tile_mask(jb, bt.h_glyphs + gl_used - n_gl);
   }
-  if (gl_used > 0) CU_TRY(s, cudaMemcpyAsync(bt.d_glyphs, bt.h_glyphs, (size_t)gl_used * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_k));
-  CU_TRY(s, cudaMemcpyAsync(bt.d_jobs, bt.h_jobs, sizeof(DevJob) * n_frames, cudaMemcpyHostToDevice, s->st_k));
+  // descriptor upload on the copy stream, so that it overlaps the kernels of the previous batch
+  if (gl_used > 0) CU_TRY(s, cudaMemcpyAsync(bt.d_glyphs, bt.h_glyphs, (size_t)gl_used * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
+  CU_TRY(s, cudaMemcpyAsync(bt.d_jobs, bt.h_jobs, sizeof(DevJob) * n_frames, cudaMemcpyHostToDevice, s->st_in));
+  CU_TRY(s, cudaEventRecord(bt.up, s->st_in));
+  CU_TRY(s, cudaStreamWaitEvent(s->st_k, bt.up, 0));
   run_kernels(s, bt.d_jobs, bt.h_jobs, n_frames, s->st_k);
   CU_TRY(s, cudaGetLastError());
   CU_TRY(s, cudaEventRecord(bt.done, s->st_k));
