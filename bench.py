@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--warmup-seconds", type=float, default=1.0, help="minimum wall time of untimed warm-up (clock ramp)")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     warmup = max(args.warmup, 3)
@@ -289,8 +290,16 @@ def main():
         def step_dev():
             s.run_batch(prepared, sync=False)
 
-    for _ in range(warmup):
+    # W warm-up steps, and at least ~1 s of them: an idle B200 sits at 120 MHz and needs a few
+    # hundred ms of load to reach its boost clock (a 45 ms timed region right after 5 short steps
+    # measured 2-4x slow, run to run)
+    tw0 = time.perf_counter()
+    n_warm = 0
+    while n_warm < warmup or time.perf_counter() - tw0 < args.warmup_seconds:
         step_dev()
+        n_warm += 1
+        if n_warm % 64 == 0:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     barrier()
     torch.cuda.synchronize()

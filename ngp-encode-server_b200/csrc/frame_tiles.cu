@@ -300,11 +300,11 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
       const bool depth_lane = depth_vec && lane * 8 < tw;
       if (depth_lane) {
         const uint8_t *dsrc = c.dep[0] + lane * 8;
-        const size_t dstride = (size_t)c.ds[0];
+        const int dstride = c.ds[0];
 #pragma unroll
         for (int i = 0; i < DROWS; i++) {
           const int r = warp + i * NW;
-          if (r < th) dreg[i] = __ldg((const uint2 *)(dsrc + (size_t)(y0 + r) * dstride));
+          if (r < th) dreg[i] = __ldg((const uint2 *)(dsrc + (y0 + r) * dstride));
         }
       }
 
@@ -403,7 +403,7 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
             for (int k = 0; k < 8; k++) yv[k] = (uint32_t)dp2a_hi(kyb, p[k], dp2a_lo(kya, p[k], Y_BIAS)) >> 15;
             const uint32_t w0 = yv[0] | (yv[1] << 8) | (yv[2] << 16) | (yv[3] << 24);
             const uint32_t w1 = yv[4] | (yv[5] << 8) | (yv[6] << 16) | (yv[7] << 24);
-            uint8_t *o = sy + (size_t)y * sys;
+            uint8_t *o = sy + y * (int)sys;
             if (BPP == 3) {
               const int x = lane * 8;
               if (vec_out && x + 8 <= tw) {
@@ -442,18 +442,31 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
         const size_t sus = (size_t)c.sus, svs = (size_t)c.svs;
         const int crows = th >> 1;
         const uint32_t px_addr = smem_base + cur * L::PX_BYTES + cc * 4;
+        const bool interior = (ya == oy) && (yb == y0 + th + HALO);  // no clamped tap rows in this tile
+        uint8_t *const du = c.du, *const dv = c.dv;
+        const int dus = c.dus, dvs = c.dvs;
         int r = grab(qB, lane);
         while (r < crows) {
           const int r_next = grab(qB, lane);
           const int ci = (y0 >> 1) + r;
+          const int rr = r;
           r = r_next;
           if (cc >= (tw >> 1)) continue;
           uint32_t t[8][4];
+          if (interior) {
+            const uint32_t base = px_addr + (uint32_t)(2 * rr) * L::ROWB;  // tile row of tap 0 = 2*rr
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const int sr = min(max(2 * ci - 3 + j, 0), H - 1) - oy;
-            const uint4 q = lds128(px_addr + sr * L::ROWB);
-            t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
+            for (int j = 0; j < 8; j++) {
+              const uint4 q = lds128(base + j * L::ROWB);
+              t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const int sr = min(max(2 * ci - 3 + j, 0), H - 1) - oy;
+              const uint4 q = lds128(px_addr + sr * L::ROWB);
+              t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
+            }
           }
           uint32_t ub = 0, vb = 0;
 #pragma unroll
@@ -464,47 +477,42 @@ k_frame_tiles(const DevJob *__restrict__ jobs, int n_jobs, int total_tiles) {
             ub |= clip8_relu(au >> 19) << (8 * k);
             vb |= clip8_relu(av >> 19) << (8 * k);
           }
-          uint8_t *ou = su_ + (size_t)ci * sus + cc;
-          uint8_t *ov = sv_ + (size_t)ci * svs + cc;
+          uint8_t *ou = su_ + ci * (int)sus + cc;
+          uint8_t *ov = sv_ + ci * (int)svs + cc;
           if (vec_out && cc + 4 <= (tw >> 1)) {
             *(uint32_t *)ou = ub;
             *(uint32_t *)ov = vb;
+            if (dy) {  // depth chroma planes are constant 128
+              *(uint32_t *)(du + ci * dus + cc) = 0x80808080u;
+              *(uint32_t *)(dv + ci * dvs + cc) = 0x80808080u;
+            }
           } else {
             for (int k = 0; k < 4; k++)
-              if (cc + k < (tw >> 1)) { ou[k] = (uint8_t)(ub >> (8 * k)); ov[k] = (uint8_t)(vb >> (8 * k)); }
+              if (cc + k < (tw >> 1)) {
+                ou[k] = (uint8_t)(ub >> (8 * k)); ov[k] = (uint8_t)(vb >> (8 * k));
+                if (dy) { du[ci * dus + cc + k] = 128; dv[ci * dvs + cc + k] = 128; }
+              }
           }
         }
       }
 
-      // ---- depth stream: Y = range-compressed gray, U = V = 128 --------------------------------
-      if (dy) {
-        const size_t dys = (size_t)c.dys;
-        if (n_src == 1) {
-          if (depth_vec) {
+      // ---- depth stream: Y = range-compressed gray (U = V = 128 went out with phase B) ----------
+      if (dy && n_src == 1) {
+        const int dys = c.dys;
+        if (depth_vec) {
+          if (depth_lane) {
+            uint8_t *o = dy + lane * 8;
 #pragma unroll
             for (int i = 0; i < DROWS; i++) {
               const int r = warp + i * NW;
-              if (depth_lane && r < th) *(uint2 *)(dy + (size_t)(y0 + r) * dys + lane * 8) = make_uint2(gray_y4_packed(dreg[i].x), gray_y4_packed(dreg[i].y));
+              if (r < th) *(uint2 *)(o + (y0 + r) * dys) = make_uint2(gray_y4_packed(dreg[i].x), gray_y4_packed(dreg[i].y));
             }
-          } else {
-            const uint8_t *dsrc = c.dep[0];
-            const size_t dstride = (size_t)c.ds[0];
-            for (int r = warp; r < th; r += NW)
-              for (int x = lane; x < tw; x += 32) dy[(size_t)(y0 + r) * dys + x] = (uint8_t)gray_y(dsrc[(size_t)(y0 + r) * dstride + x]);
           }
-        }
-        uint8_t *const du = c.du, *const dv = c.dv;
-        const size_t dus = (size_t)c.dus, dvs = (size_t)c.dvs;
-        for (int r = warp; r < (th >> 1); r += NW) {
-          const int ci = (y0 >> 1) + r;
-          uint8_t *ou = du + (size_t)ci * dus, *ov = dv + (size_t)ci * dvs;
-          const int cc = lane * 4;
-          if (vec_out && cc + 4 <= (tw >> 1)) {
-            *(uint32_t *)(ou + cc) = 0x80808080u;
-            *(uint32_t *)(ov + cc) = 0x80808080u;
-          } else {
-            for (int i = cc; i < min(cc + 4, tw >> 1); i++) { ou[i] = 128; ov[i] = 128; }
-          }
+        } else {
+          const uint8_t *dsrc = c.dep[0];
+          const int dstride = c.ds[0];
+          for (int r = warp; r < th; r += NW)
+            for (int x = lane; x < tw; x += 32) dy[(y0 + r) * dys + x] = (uint8_t)gray_y(dsrc[(size_t)(y0 + r) * dstride + x]);
         }
       }
     }

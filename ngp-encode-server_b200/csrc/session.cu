@@ -248,6 +248,12 @@ int validate(const nes_gpu_session *s, const nes_frame_in *in, const nes_frame_o
       if (sr.depth_bytes < (uint64_t)(ds * (H - 1) + W)) return NES_ERR_SHORT_BUFFER;
     }
   }
+  // the kernels index planes with 32-bit offsets
+  if ((int64_t)W * 4 * H >= (int64_t)1 << 31 || (int64_t)out->scene_linesize[0] * Hd >= (int64_t)1 << 31 ||
+      (want_depth && (int64_t)out->depth_linesize[0] * Hd >= (int64_t)1 << 31))
+    return NES_ERR_TOO_LARGE;
+  for (int k = 0; k < in->n_sources; k++)
+    if ((int64_t)in->src[k].rgb_stride * H >= (int64_t)1 << 31 || (int64_t)in->src[k].depth_stride * H >= (int64_t)1 << 31) return NES_ERR_TOO_LARGE;
   for (int p = 0; p < 3; p++) {
     const int minls = p ? (Wd + 1) / 2 : Wd;
     if (!out->scene[p] || out->scene_linesize[p] < minls) return NES_ERR_INVALID_ARG;
