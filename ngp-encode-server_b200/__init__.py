@@ -7,3 +7,4 @@ The directory name carries a hyphen (it mirrors the reference's name); import it
 from .api import *  # noqa: F401,F403
 from . import api  # noqa: F401
 from . import synth  # noqa: F401,E402
+from . import shard  # noqa: F401,E402

@@ -346,3 +346,27 @@ def test_full_size_properties(N, O, session, golden):
     left, _ = run_gpu(N, session, "rgb24", [(np.ascontiguousarray(rgb[:, :3840]), None)], 3840, h, want_depth=False)
     assert np.array_equal(sc.planes[0][:, :3840], left.planes[0][:, :3840])
     assert np.array_equal(sc.planes[1][:, :1920], left.planes[1][:, :1920])
+
+
+def test_cpp_shim_process_frame(N, O, port, glyphs, tmp_path):
+    """The reference's process_frame_thread body (encode.cpp:55-98) compiled in C++ against
+    include/nes_gpu_shim.hpp: wire bytes -> RenderedFrame -> 4 overlays -> convert_frame()."""
+    import subprocess
+    from conftest import FONT
+    from test_host import build_process_frame
+    if N.find_freetype() is None:
+        pytest.skip("no FreeType binary in this image")
+    exe = build_process_frame(tmp_path)
+    w, h = 1280, 720
+    rgb, dep = O.synth_rgb(w, h, 9), O.synth_depth(w, h, 9)
+    (tmp_path / "m.bin").write_bytes(O.pack_rendered_frame(9, False, w, h, O.KINITIAL_CAMERA_MATRIX, rgb.tobytes(), dep.tobytes()))
+    r = subprocess.run([exe, str(tmp_path / "m.bin"), FONT, N.find_freetype(), str(w), str(h), "12:34:56.789", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == "ok index=9 left=0"
+    surf = np.ascontiguousarray(rgb.copy())
+    for pos, txt in O.reference_strings(index=9, is_left=False):
+        port.render_string(surf, pos, txt, glyphs)
+    want_s, want_d = port.rgb_to_yuv420p(surf, "rgb24").cropped(), port.gray_to_yuv420p(dep).cropped()
+    assert (tmp_path / "o.scene.yuv").read_bytes() == want_s
+    assert (tmp_path / "o.depth.yuv").read_bytes() == want_d
+    assert (tmp_path / "o.sws.yuv").read_bytes() == want_s

@@ -1,0 +1,93 @@
+"""CPU tests of the host side: C++ shim compiles against the C ABI, session sharding across
+ranks (world_size 2 over gloo), bench.py's reference arm prints a well-formed line."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_process_frame(tmp_path):
+    exe = str(tmp_path / "process_frame")
+    lib_dir = os.path.join(ROOT, "ngp-encode-server_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "process_frame.cpp"),
+                    "-o", exe, "-L", lib_dir, "-l:libnes_gpu.so", f"-Wl,-rpath,{lib_dir}"], check=True)
+    return exe
+
+
+def test_cpp_shim_compiles_and_fails_loudly_without_gpu(N, O, tmp_path):
+    """include/nes_gpu_shim.hpp + the reference's process_frame_thread body compile and link against
+    libnes_gpu.so; without a GPU the run must fail with an error (no CPU fallback), after the
+    host-only parts (FreeType rasterise, wire unpack) succeeded."""
+    exe = build_process_frame(tmp_path)
+    if N.device_count() > 0 or N.find_freetype() is None:
+        pytest.skip("needs a GPU-less box with FreeType")
+    msg = O.pack_rendered_frame(3, True, 64, 32, O.KINITIAL_CAMERA_MATRIX, O.synth_rgb(64, 32).tobytes(), O.synth_depth(64, 32).tobytes())
+    (tmp_path / "m.bin").write_bytes(msg)
+    r = subprocess.run([exe, str(tmp_path / "m.bin"), os.path.join(ROOT, "tests", "golden", "Aileron-Regular.ttf"), N.find_freetype(), "64", "32", "12:34:56.789", str(tmp_path / "o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "CUDA error" in r.stderr, (r.returncode, r.stderr)
+    # truncated payload: rejected by the shim before any GPU work (the reference would read out of bounds)
+    bad = O.pack_rendered_frame(3, True, 64, 32, O.KINITIAL_CAMERA_MATRIX, b"x" * 100, b"y" * 10)
+    (tmp_path / "b.bin").write_bytes(bad)
+    r = subprocess.run([exe, str(tmp_path / "b.bin"), os.path.join(ROOT, "tests", "golden", "Aileron-Regular.ttf"), N.find_freetype(), "64", "32", "t", str(tmp_path / "o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "payload shorter" in r.stderr
+
+
+def test_shard_partition(N):
+    for world in (1, 2, 4, 8):
+        shards = [N.shard.sessions_of_rank(r, world, 64) for r in range(world)]
+        assert sorted(s for sh in shards for s in sh) == list(range(64))
+        assert all(len(sh) == 64 // world for sh in shards)
+        assert all(N.shard.device_for_session(s, world) == r for r, sh in enumerate(shards) for s in sh)
+    assert N.shard.aggregate_fps([100, 100], [1.0, 2.0]) == 100.0
+    with pytest.raises(ValueError):
+        N.shard.sessions_of_rank(2, 2, 64)
+
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, os.environ["NES_ROOT"])
+import torch, torch.distributed as dist
+import ngp_encode_server_b200 as n
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+mine = n.shard.sessions_of_rank(rank, world, 64)
+got = [None] * world
+dist.all_gather_object(got, mine)
+flat = sorted(s for sh in got for s in sh)
+t = n.shard.max_over_ranks(1.0 + rank, dist)     # slowest rank defines the step time
+frames = [len(sh) * 10 for sh in got]
+fps = n.shard.aggregate_fps(frames, [t] * world)
+dist.barrier()
+if rank == 0:
+    print(json.dumps({"ok": flat == list(range(64)), "t": t, "fps": fps, "world": world}))
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_gloo(tmp_path):
+    """The N>1 host path (shard plan, barrier, max-over-ranks) with two CPU processes over gloo."""
+    w = tmp_path / "worker.py"
+    w.write_text(WORKER)
+    env = dict(os.environ, NES_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29731", str(w)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d == {"ok": True, "t": 2.0, "fps": 640 / 2.0, "world": 2}
+
+
+def test_bench_reference_arm_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3", "--workload", "c2_1080p_2src_composite"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["config"]["workload"] == "c2_1080p_2src_composite" and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
