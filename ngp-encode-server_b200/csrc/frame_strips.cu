@@ -1,0 +1,775 @@
+// frame_strips.cu -- k_frame_strips: the fused same-size frame kernel (the hot kernel).
+//
+// Per frame, in ONE launch for a whole batch of frames:
+//   [depth-select composite of N sources] -> glyph stamp overlay -> Y (pointwise)
+//   + horizontally pair-summed chroma -> 8-tap vertical bicubic -> U,V planes, and the depth
+//   stream GRAY8 -> Y (range compression) with U = V = 128.
+// Arithmetic: libswscale's C path as driven by the reference
+// (/root/reference/src/base/video/type_managers.cc:143-155 via rendered_frame.h:24-33, after
+// the overlay of render_text.cc:81-110); integer spec in SURVEY.md Appendix A.2 / A.4.
+//
+// Shape of the kernel (HBM-bound u8/int32 streaming work, no tensor cores):
+//   * work unit = one SEGMENT (seg_rows output rows) of one 256-pixel column STRIP of one
+//     frame; persistent CTAs fetch units from a global counter;
+//   * a CTA walks its segment top to bottom in CHUNKS of chunk_rows source rows.  The chroma
+//     rows of the last 6 source rows of a chunk are carried to the next chunk in shared
+//     memory, so the 3+3 halo rows of the 8-tap vertical chroma filter are computed once
+//     per segment (6.7 % at 90 rows) instead of once per tile;
+//   * warp 8 is the PRODUCER: it describes the next chunk in shared memory (ChunkCtx: all
+//     pointers pre-offset, coefficients, row ranges) and stages the chunk's packed-pixel rows
+//     -- of every source, plus the depth rows when compositing -- with bulk async copies
+//     (cp.async.bulk -> SASS UBLKCP, completion on a "full" mbarrier), two stages deep; the
+//     8 CONSUMER warps release a stage through an "empty" mbarrier, so copies of chunk t+1
+//     (and t+2) overlap the arithmetic of chunk t and there is no CTA-wide barrier per chunk
+//     other than the one between the two phases;
+//   * phase A (static: warp w owns chunk rows w, w+8, ...): Y with two dp2a per pixel
+//     (coefficients doubled so that the result is byte 2 of the sum: three PRMT pack four
+//     pixels), pair-summed chroma with six (3-byte pixels, straight from the raw words, no
+//     unpacking) or eight (4-byte pixels) dp2a per pixel pair; the 14-bit chroma rows
+//     (u | v<<16) are written IN PLACE over the pixel row the warp has just consumed;
+//   * phase B (warp per chroma row): the taps [-58,-172,492,1786,1786,492,-172,-58]/4096 are
+//     symmetric and even: rows are pair-added on the packed words, the three small taps are
+//     dp2a on the packed word (no unpacking), the big one is one IMAD per channel;
+//   * the depth stream is pointwise: single-source depth is loaded to registers at the top
+//     of a chunk and consumed after phase A; composite depth comes out of the select.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_common.cuh"
+#include "nes_internal.h"
+
+namespace nes {
+
+namespace {
+
+enum { MODE_ROWS = 0, MODE_SELECT = 1, MODE_MATERIALIZED = 2 };
+
+// Everything the consumer warps need to know about one chunk, written to shared memory by
+// lane 0 of the producer warp while earlier chunks are being computed (no consumer reads the
+// job descriptor from global memory on the critical path).  Plane pointers are pre-offset
+// to the strip.
+struct ChunkCtx {
+  int32_t last;    // last chunk this CTA processes
+  int32_t mode;    // MODE_*
+  int32_t tma;     // rows were staged by bulk copies (else the consumers fill them)
+  int32_t stamp;   // a glyph may intersect this chunk
+  int32_t n_src, job, ch;
+  int32_t x0, tw;
+  int32_t yc0;     // frame row of chunk-local row 0 (negative above the frame)
+  int32_t ra, rb;  // staged source rows [ra, rb)
+  int32_t ya, yb;  // luma rows to emit [ya, yb)
+  int32_t cA, cB;  // chroma rows to emit [cA, cB)
+  int32_t H;
+  int32_t edge;    // a vertical tap of [cA, cB) is clamped at the frame border
+  int32_t carry;   // the segment continues: keep the last CARRY_ROWS chroma rows
+  int32_t vec_in, vec_out, a_shift, rgb_base, depth_regs;
+  uint32_t ky[4], ku[3], kv[3];
+  int32_t sys, sus, svs, dys, dus, dvs;
+  uint8_t *sy, *su, *sv, *dy, *du, *dv;  // + strip column offset
+  const uint8_t *rgb[NES_MAX_SOURCES];   // + strip column offset
+  const uint8_t *dep[NES_MAX_SOURCES];
+  int32_t rs[NES_MAX_SOURCES], ds[NES_MAX_SOURCES];
+};
+
+template <int BPP>
+struct StripSmem {
+  static constexpr int ROWB = STRIP_W * BPP;
+  static constexpr int PX_BYTES = (CARRY_ALLOC + CHUNK_ROWS_MAX) * ROWB;
+  static constexpr int DEP_BYTES = BPP == 4 ? CHUNK_ROWS_MAX * STRIP_W : 0;  // composite staging (4-byte pixels only)
+  static constexpr int STAGE = PX_BYTES + DEP_BYTES;
+  static constexpr int OFF_CTX = 2 * STAGE;
+  static constexpr int OFF_BAR = OFF_CTX + 2 * (((int)sizeof(ChunkCtx) + 15) & ~15);
+  static constexpr int OFF_HITS = OFF_BAR + 32;
+  static constexpr int TOTAL = OFF_HITS + HIT_CAP * 4 + 16;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk async copy (TMA engine, no tensor map), completes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// explicit shared-space accesses (32-bit shared addresses; keeps the hot loops off generic LD/ST)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t x) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// barrier among the consumer warps only (the producer warp never joins)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * CONSUMER_WARPS) : "memory"); }
+
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1   (a: signed 16-bit halves, b: unsigned bytes)
+__device__ __forceinline__ int dp2a_lo(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// d = c + a.lo16 * b.byte2 + a.hi16 * b.byte3
+__device__ __forceinline__ int dp2a_hi(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// the same with unsigned 16-bit halves (luma coefficients doubled: 2*16519 > 32767)
+__device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi_uu(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// a: unsigned 16-bit halves (packed chroma pair sums), b: SIGNED bytes (small filter taps)
+__device__ __forceinline__ int dp2a_lo_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// max(min(v, 255), 0) in one instruction
+__device__ __forceinline__ uint32_t clip8_relu(int v) {
+  int d;
+  asm("min.s32.relu %0, %1, %2;" : "=r"(d) : "r"(v), "r"(255));
+  return (uint32_t)d;
+}
+// bytes 2 of four sums -> one word (the doubled luma sums carry Y in byte 2, byte 3 is 0)
+__device__ __forceinline__ uint32_t pack_b2(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3) {
+  return __byte_perm(__byte_perm(s0, s1, 0x0062), __byte_perm(s2, s3, 0x0062), 0x5410);
+}
+
+// GRAY8 -> limited-range luma for the 4 bytes of a word:
+//   Y = (d*219 + 127)/255 + 16, two pixels per multiply in 16-bit lanes;
+//   floor(t/255) == (t + (t >> 8) + 1) >> 8 for every t = d*219 + 127, d in 0..255
+__device__ __forceinline__ uint32_t gray_y4_packed(uint32_t w) {
+  const uint32_t p01 = __byte_perm(w, 0u, 0x4140), p23 = __byte_perm(w, 0u, 0x4342);  // d0 | d1<<16 ; d2 | d3<<16
+  const uint32_t t01 = p01 * 219u + 0x007F007Fu, t23 = p23 * 219u + 0x007F007Fu;
+  const uint32_t s01 = t01 + __byte_perm(t01, 0u, 0x4341) + 0x10011001u;  // + (t>>8) + 1 + (16<<8) per lane
+  const uint32_t s23 = t23 + __byte_perm(t23, 0u, 0x4341) + 0x10011001u;
+  return __byte_perm(s01, s23, 0x7531);  // byte 1 of every 16-bit lane
+}
+
+// pair-summed chroma of a horizontal pixel pair -> packed 14-bit (u | v<<16); su, sv include C_BIAS
+__device__ __forceinline__ uint32_t pack_uv14(int su, int sv) { return ((uint32_t)su >> 10) | (((uint32_t)sv << 6) & 0xFFFF0000u); }
+
+// store 4 (or 8) output bytes at column x of a row that holds tw valid columns
+__device__ __forceinline__ void store4(uint8_t *row, int x, uint32_t w, int tw, bool vec) {
+  if (vec && x + 4 <= tw) *(uint32_t *)(row + x) = w;
+  else
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (x + k < tw) row[x + k] = (uint8_t)(w >> (8 * k));
+}
+__device__ __forceinline__ void store8(uint8_t *row, int x, uint32_t w0, uint32_t w1, int tw, bool vec) {
+  if (vec && x + 8 <= tw) *(uint2 *)(row + x) = make_uint2(w0, w1);
+  else { store4(row, x, w0, tw, false); store4(row, x + 4, w1, tw, false); }
+}
+
+// Which job of this kernel's bpp class does work unit `u` belong to (unit_base is a prefix
+// sum over the batch in which the jobs of the other class take no units): the last job
+// whose base is <= u.
+__device__ __forceinline__ int job_of_unit(const DevJob *jobs, int n_jobs, int cls, int u) {
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].unit_base[cls] <= u) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// Depth-select composite of the 8 pixels a lane owns in a chunk row (4 at column 4*lane, 4 at
+// 128 + 4*lane) from the N staged sources: the winner's pixel words and depth bytes.
+// Semantics: DESIGN.md "composite" / oracle/overlay_port.c nes_oracle_composite.
+template <int ROWB>
+__device__ __forceinline__ void select_staged(uint32_t px0, uint32_t dep0, int r, int ch, int n_src, int ash, int lane,
+                                              uint32_t (&p)[8], uint32_t (&d4)[2]) {
+  uint32_t bd[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { p[i] = 0; bd[i] = 256; }
+#pragma unroll
+  for (int k = 0; k < NES_MAX_SOURCES; k++) {
+    if (k >= n_src) break;
+    const uint32_t rp = px0 + (uint32_t)(k * ch + r) * ROWB + lane * 16;
+    const uint32_t dp = dep0 + (uint32_t)(k * ch + r) * STRIP_W + lane * 4;
+    const uint4 q[2] = {lds128(rp), lds128(rp + 512)};
+    const uint32_t dw[2] = {lds32(dp), lds32(dp + 128)};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const uint32_t w[4] = {q[h].x, q[h].y, q[h].z, q[h].w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t d = (dw[h] >> (8 * i)) & 255u;
+        const bool take = ((w[i] >> ash) & 255u) != 0 && d < bd[4 * h + i];
+        bd[4 * h + i] = take ? d : bd[4 * h + i];
+        p[4 * h + i] = take ? w[i] : p[4 * h + i];
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++)
+    d4[h] = min(bd[4 * h], 255u) | (min(bd[4 * h + 1], 255u) << 8) | (min(bd[4 * h + 2], 255u) << 16) | (min(bd[4 * h + 3], 255u) << 24);
+}
+
+// Glyph stamp into the staged rows of source 0 (consumer warps only).  Reference semantics
+// (render_text.cc:94-106): every bitmap pixel with coverage != 0 inside the frame becomes
+// (255,255,255).  All stamps write the same value: overlapping glyphs are order-free.
+template <int BPP>
+__device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *rows, int x0, int x1, int yc0, int ra, int rb, int rgb_base,
+                                            int *s_hits, int *s_nhits) {
+  constexpr int ROWB = STRIP_W * BPP;
+  constexpr int NT = 32 * CONSUMER_WARPS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int base = 0; base < jb.n_glyphs; base += HIT_CAP) {
+    if (tid == 0) *s_nhits = 0;
+    consumer_sync();
+    for (int g = base + tid; g < min(base + HIT_CAP, jb.n_glyphs); g += NT) {
+      const DevPlaced pg = jb.glyphs[g];
+      if (pg.x < x1 && pg.x + pg.w > x0 && pg.y < rb && pg.y + pg.h > ra) s_hits[atomicAdd(s_nhits, 1)] = g;
+    }
+    consumer_sync();
+    const int nh = *s_nhits;
+    for (int h = warp; h < nh; h += CONSUMER_WARPS) {
+      const DevPlaced pg = jb.glyphs[s_hits[h]];
+      const uint8_t *cov = jb.atlas + pg.atlas_off;
+      const int q0 = max(0, ra - pg.y), q1 = min(pg.h, rb - pg.y);
+      const int p0 = max(0, x0 - pg.x), p1 = min(pg.w, x1 - pg.x);
+      for (int q = q0; q < q1; q++)
+        for (int p = p0 + lane; p < p1; p += 32)
+          if (cov[q * pg.pitch + p]) {
+            uint8_t *px = rows + (pg.y + q - yc0) * ROWB + (pg.x + p - x0) * BPP + (BPP == 4 ? rgb_base : 0);
+            px[0] = 255; px[1] = 255; px[2] = 255;
+          }
+    }
+    consumer_sync();
+  }
+}
+
+}  // namespace
+
+template <int BPP>
+__global__ void __launch_bounds__(CTA_THREADS, BPP == 3 ? 3 : 2)
+k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  using L = StripSmem<BPP>;
+  constexpr int ROWB = L::ROWB;
+  constexpr int CLS = BPP - 3;
+  constexpr int NW = CONSUMER_WARPS;
+  ChunkCtx *s_ctx = (ChunkCtx *)(smem + L::OFF_CTX);
+  uint64_t *s_full = (uint64_t *)(smem + L::OFF_BAR);  // [2]
+  uint64_t *s_empty = s_full + 2;                       // [2]
+  int *s_hits = (int *)(smem + L::OFF_HITS);
+  int *s_nhits = s_hits + HIT_CAP;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (tid == 0) {
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(&s_empty[0], NW);
+    mbar_init(&s_empty[1], NW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // =========================== producer warp ===========================================
+    // the first unit is static (grid <= total_units: every CTA has work), the rest come from a
+    // global counter
+    int cur_u = blockIdx.x, next_u = 0;
+    if (lane == 0) next_u = (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
+    next_u = __shfl_sync(0xffffffffu, next_u, 0);
+    int it = 0;
+    while (cur_u < total_units) {
+      // ---- unit geometry (all lanes compute it: cheap, keeps the copy loop uniform) ---------
+      const int j = job_of_unit(jobs, n_jobs, CLS, cur_u);
+      const DevJob *jp = jobs + j;
+      const int local = cur_u - jp->unit_base[CLS];
+      const int strip = local % jp->strips_x, seg = local / jp->strips_x;
+      const int W = jp->W, H = jp->H, S = jp->seg_rows, ch = jp->chunk_rows, n_src = jp->n_src;
+      const int x0 = strip * STRIP_W, tw = min(STRIP_W, W - x0);
+      const int Y0 = seg * S, Y1 = min(Y0 + S, H);
+      const int L0 = Y0 - HALO, need_end = min(Y1 + HALO, H);
+      const int nchunks = (need_end - L0 + ch - 1) / ch;
+      const int tma = jp->tma_ok;
+      const int staged_composite = tma && n_src > 1;
+      const int nbands = (H + (1 << MASK_BAND_SHIFT) - 1) >> MASK_BAND_SHIFT;
+      for (int k = 0; k < nchunks; k++, it++) {
+        const int b = it & 1;
+        if (it >= 2) mbar_wait(&s_empty[b], (uint32_t)((it >> 1) - 1) & 1u);
+        const int yc0 = L0 + k * ch;
+        const int ra = max(yc0, 0), rb = min(yc0 + ch, need_end);
+        const bool last_k = (k == nchunks - 1);
+        if (lane == 0) {
+          ChunkCtx &c = s_ctx[b];
+          int stamp = 0;
+          if (jp->n_glyphs > 0) {
+            stamp = 1;
+            if (jp->use_mask) {
+              stamp = 0;
+              for (int band = ra >> MASK_BAND_SHIFT; band <= (rb - 1) >> MASK_BAND_SHIFT && band < nbands; band++) {
+                const int bit = band * jp->strips_x + strip;
+                stamp |= (jp->tile_mask[bit >> 5] >> (bit & 31)) & 1u;
+              }
+            }
+          }
+          c.last = last_k && next_u >= total_units;
+          c.tma = tma;
+          c.stamp = stamp;
+          c.mode = staged_composite ? (stamp ? MODE_MATERIALIZED : MODE_SELECT) : MODE_ROWS;
+          c.n_src = n_src; c.job = j; c.ch = ch;
+          c.x0 = x0; c.tw = tw; c.yc0 = yc0; c.ra = ra; c.rb = rb;
+          c.ya = max(ra, Y0); c.yb = min(rb, Y1);
+          const int cA = (k == 0) ? (Y0 >> 1) : (Y0 >> 1) + ((k * ch) >> 1) - 3;
+          const int cB = last_k ? (Y1 >> 1) : (Y0 >> 1) + (((k + 1) * ch) >> 1) - 3;
+          c.cA = cA; c.cB = cB; c.H = H;
+          c.edge = (2 * cA - 3 < 0) || (2 * (cB - 1) + 4 > H - 1);
+          c.carry = !last_k;
+          c.vec_in = jp->in_vec; c.vec_out = jp->out_vec;
+          c.a_shift = jp->a_off > 0 ? 8 * jp->a_off : 0;
+          c.rgb_base = jp->rgb_base;
+          c.depth_regs = jp->dy && n_src == 1 && jp->in_vec && jp->out_vec && (tw & 7) == 0;
+          if (BPP == 3) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) c.ky[i] = jp->ky3[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { c.ku[i] = jp->ku3[i]; c.kv[i] = jp->kv3[i]; }
+          } else {
+            c.ky[0] = jp->ky2[0]; c.ky[1] = jp->ky2[1];
+            c.ku[0] = jp->ku[0]; c.ku[1] = jp->ku[1]; c.kv[0] = jp->kv[0]; c.kv[1] = jp->kv[1];
+          }
+          c.sys = jp->sys; c.sus = jp->sus; c.svs = jp->svs; c.dys = jp->dys; c.dus = jp->dus; c.dvs = jp->dvs;
+          c.sy = jp->sy + x0; c.su = jp->su + (x0 >> 1); c.sv = jp->sv + (x0 >> 1);
+          c.dy = jp->dy ? jp->dy + x0 : nullptr;
+          c.du = jp->dy ? jp->du + (x0 >> 1) : nullptr;
+          c.dv = jp->dy ? jp->dv + (x0 >> 1) : nullptr;
+          for (int s = 0; s < n_src; s++) {
+            c.rgb[s] = jp->src[s].rgb + (size_t)x0 * BPP;
+            c.dep[s] = jp->src[s].depth ? jp->src[s].depth + x0 : nullptr;
+            c.rs[s] = jp->src[s].rgb_stride; c.ds[s] = jp->src[s].depth_stride;
+          }
+        }
+        __syncwarp();
+        if (tma) {
+          const uint32_t px0 = smem_base + b * L::STAGE + CARRY_ALLOC * ROWB;
+          const uint32_t dep0 = smem_base + b * L::STAGE + L::PX_BYTES;
+          const uint32_t rowb = (uint32_t)tw * BPP;
+          const int nrows = rb - ra;
+          uint32_t bytes = 0;
+          for (int s = 0; s < n_src; s++) {
+            const uint8_t *src = jp->src[s].rgb + (size_t)x0 * BPP;
+            const int stride = jp->src[s].rgb_stride;
+            for (int y = ra + lane; y < rb; y += 32) bulk_g2s(px0 + (uint32_t)(s * ch + (y - yc0)) * ROWB, src + (size_t)y * stride, rowb, &s_full[b]);
+            bytes += rowb * (uint32_t)nrows;
+            if (staged_composite) {
+              const uint8_t *dsrc = jp->src[s].depth + x0;
+              const int dstride = jp->src[s].depth_stride;
+              for (int y = ra + lane; y < rb; y += 32) bulk_g2s(dep0 + (uint32_t)(s * ch + (y - yc0)) * STRIP_W, dsrc + (size_t)y * dstride, (uint32_t)tw, &s_full[b]);
+              bytes += (uint32_t)tw * (uint32_t)nrows;
+            }
+          }
+          if (lane == 0) mbar_arrive_expect_tx(&s_full[b], bytes);
+        } else if (lane == 0) {
+          mbar_arrive(&s_full[b]);  // nothing in flight: the consumers fill the rows themselves
+        }
+      }
+      cur_u = next_u;
+      if (lane == 0 && cur_u < total_units) next_u = (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
+      next_u = __shfl_sync(0xffffffffu, next_u, 0);
+    }
+    // the last CTA to run out of work re-arms the counters for the next launch on this stream
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) { counters[0] = 0; counters[1] = 0; __threadfence(); }
+    }
+    return;
+  }
+
+  // ============================= consumer warps ===========================================
+  for (int it = 0;; it++) {
+    const int cur = it & 1;
+    mbar_wait(&s_full[cur], (uint32_t)(it >> 1) & 1u);
+    const ChunkCtx &c = s_ctx[cur];
+    const int last = c.last;
+    {
+      const uint32_t stage = smem_base + cur * L::STAGE;
+      const uint32_t px0 = stage + CARRY_ALLOC * ROWB;  // chunk-local row 0 of source 0
+      const uint32_t dep0 = stage + L::PX_BYTES;
+      uint8_t *const rows0 = smem + cur * L::STAGE + CARRY_ALLOC * ROWB;
+      const int x0 = c.x0, tw = c.tw, yc0 = c.yc0, ra = c.ra, rb = c.rb, ya = c.ya, yb = c.yb, ch = c.ch;
+      const int n_src = c.n_src;
+      const int mode = c.mode;
+      const bool vec_out = c.vec_out != 0;
+      uint8_t *const dy = c.dy;
+      const int dys = c.dys;
+
+      // ---- depth loads of a single-source chunk (consumed after phase A) -------------------
+      constexpr int RPW = CHUNK_ROWS_MAX / NW;  // rows per warp
+      uint2 dreg[RPW];
+      const bool depth_regs = c.depth_regs != 0;  // CTA-uniform
+      const bool depth_lane = depth_regs && lane * 8 < tw;
+      if (depth_lane) {
+        const uint8_t *dsrc = c.dep[0] + lane * 8;
+        const int dstride = c.ds[0];
+#pragma unroll
+        for (int i = 0; i < RPW; i++) {
+          const int y = yc0 + warp + i * NW;
+          if (y >= ya && y < yb) dreg[i] = __ldg((const uint2 *)(dsrc + y * dstride));
+        }
+      }
+
+      // ---- fill the rows ourselves when they were not staged by bulk copies ----------------
+      if (!c.tma) {
+        for (int y = ra + warp; y < rb; y += NW) {
+          uint8_t *s = rows0 + (y - yc0) * ROWB;
+          if (n_src == 1) {
+            const uint8_t *g = c.rgb[0] + (size_t)y * c.rs[0];
+            const int nbytes = tw * BPP;
+            for (int i = lane; i < nbytes; i += 32) s[i] = g[i];
+          } else {
+            const bool core = (y >= ya) && (y < yb);
+            const DevJob &jb = jobs[c.job];
+            for (int x = lane; x < tw; x += 32) {
+              uint32_t d;
+              composite_px<BPP>(jb, x0 + x, y, s + x * BPP, &d);
+              if (core && dy) dy[(size_t)y * dys + x] = (uint8_t)gray_y(d);
+            }
+          }
+        }
+        consumer_sync();
+      }
+      // ---- staged composite under text: materialise the select into source 0's rows ----------
+      if (BPP == 4 && mode == MODE_MATERIALIZED) {
+        for (int r = warp; r < ch; r += NW) {
+          const int y = yc0 + r;
+          if (y < ra || y >= rb) continue;
+          uint32_t p[8], d4[2];
+          select_staged<ROWB>(px0, dep0, r, ch, n_src, c.a_shift, lane, p, d4);
+          __syncwarp();
+          sts128(px0 + r * ROWB + lane * 16, p[0], p[1], p[2], p[3]);
+          sts128(px0 + r * ROWB + 512 + lane * 16, p[4], p[5], p[6], p[7]);
+          sts32(dep0 + r * STRIP_W + lane * 4, d4[0]);
+          sts32(dep0 + r * STRIP_W + 128 + lane * 4, d4[1]);
+        }
+      }
+      // ---- text overlay, stamped into the staged rows of source 0 ----------------------------
+      if (c.stamp) {
+        stamp_chunk<BPP>(jobs[c.job], rows0, x0, x0 + tw, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
+      }
+
+      // ---- phase A: per source row: Y out, pair-summed chroma (u14 | v14<<16) in place --------
+      {
+        uint8_t *const sy = c.sy;
+        const int sys = c.sys;
+#pragma unroll 1
+        for (int i = 0; i < RPW; i++) {
+          const int r = warp + i * NW;
+          const int y = yc0 + r;
+          if (r >= ch || y < ra || y >= rb) continue;
+          const uint32_t row = px0 + r * ROWB;
+          const bool core = (y >= ya) && (y < yb);
+          uint32_t uv[4];
+          uint32_t yw0 = 0, yw1 = 0;
+          if (BPP == 3) {
+            // lane owns pixels 8*lane .. 8*lane+7 = 6 raw words (8-byte loads at 24-byte stride are
+            // conflict free); the coefficient pairs are laid out per byte phase, so nothing is unpacked
+            const uint2 a = lds64(row + lane * 24), b = lds64(row + lane * 24 + 8), d = lds64(row + lane * 24 + 16);
+            const uint32_t w[6] = {a.x, a.y, b.x, b.y, d.x, d.y};
+            __syncwarp();  // every lane has read its pixels before anyone overwrites the row
+            const uint32_t u01 = c.ku[0], u20 = c.ku[1], u12 = c.ku[2], v01 = c.kv[0], v20 = c.kv[1], v12 = c.kv[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const uint32_t w0 = w[3 * h], w1 = w[3 * h + 1], w2 = w[3 * h + 2];
+              const int su0 = dp2a_lo(u12, w1, dp2a_hi(u20, w0, dp2a_lo(u01, w0, C_BIAS)));
+              const int sv0 = dp2a_lo(v12, w1, dp2a_hi(v20, w0, dp2a_lo(v01, w0, C_BIAS)));
+              const int su1 = dp2a_hi(u12, w2, dp2a_lo(u20, w2, dp2a_hi(u01, w1, C_BIAS)));
+              const int sv1 = dp2a_hi(v12, w2, dp2a_lo(v20, w2, dp2a_hi(v01, w1, C_BIAS)));
+              uv[2 * h] = pack_uv14(su0, sv0);
+              uv[2 * h + 1] = pack_uv14(su1, sv1);
+            }
+            sts128(row + lane * 16, uv[0], uv[1], uv[2], uv[3]);  // chroma cols 4*lane..+3
+            if (core) {
+              const uint32_t y01 = c.ky[0], y2_ = c.ky[1], y_0 = c.ky[2], y12 = c.ky[3];
+              uint32_t s[8];
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const uint32_t w0 = w[3 * h], w1 = w[3 * h + 1], w2 = w[3 * h + 2];
+                s[4 * h] = dp2a_hi_uu(y2_, w0, dp2a_lo_uu(y01, w0, 2 * Y_BIAS));
+                s[4 * h + 1] = dp2a_lo_uu(y12, w1, dp2a_hi_uu(y_0, w0, 2 * Y_BIAS));
+                s[4 * h + 2] = dp2a_lo_uu(y2_, w2, dp2a_hi_uu(y01, w1, 2 * Y_BIAS));
+                s[4 * h + 3] = dp2a_hi_uu(y12, w2, dp2a_lo_uu(y_0, w2, 2 * Y_BIAS));
+              }
+              yw0 = pack_b2(s[0], s[1], s[2], s[3]);
+              yw1 = pack_b2(s[4], s[5], s[6], s[7]);
+              store8(sy + y * sys, lane * 8, yw0, yw1, tw, vec_out);
+            }
+          } else {
+            // lane owns pixels 4*lane..+3 and 128+4*lane..+3 (16-byte accesses at 16-byte stride)
+            uint32_t p[8];
+            uint32_t d4[2];
+            if (mode == MODE_SELECT) {
+              select_staged<ROWB>(px0, dep0, r, ch, n_src, c.a_shift, lane, p, d4);
+            } else {
+              const uint4 a = lds128(row + lane * 16), b = lds128(row + 512 + lane * 16);
+              p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+              if (mode == MODE_MATERIALIZED) { d4[0] = lds32(dep0 + r * STRIP_W + lane * 4); d4[1] = lds32(dep0 + r * STRIP_W + 128 + lane * 4); }
+            }
+            __syncwarp();
+            const uint32_t kua = c.ku[0], kub = c.ku[1], kva = c.kv[0], kvb = c.kv[1];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              int su = dp2a_lo(kua, p[2 * j], C_BIAS); su = dp2a_hi(kub, p[2 * j], su);
+              su = dp2a_lo(kua, p[2 * j + 1], su); su = dp2a_hi(kub, p[2 * j + 1], su);
+              int sv = dp2a_lo(kva, p[2 * j], C_BIAS); sv = dp2a_hi(kvb, p[2 * j], sv);
+              sv = dp2a_lo(kva, p[2 * j + 1], sv); sv = dp2a_hi(kvb, p[2 * j + 1], sv);
+              uv[j] = pack_uv14(su, sv);
+            }
+            sts64(row + lane * 8, uv[0], uv[1]);        // chroma cols 2*lane, 2*lane+1
+            sts64(row + 256 + lane * 8, uv[2], uv[3]);  // chroma cols 64+2*lane, +1
+            if (core) {
+              const uint32_t kya = c.ky[0], kyb = c.ky[1];
+              uint32_t s[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++) s[k] = dp2a_hi_uu(kyb, p[k], dp2a_lo_uu(kya, p[k], 2 * Y_BIAS));
+              yw0 = pack_b2(s[0], s[1], s[2], s[3]);
+              yw1 = pack_b2(s[4], s[5], s[6], s[7]);
+              uint8_t *o = sy + y * sys;
+              store4(o, lane * 4, yw0, tw, vec_out);
+              store4(o, 128 + lane * 4, yw1, tw, vec_out);
+              if (mode != MODE_ROWS && dy) {
+                uint8_t *od = dy + y * dys;
+                store4(od, lane * 4, gray_y4_packed(d4[0]), tw, vec_out);
+                store4(od, 128 + lane * 4, gray_y4_packed(d4[1]), tw, vec_out);
+              }
+            }
+          }
+        }
+      }
+
+      // ---- depth stream of a single source: Y = range-compressed gray -------------------------
+      if (dy && n_src == 1) {
+        if (depth_regs) {
+          if (depth_lane) {
+            uint8_t *o = dy + lane * 8;
+#pragma unroll
+            for (int i = 0; i < RPW; i++) {
+              const int y = yc0 + warp + i * NW;
+              if (y >= ya && y < yb) *(uint2 *)(o + y * dys) = make_uint2(gray_y4_packed(dreg[i].x), gray_y4_packed(dreg[i].y));
+            }
+          }
+        } else {
+          const uint8_t *dsrc = c.dep[0];
+          const int dstride = c.ds[0];
+          for (int y = ya + warp; y < yb; y += NW)
+            for (int x = lane; x < tw; x += 32) dy[(size_t)y * dys + x] = (uint8_t)gray_y(dsrc[(size_t)y * dstride + x]);
+        }
+      }
+      consumer_sync();
+
+      // ---- phase B: 8-tap vertical bicubic on chroma; edge taps fold = clamped row index ------
+      // T/2 = [-29,-86,246,893,893,246,-86,-29] on 14-bit samples, out = (2^16 + sum) >> 17:
+      // the symmetric rows are added on the packed words first (2*15360 < 32768: no carry), the
+      // small taps are dp2a on the packed word (bytes (t,0,0,t): .lo picks u, .hi picks v;
+      // 246 = 2*123 on the doubled sum), the big one is one IMAD per channel.
+      {
+        const int cc = lane * 4;  // chroma column inside the strip
+        const int cw = tw >> 1;
+        uint8_t *const su_ = c.su, *const sv_ = c.sv;
+        const int sus = c.sus, svs = c.svs;
+        uint8_t *const du = c.du, *const dv = c.dv;
+        const int dus = c.dus, dvs = c.dvs;
+        const int cA = c.cA, cB = c.cB, H = c.H;
+        const bool edge = c.edge != 0;
+        const uint32_t col = px0 + cc * 4;
+        if (cc < cw) {
+#pragma unroll 1
+          for (int ci = cA + warp; ci < cB; ci += NW) {
+            uint32_t t[8][4];
+            if (!edge) {
+              const uint32_t base = col + (uint32_t)((2 * ci - 3 - yc0) * ROWB);
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const uint4 q = lds128(base + j * ROWB);
+                t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const int sr = min(max(2 * ci - 3 + j, 0), H - 1) - yc0;
+                const uint4 q = lds128(col + (uint32_t)(sr * ROWB));
+                t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
+              }
+            }
+            uint32_t us[4], vs[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const uint32_t a07 = t[0][k] + t[7][k], a16 = t[1][k] + t[6][k], a25 = (t[2][k] + t[5][k]) * 2u, a34 = t[3][k] + t[4][k];
+              int au = dp2a_lo_us(a07, 0xE30000E3u, 1 << 16);  // -29
+              au = dp2a_lo_us(a16, 0xAA0000AAu, au);           // -86
+              au = dp2a_lo_us(a25, 0x7B00007Bu, au);           // 123 * 2
+              au += 893 * (int)(a34 & 0xFFFFu);
+              int av = dp2a_hi_us(a07, 0xE30000E3u, 1 << 16);
+              av = dp2a_hi_us(a16, 0xAA0000AAu, av);
+              av = dp2a_hi_us(a25, 0x7B00007Bu, av);
+              av += 893 * (int)(a34 >> 16);
+              us[k] = clip8_relu(au >> 17);
+              vs[k] = clip8_relu(av >> 17);
+            }
+            const uint32_t ub = __byte_perm(__byte_perm(us[0], us[1], 0x0040), __byte_perm(us[2], us[3], 0x0040), 0x5410);
+            const uint32_t vb = __byte_perm(__byte_perm(vs[0], vs[1], 0x0040), __byte_perm(vs[2], vs[3], 0x0040), 0x5410);
+            store4(su_ + ci * sus, cc, ub, cw, vec_out);
+            store4(sv_ + ci * svs, cc, vb, cw, vec_out);
+            if (dy) {  // depth chroma planes are constant 128
+              store4(du + ci * dus, cc, 0x80808080u, cw, vec_out);
+              store4(dv + ci * dvs, cc, 0x80808080u, cw, vec_out);
+            }
+          }
+        }
+        // the next chunk of this segment still needs the chroma of our last CARRY_ROWS rows
+        if (c.carry) {
+          const uint32_t from = px0 + (uint32_t)((ch - CARRY_ROWS) * ROWB);
+          const uint32_t to = smem_base + (cur ^ 1) * L::STAGE + (CARRY_ALLOC - CARRY_ROWS) * ROWB;
+#pragma unroll
+          for (int q = 0; q < (CARRY_ROWS * (STRIP_W / 2)) / (32 * NW); q++) {
+            const int idx = tid + q * 32 * NW;
+            const uint32_t off = (uint32_t)(idx >> 7) * ROWB + (uint32_t)(idx & 127) * 4;
+            sts32(to + off, lds32(from + off));
+          }
+        }
+      }
+    }
+    // release the stage: order our generic-proxy writes (in-place chroma, stamps) before the
+    // bulk copies that will refill it
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[cur]);
+    if (last) break;
+  }
+}
+
+static int g_ctas_per_sm[2] = {0, 0};
+static int g_num_sms = 0;
+
+int frame_strips_init() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_frame_strips<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripSmem<3>::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_frame_strips<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripSmem<4>::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas_per_sm[0], k_frame_strips<3>, CTA_THREADS, StripSmem<3>::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas_per_sm[1], k_frame_strips<4>, CTA_THREADS, StripSmem<4>::TOTAL);
+  if (e != cudaSuccess) return (int)e;
+  if (g_ctas_per_sm[0] < 1 || g_ctas_per_sm[1] < 1) return (int)cudaErrorLaunchOutOfResources;
+  return 0;
+}
+
+// Host-side planning of a launch: chunk height per job (by source count), one segment height
+// per bpp class (trade: 6 halo rows per segment against the one-unit tail of the persistent
+// grid), unit numbering.  Jobs of the other class (and general jobs) take no units.
+void plan_frame_strips(DevJob *jobs, int n_jobs) {
+  const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  for (int cls = 0; cls < 2; cls++) {
+    const int grid = sms * (g_ctas_per_sm[cls] > 0 ? g_ctas_per_sm[cls] : (cls == 0 ? 3 : 2));
+    int best_s = 26;
+    double best_cost = 1e30;
+    for (int S = 26; S <= 250; S += 32) {
+      double work = 0;
+      long units = 0;
+      for (int j = 0; j < n_jobs; j++) {
+        const DevJob &jb = jobs[j];
+        if (jb.general || jb.bpp != 3 + cls) continue;
+        const int strips = (jb.W + STRIP_W - 1) / STRIP_W, segs = (jb.H + S - 1) / S;
+        units += (long)strips * segs;
+        work += (double)strips * (jb.H + segs * 3.6);  // halo rows cost the chroma half of phase A
+      }
+      if (units == 0) break;
+      const double unit_cost = S + 3.6;
+      const double cost = units <= grid ? unit_cost : work / grid + 0.7 * unit_cost;
+      if (cost < best_cost - 1e-9) { best_cost = cost; best_s = S; }
+    }
+    int base = 0;
+    for (int j = 0; j < n_jobs; j++) {
+      DevJob &jb = jobs[j];
+      jb.unit_base[cls] = base;
+      if (jb.general || jb.bpp != 3 + cls) continue;
+      jb.chunk_rows = jb.n_src <= 1 ? 32 : (jb.n_src == 2 ? 16 : 8);
+      jb.seg_rows = best_s;
+      jb.strips_x = (jb.W + STRIP_W - 1) / STRIP_W;
+      jb.segs_y = (jb.H + best_s - 1) / best_s;
+      jb.n_units = jb.strips_x * jb.segs_y;
+      base += jb.n_units;
+    }
+  }
+}
+
+int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream) {
+  int total[2] = {0, 0};
+  for (int j = 0; j < n_jobs; j++) {
+    const DevJob &jb = jobs_host[j];
+    if (!jb.general) total[jb.bpp - 3] += jb.n_units;
+  }
+  int launches = 0;
+  if (total[0] > 0) {
+    const int grid = total[0] < g_num_sms * g_ctas_per_sm[0] ? total[0] : g_num_sms * g_ctas_per_sm[0];
+    k_frame_strips<3><<<grid, CTA_THREADS, StripSmem<3>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[0], counters);
+    launches++;
+  }
+  if (total[1] > 0) {
+    const int grid = total[1] < g_num_sms * g_ctas_per_sm[1] ? total[1] : g_num_sms * g_ctas_per_sm[1];
+    k_frame_strips<4><<<grid, CTA_THREADS, StripSmem<4>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[1], counters + 2);
+    launches++;
+  }
+  return launches;
+}
+
+}  // namespace nes

@@ -259,7 +259,7 @@ static int g_resize_smem_cap = 0;
 
 int kernels_init() {
   cudaError_t e;
-  if (int r = frame_tiles_init()) return r;
+  if (int r = frame_strips_init()) return r;
   g_resize_smem_cap = 200 * 1024;
   e = cudaFuncSetAttribute(k_resize_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, g_resize_smem_cap);
   if (e != cudaSuccess) return (int)e;

@@ -9,16 +9,21 @@
 
 namespace nes {
 
-// Same-size fused tile geometry (kernels.cu, k_frame_tiles): one CTA owns a
-// TILE_W x TILE_H block of source pixels and loads 3 halo rows above and below
-// for the 8-tap vertical chroma filter.
-constexpr int TILE_W = 256;
-constexpr int TILE_H = 30;  // divides 720/1080/1440/2160: no ragged last tile row
+// Same-size fused kernel geometry (frame_strips.cu, k_frame_strips).  A frame is cut into
+// column strips of STRIP_W pixels; a strip is cut into segments of `seg_rows` output rows
+// (one work unit = one segment of one strip); a CTA walks a segment top to bottom in chunks of
+// `chunk_rows` source rows, carrying the chroma rows the 8-tap vertical filter still needs
+// from chunk to chunk, so the 3+3 halo rows are paid once per segment, not once per chunk.
+constexpr int STRIP_W = 256;
 constexpr int HALO = 3;
-constexpr int TILE_ROWS = TILE_H + 2 * HALO;
-constexpr int CTA_THREADS = 256;
+constexpr int CHUNK_ROWS_MAX = 32;  // chunk_rows = 32 (1 source), 16 (2 sources), 8 (3-4 sources)
+constexpr int CARRY_ROWS = 6;       // chroma rows of the previous chunk the filter still reads
+constexpr int CARRY_ALLOC = 8;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int CTA_THREADS = 32 * (CONSUMER_WARPS + 1);  // + one producer warp (bulk copies, chunk contexts)
 constexpr int HIT_CAP = 256;  // glyph rect tests per overlay chunk
-constexpr int MASK_WORDS = 128;  // per-job bitmap of tiles touched by text (4096 tiles)
+constexpr int MASK_WORDS = 128;  // per-job bitmap: (32-row band, strip) cells touched by text
+constexpr int MASK_BAND_SHIFT = 5;
 
 // Resize tile geometry (k_resize_tiles): destination pixels per CTA.
 constexpr int RS_TILE_W = 64;
@@ -72,8 +77,17 @@ struct DevJob {
   int32_t tma_ok;     // single source, 16-byte aligned rows: tiles are staged with bulk async copies
   int32_t use_mask;   // tile_mask valid (tiles_x*tiles_y <= 32*MASK_WORDS)
   int32_t pad1;
-  uint32_t tile_mask[MASK_WORDS];  // bit t set: tile t (or its halo rows) intersects a placed glyph
-  int32_t tiles_x, tiles_y, tile_base;
+  uint32_t tile_mask[MASK_WORDS];  // bit (band * strips_x + strip) set: a placed glyph intersects that cell
+  int32_t tiles_x, tiles_y, tile_base;  // k_resize_tiles work (general jobs only; 0 tiles otherwise)
+  // k_frame_strips work (same-size jobs only)
+  int32_t strips_x, segs_y;
+  int32_t seg_rows;    // output rows per segment (even)
+  int32_t chunk_rows;  // source rows per chunk
+  int32_t unit_base[2];  // [bpp-3]: units of that bpp class ahead of this job in the batch
+  int32_t n_units;
+  // dp2a operands for packed 3-byte pixels read as raw words (frame_strips.cu phase A)
+  uint32_t ky3[4], ku3[3], kv3[3];
+  uint32_t ky2[2];     // luma coefficients x2, unsigned (4-byte pixels): Y lands in byte 2 of the sum
   // resize only
   DevFilter hl, hc, vl, vc;
   int32_t half;  // chroma horizontally pair-summed before the H pass
@@ -86,11 +100,13 @@ struct DevJob {
 };
 
 // Launchers (kernels.cu).  jobs: device pointer to n_jobs descriptors.
-int launch_frame_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
+int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream);
+// Assigns seg_rows / chunk_rows / unit_base of the same-size jobs of a launch (host).
+void plan_frame_strips(DevJob *jobs_host, int n_jobs);
 int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
 int launch_composite(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
 int kernels_init();  // opt-in shared memory sizes; returns cudaError_t
-int frame_tiles_init();
+int frame_strips_init();
 
 }  // namespace nes
 #endif

@@ -81,6 +81,7 @@ struct nes_gpu_session {
   uint64_t launches = 0;
   HostAtlas atlas;
   uint8_t *d_atlas = nullptr;
+  uint32_t *d_counters = nullptr;  // k_frame_strips work counters (self re-arming), [2] per bpp class
   std::map<std::tuple<int, int, int, int>, FilterSet> filters;
   nes_timing last{};
   std::string err;
@@ -284,38 +285,46 @@ void job_common(DevJob *jb, const nes_frame_in *in, const nes_frame_out *out, in
     k[c][0] = ((uint32_t)cb[c][0] & 0xFFFFu) | ((uint32_t)cb[c][1] << 16);
     k[c][1] = ((uint32_t)cb[c][2] & 0xFFFFu) | ((uint32_t)cb[c][3] << 16);
   }
+  // luma coefficients doubled and unsigned: Y comes out as byte 2 of the sum (frame_strips.cu)
+  jb->ky2[0] = ((uint32_t)(2 * cb[0][0]) & 0xFFFFu) | ((uint32_t)(2 * cb[0][1]) << 16);
+  jb->ky2[1] = ((uint32_t)(2 * cb[0][2]) & 0xFFFFu) | ((uint32_t)(2 * cb[0][3]) << 16);
+  if (bpp == 3) {
+    // 3-byte pixels are consumed as raw words: coefficient pairs per byte phase
+    auto pk = [](int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); };
+    const int *y = jb->cy, *u = jb->cu, *v = jb->cv;
+    jb->ky3[0] = pk(2 * y[0], 2 * y[1]); jb->ky3[1] = pk(2 * y[2], 0); jb->ky3[2] = pk(0, 2 * y[0]); jb->ky3[3] = pk(2 * y[1], 2 * y[2]);
+    jb->ku3[0] = pk(u[0], u[1]); jb->ku3[1] = pk(u[2], u[0]); jb->ku3[2] = pk(u[1], u[2]);
+    jb->kv3[0] = pk(v[0], v[1]); jb->kv3[1] = pk(v[2], v[0]); jb->kv3[2] = pk(v[1], v[2]);
+  }
   jb->W = in->width; jb->H = in->height; jb->Wd = out->width; jb->Hd = out->height;
 }
 
-// Bitmap of the fused kernel's tiles (incl. their halo rows) that a placed glyph touches, so
-// that every other tile skips the overlay stage without looking at the glyph list.
+// Bitmap of the (32-row band, strip) cells of the fused kernel that a placed glyph touches, so
+// that every other chunk skips the overlay stage without looking at the glyph list.
 void job_tile_mask(DevJob *jb, const DevPlaced *placed) {
   jb->use_mask = 0;
-  if (jb->general || jb->n_glyphs <= 0 || jb->tiles_x * jb->tiles_y > 32 * MASK_WORDS) return;
+  if (jb->general || jb->n_glyphs <= 0) return;
+  const int strips = (jb->W + STRIP_W - 1) / STRIP_W;
+  const int nbands = (jb->H + (1 << MASK_BAND_SHIFT) - 1) >> MASK_BAND_SHIFT;
+  if (strips * nbands > 32 * MASK_WORDS) return;
   std::memset(jb->tile_mask, 0, sizeof(jb->tile_mask));
   for (int g = 0; g < jb->n_glyphs; g++) {
     const DevPlaced &p = placed[g];
     const int x0 = std::max(p.x, 0), x1 = std::min(p.x + p.w, jb->W), y0 = std::max(p.y, 0), y1 = std::min(p.y + p.h, jb->H);
     if (x0 >= x1 || y0 >= y1) continue;
-    const int tx0 = x0 / TILE_W, tx1 = (x1 - 1) / TILE_W;
-    const int ty0 = std::max((y0 - HALO) / TILE_H - 1, 0), ty1 = std::min((y1 + HALO) / TILE_H + 1, jb->tiles_y - 1);
-    for (int ty = ty0; ty <= ty1; ty++) {
-      const int ra = ty * TILE_H - HALO, rb = ty * TILE_H + TILE_H + HALO;  // rows the tile stages
-      if (y0 >= rb || y1 <= ra) continue;
-      for (int tx = tx0; tx <= tx1; tx++) {
-        const int t = ty * jb->tiles_x + tx;
+    for (int band = y0 >> MASK_BAND_SHIFT; band <= (y1 - 1) >> MASK_BAND_SHIFT; band++)
+      for (int st = x0 / STRIP_W; st <= (x1 - 1) / STRIP_W; st++) {
+        const int t = band * strips + st;
         jb->tile_mask[t >> 5] |= 1u << (t & 31);
       }
-    }
   }
   jb->use_mask = 1;
 }
 
+// Resize tiles of the general jobs of a launch (the same-size jobs are planned by plan_frame_strips).
 void job_tiles(DevJob *jb, int tile_base) {
-  if (!jb->general) {
-    jb->tiles_x = (jb->W + TILE_W - 1) / TILE_W;
-    jb->tiles_y = (jb->H + TILE_H - 1) / TILE_H;
-  } else {
+  jb->tiles_x = jb->tiles_y = 0;
+  if (jb->general) {
     jb->tiles_x = (jb->Wd + RS_TILE_W - 1) / RS_TILE_W;
     jb->tiles_y = (jb->Hd + RS_TILE_H - 1) / RS_TILE_H;
   }
@@ -332,7 +341,8 @@ void job_alignment(DevJob *jb) {
   if (jb->dy) ov = ov && aligned16(jb->dy, jb->dys) && aligned16(jb->du, jb->dus) && aligned16(jb->dv, jb->dvs);
   jb->in_vec = iv;
   jb->out_vec = ov;
-  jb->tma_ok = iv && jb->n_src == 1 && (jb->W % 16) == 0;
+  // rows staged with bulk async copies: 16-byte aligned rows; composites only for 4-byte pixels
+  jb->tma_ok = iv && (jb->W % 16) == 0 && (jb->n_src == 1 || jb->bpp == 4);
 }
 
 // Text runs -> placed glyph descriptors at dst[0..].  Returns count or negative status.
@@ -358,7 +368,7 @@ int place_text(nes_gpu_session *s, int W, int H, const nes_text_run *runs, int n
 int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, int n, cudaStream_t st) {
   int l = 0;
   l += launch_composite(d_jobs, h_jobs, n, st);
-  l += launch_frame_tiles(d_jobs, h_jobs, n, st);
+  l += launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, st);
   const int r = launch_resize_tiles(d_jobs, h_jobs, n, st);
   if (r > 0) l += r;
   s->launches += (uint64_t)l;
@@ -417,6 +427,8 @@ int nes_gpu_session_create(const nes_gpu_cfg *cfg, nes_gpu_session **out) {
   if (cudaStreamCreateWithFlags(&s->st_in, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&s->st_k, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&s->st_out, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
+  if (cudaMalloc((void **)&s->d_counters, 4 * sizeof(uint32_t)) != cudaSuccess) return fail(NES_ERR_CUDA);
+  if (cudaMemset(s->d_counters, 0, 4 * sizeof(uint32_t)) != cudaSuccess) return fail(NES_ERR_CUDA);
   s->slots.resize((size_t)s->cfg.ring_depth);
   const size_t gl_bytes = (size_t)s->cfg.max_glyphs * sizeof(DevPlaced);
   for (Slot &sl : s->slots) {
@@ -454,6 +466,7 @@ void nes_gpu_session_destroy(nes_gpu_session *s) {
   }
   for (auto &kv : s->filters) cudaFree(kv.second.blob);
   cudaFree(s->d_atlas);
+  cudaFree(s->d_counters);
   if (s->st_in) cudaStreamDestroy(s->st_in);
   if (s->st_k) cudaStreamDestroy(s->st_k);
   if (s->st_out) cudaStreamDestroy(s->st_out);
@@ -699,6 +712,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   job_tiles(jb, 0);
   job_alignment(jb);
   job_tile_mask(jb, sl.h_glyphs);
+  plan_frame_strips(jb, 1);
 
   if (n_gl > 0) CU_TRY(s, cudaMemcpyAsync(sl.d_glyphs, sl.h_glyphs, (size_t)n_gl * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaMemcpyAsync(sl.d_job, sl.h_job, sizeof(DevJob), cudaMemcpyHostToDevice, s->st_in));
@@ -842,6 +856,7 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
     job_alignment(jb);
     job_tile_mask(jb, bt.h_glyphs + gl_used - n_gl);
   }
+  plan_frame_strips(bt.h_jobs, n_frames);
   // descriptor upload on the copy stream, so that it overlaps the kernels of the previous batch
   if (gl_used > 0) CU_TRY(s, cudaMemcpyAsync(bt.d_glyphs, bt.h_glyphs, (size_t)gl_used * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaMemcpyAsync(bt.d_jobs, bt.h_jobs, sizeof(DevJob) * n_frames, cudaMemcpyHostToDevice, s->st_in));
