@@ -403,7 +403,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload)
-    kernel = "k_resize_tiles" if (w != wd or h != hd) else f"k_frame_tiles<{bpp}>"
+    kernel = "k_resize_tiles" if (w != wd or h != hd) else f"k_frame_strips<{bpp}>"
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "kernel": kernel, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg * B, "launch_us": round(launch_s * 1e6, 2)}
 
