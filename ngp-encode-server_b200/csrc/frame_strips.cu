@@ -11,29 +11,32 @@
 // Shape of the kernel (HBM-bound u8/int32 streaming work, no tensor cores):
 //   * work unit = one SEGMENT (seg_rows output rows) of one 256-pixel column STRIP of one
 //     frame; persistent CTAs fetch units from a global counter;
-//   * a CTA walks its segment top to bottom in CHUNKS of chunk_rows source rows.  The chroma
-//     rows of the last 6 source rows of a chunk are carried to the next chunk in shared
-//     memory, so the 3+3 halo rows of the 8-tap vertical chroma filter are computed once
-//     per segment (6.7 % at 90 rows) instead of once per tile;
-//   * warp 8 is the PRODUCER: it describes the next chunk in shared memory (ChunkCtx: all
-//     pointers pre-offset, coefficients, row ranges) and stages the chunk's packed-pixel rows
-//     -- of every source, plus the depth rows when compositing -- with bulk async copies
-//     (cp.async.bulk -> SASS UBLKCP, completion on a "full" mbarrier), two stages deep; the
-//     8 CONSUMER warps release a stage through an "empty" mbarrier, so copies of chunk t+1
-//     (and t+2) overlap the arithmetic of chunk t and there is no CTA-wide barrier per chunk
-//     other than the one between the two phases;
-//   * phase A (static: warp w owns chunk rows w, w+8, ...): Y with two dp2a per pixel
-//     (coefficients doubled so that the result is byte 2 of the sum: three PRMT pack four
-//     pixels), pair-summed chroma with six (3-byte pixels, straight from the raw words, no
-//     unpacking) or eight (4-byte pixels) dp2a per pixel pair; the 14-bit chroma rows
-//     (u | v<<16) are written IN PLACE over the pixel row the warp has just consumed;
-//   * phase B (warp per chroma row): the taps [-58,-172,492,1786,1786,492,-172,-58]/4096 are
-//     symmetric and even: rows are pair-added on the packed words, the three small taps are
-//     dp2a on the packed word (no unpacking), the big one is one IMAD per channel;
-//   * the depth stream is pointwise: single-source depth is loaded to registers at the top
-//     of a chunk and consumed after phase A; composite depth comes out of the select.
+//   * a CTA walks its segment top to bottom in CHUNKS of 16 source rows;
+//   * source rows travel through a ring of 8-row SUB-STAGES in shared memory.  Warp 8 is the
+//     PRODUCER: per sub-stage it issues one 2D tensor-map TMA copy per staged plane
+//     (cp.async.bulk.tensor -> SASS UTMALDG: the packed pixels of every source and their GRAY8
+//     depth rows; rows outside the frame are zero-filled by the TMA unit) completing on the
+//     sub-stage's "full" mbarrier, and it describes every chunk in shared memory (ChunkCtx: all
+//     pointers pre-offset, coefficients, row ranges), so no consumer reads the job descriptor
+//     on the critical path.  The ring is 2-8 sub-stages deep (by source count), i.e. the loads
+//     run up to four chunks ahead of the arithmetic;
+//   * the 8 CONSUMER warps own one row of every sub-stage: phase A turns the row into Y (two
+//     dp2a per pixel, coefficients doubled so that the result is byte 2 of the sum) and into
+//     14-bit pair-summed chroma (u | v<<16; six dp2a per pixel pair straight from the raw words
+//     for 3-byte pixels, eight for 4-byte pixels) written to a separate CHROMA RING of 40 rows,
+//     then releases the sub-stage ("empty" mbarrier) at once -- the ring, not the stage, carries
+//     the 6 rows the vertical filter needs from chunk to chunk, so the 3+3 halo rows are
+//     computed once per segment and nothing is copied between chunks;
+//   * phase B (warp per chroma row, after the one consumer barrier of the chunk): the taps
+//     [-58,-172,492,1786,1786,492,-172,-58]/4096 are symmetric and even: rows are pair-added on
+//     the packed words, the three small taps are dp2a on the packed word (no unpacking), the
+//     big one is one IMAD per channel; fast warps run ahead into phase A of the next chunk;
+//   * composite: the select among the N staged sources happens in registers (tiles without
+//     text) or is materialised into source 0's rows first (tiles a glyph touches).
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <algorithm>
 
 #include "device_common.cuh"
 #include "nes_internal.h"
@@ -44,43 +47,47 @@ namespace {
 
 enum { MODE_ROWS = 0, MODE_SELECT = 1, MODE_MATERIALIZED = 2 };
 
+constexpr int DEP_ROWB = STRIP_W;  // bytes of a staged depth row
+
 // Everything the consumer warps need to know about one chunk, written to shared memory by
-// lane 0 of the producer warp while earlier chunks are being computed (no consumer reads the
-// job descriptor from global memory on the critical path).  Plane pointers are pre-offset
-// to the strip.
+// lane 0 of the producer warp while earlier chunks are being computed.  Plane pointers are
+// pre-offset to the strip.
 struct ChunkCtx {
-  int32_t last;    // last chunk this CTA processes
-  int32_t mode;    // MODE_*
-  int32_t tma;     // rows were staged by bulk copies (else the consumers fill them)
-  int32_t stamp;   // a glyph may intersect this chunk
-  int32_t n_src, job, ch;
+  int32_t last;      // last chunk this CTA processes
+  int32_t mode;      // MODE_*
+  int32_t tma;       // rows were staged by TMA (else the consumers fill them)
+  int32_t stamp;     // a glyph may intersect this chunk
+  int32_t n_src, job;
+  int32_t n_staged;  // sources laid out in a sub-stage (n_src when staged by TMA, else 1)
   int32_t x0, tw;
-  int32_t yc0;     // frame row of chunk-local row 0 (negative above the frame)
-  int32_t ra, rb;  // staged source rows [ra, rb)
-  int32_t ya, yb;  // luma rows to emit [ya, yb)
-  int32_t cA, cB;  // chroma rows to emit [cA, cB)
+  int32_t yc0;       // frame row of chunk-local row 0 (negative above the frame)
+  int32_t ra, rb;    // source rows of this chunk that exist / are needed [ra, rb)
+  int32_t ya, yb;    // luma rows to emit [ya, yb)
+  int32_t cA, cB;    // chroma rows to emit [cA, cB)
   int32_t H;
-  int32_t edge;    // a vertical tap of [cA, cB) is clamped at the frame border
-  int32_t carry;   // the segment continues: keep the last CARRY_ROWS chroma rows
-  int32_t vec_in, vec_out, a_shift, rgb_base, depth_regs;
+  int32_t edge;      // a vertical tap of [cA, cB) is clamped at the frame border
+  int32_t rbase;     // chroma-ring slot of chunk-local row 0
+  int32_t fullw;     // full-width strip, 16-byte aligned planes: unconditional vector stores
+  int32_t vec_out, rgb_base, dep_staged;
+  uint32_t a_mask;   // alpha byte mask of a pixel word (composite validity)
   uint32_t ky[4], ku[3], kv[3];
   int32_t sys, sus, svs, dys, dus, dvs;
   uint8_t *sy, *su, *sv, *dy, *du, *dv;  // + strip column offset
-  const uint8_t *rgb[NES_MAX_SOURCES];   // + strip column offset
-  const uint8_t *dep[NES_MAX_SOURCES];
-  int32_t rs[NES_MAX_SOURCES], ds[NES_MAX_SOURCES];
 };
 
 template <int BPP>
 struct StripSmem {
   static constexpr int ROWB = STRIP_W * BPP;
-  static constexpr int PX_BYTES = (CARRY_ALLOC + CHUNK_ROWS_MAX) * ROWB;
-  static constexpr int DEP_BYTES = BPP == 4 ? CHUNK_ROWS_MAX * STRIP_W : 0;  // composite staging (4-byte pixels only)
-  static constexpr int STAGE = PX_BYTES + DEP_BYTES;
-  static constexpr int OFF_CTX = 2 * STAGE;
-  static constexpr int OFF_BAR = OFF_CTX + 2 * (((int)sizeof(ChunkCtx) + 15) & ~15);
-  static constexpr int OFF_HITS = OFF_BAR + 32;
+  static constexpr int STAGE_BYTES = (BPP == 4 ? 80 : 48) * 1024;  // the sub-stage ring
+  static constexpr int OFF_RING = STAGE_BYTES;
+  static constexpr int RING_ROWB = (STRIP_W / 2) * 4;
+  static constexpr int OFF_CTX = OFF_RING + RING_ROWS * RING_ROWB;
+  static constexpr int CTX_BYTES = ((int)sizeof(ChunkCtx) + 15) & ~15;
+  static constexpr int OFF_BAR = OFF_CTX + NCTX * CTX_BYTES;
+  static constexpr int OFF_HITS = OFF_BAR + 2 * NS_MAX * 8;
   static constexpr int TOTAL = OFF_HITS + HIT_CAP * 4 + 16;
+  // bytes of one sub-stage holding n sources: 8 pixel rows + 8 depth rows per source
+  static constexpr int slot_bytes(int n) { return n * SUB_ROWS * (ROWB + DEP_ROWB); }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,10 +112,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// global -> shared bulk async copy (TMA engine, no tensor map), completes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
+// global -> shared 2D tensor-map copy (TMA): box = 8 rows x one strip of u32 elements at element
+// coordinates (x, y); rows / columns outside the tensor are zero-filled and still counted
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const TMap *map, int x, int y, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
                : "memory");
 }
 // explicit shared-space accesses (32-bit shared addresses; keeps the hot loops off generic LD/ST)
@@ -209,6 +217,8 @@ __device__ __forceinline__ void store8(uint8_t *row, int x, uint32_t w0, uint32_
   if (vec && x + 8 <= tw) *(uint2 *)(row + x) = make_uint2(w0, w1);
   else { store4(row, x, w0, tw, false); store4(row, x + 4, w1, tw, false); }
 }
+__device__ __forceinline__ void stg32(uint8_t *p, uint32_t w) { *(uint32_t *)p = w; }
+__device__ __forceinline__ void stg64(uint8_t *p, uint32_t w0, uint32_t w1) { *(uint2 *)p = make_uint2(w0, w1); }
 
 // Which job of this kernel's bpp class does work unit `u` belong to (unit_base is a prefix
 // sum over the batch in which the jobs of the other class take no units): the last job
@@ -222,20 +232,22 @@ __device__ __forceinline__ int job_of_unit(const DevJob *jobs, int n_jobs, int c
   return lo;
 }
 
-// Depth-select composite of the 8 pixels a lane owns in a chunk row (4 at column 4*lane, 4 at
-// 128 + 4*lane) from the N staged sources: the winner's pixel words and depth bytes.
+
+// Depth-select composite of the 8 pixels a lane owns in a sub-stage row (4 at column 4*lane, 4
+// at 128 + 4*lane) from the N staged sources: the winner's pixel words and depth bytes.
+// px / dep: shared addresses of source 0's row; source k's row is k*SUB_ROWS rows further.
 // Semantics: DESIGN.md "composite" / oracle/overlay_port.c nes_oracle_composite.
 template <int ROWB>
-__device__ __forceinline__ void select_staged(uint32_t px0, uint32_t dep0, int r, int ch, int n_src, int ash, int lane,
-                                              uint32_t (&p)[8], uint32_t (&d4)[2]) {
+__device__ __forceinline__ void select_staged(uint32_t px, uint32_t dep, int n_src, uint32_t a_mask, int lane, uint32_t (&p)[8],
+                                              uint32_t (&d4)[2]) {
   uint32_t bd[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) { p[i] = 0; bd[i] = 256; }
 #pragma unroll
-  for (int k = 0; k < NES_MAX_SOURCES; k++) {
+  for (int k = 0; k < TMA_MAX_SOURCES; k++) {
     if (k >= n_src) break;
-    const uint32_t rp = px0 + (uint32_t)(k * ch + r) * ROWB + lane * 16;
-    const uint32_t dp = dep0 + (uint32_t)(k * ch + r) * STRIP_W + lane * 4;
+    const uint32_t rp = px + (uint32_t)(k * SUB_ROWS) * ROWB + lane * 16;
+    const uint32_t dp = dep + (uint32_t)(k * SUB_ROWS) * DEP_ROWB + lane * 4;
     const uint4 q[2] = {lds128(rp), lds128(rp + 512)};
     const uint32_t dw[2] = {lds32(dp), lds32(dp + 128)};
 #pragma unroll
@@ -243,24 +255,28 @@ __device__ __forceinline__ void select_staged(uint32_t px0, uint32_t dep0, int r
       const uint32_t w[4] = {q[h].x, q[h].y, q[h].z, q[h].w};
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const uint32_t d = (dw[h] >> (8 * i)) & 255u;
-        const bool take = ((w[i] >> ash) & 255u) != 0 && d < bd[4 * h + i];
+        const uint32_t d = __byte_perm(dw[h], 0u, 0x4440 + i);
+        const bool take = (w[i] & a_mask) != 0 && d < bd[4 * h + i];
         bd[4 * h + i] = take ? d : bd[4 * h + i];
         p[4 * h + i] = take ? w[i] : p[4 * h + i];
       }
     }
   }
 #pragma unroll
-  for (int h = 0; h < 2; h++)
-    d4[h] = min(bd[4 * h], 255u) | (min(bd[4 * h + 1], 255u) << 8) | (min(bd[4 * h + 2], 255u) << 16) | (min(bd[4 * h + 3], 255u) << 24);
+  for (int h = 0; h < 2; h++) {
+    const uint32_t lo = __byte_perm(min(bd[4 * h], 255u), min(bd[4 * h + 1], 255u), 0x0040);
+    const uint32_t hi = __byte_perm(min(bd[4 * h + 2], 255u), min(bd[4 * h + 3], 255u), 0x0040);
+    d4[h] = __byte_perm(lo, hi, 0x5410);
+  }
 }
 
 // Glyph stamp into the staged rows of source 0 (consumer warps only).  Reference semantics
 // (render_text.cc:94-106): every bitmap pixel with coverage != 0 inside the frame becomes
 // (255,255,255).  All stamps write the same value: overlapping glyphs are order-free.
+// Chunk-local row r lives in sub-stage r / 8 (generic pointers sub0 / sub1), row r % 8.
 template <int BPP>
-__device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *rows, int x0, int x1, int yc0, int ra, int rb, int rgb_base,
-                                            int *s_hits, int *s_nhits) {
+__device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *sub0, uint8_t *sub1, int x0, int x1, int yc0, int ra, int rb,
+                                            int rgb_base, int *s_hits, int *s_nhits) {
   constexpr int ROWB = STRIP_W * BPP;
   constexpr int NT = 32 * CONSUMER_WARPS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -278,12 +294,15 @@ __device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *rows, int
       const uint8_t *cov = jb.atlas + pg.atlas_off;
       const int q0 = max(0, ra - pg.y), q1 = min(pg.h, rb - pg.y);
       const int p0 = max(0, x0 - pg.x), p1 = min(pg.w, x1 - pg.x);
-      for (int q = q0; q < q1; q++)
+      for (int q = q0; q < q1; q++) {
+        const int r = pg.y + q - yc0;
+        uint8_t *row = (r < SUB_ROWS ? sub0 : sub1) + (r & (SUB_ROWS - 1)) * ROWB;
         for (int p = p0 + lane; p < p1; p += 32)
           if (cov[q * pg.pitch + p]) {
-            uint8_t *px = rows + (pg.y + q - yc0) * ROWB + (pg.x + p - x0) * BPP + (BPP == 4 ? rgb_base : 0);
+            uint8_t *px = row + (pg.x + p - x0) * BPP + (BPP == 4 ? rgb_base : 0);
             px[0] = 255; px[1] = 255; px[2] = 255;
           }
+      }
     }
     consumer_sync();
   }
@@ -293,15 +312,15 @@ __device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *rows, int
 
 template <int BPP>
 __global__ void __launch_bounds__(CTA_THREADS, BPP == 3 ? 3 : 2)
-k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters) {
-  extern __shared__ __align__(128) uint8_t smem[];
+k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters, int ns, int slot_bytes) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   using L = StripSmem<BPP>;
   constexpr int ROWB = L::ROWB;
+  constexpr int RING_ROWB = L::RING_ROWB;
   constexpr int CLS = BPP - 3;
   constexpr int NW = CONSUMER_WARPS;
-  ChunkCtx *s_ctx = (ChunkCtx *)(smem + L::OFF_CTX);
-  uint64_t *s_full = (uint64_t *)(smem + L::OFF_BAR);  // [2]
-  uint64_t *s_empty = s_full + 2;                       // [2]
+  uint64_t *s_full = (uint64_t *)(smem + L::OFF_BAR);  // [NS_MAX]
+  uint64_t *s_empty = s_full + NS_MAX;                  // [NS_MAX]
   int *s_hits = (int *)(smem + L::OFF_HITS);
   int *s_nhits = s_hits + HIT_CAP;
 
@@ -309,10 +328,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
   const uint32_t smem_base = smem_u32(smem);
 
   if (tid == 0) {
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    mbar_init(&s_empty[0], NW);
-    mbar_init(&s_empty[1], NW);
+    for (int i = 0; i < NS_MAX; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -324,29 +340,45 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
     int cur_u = blockIdx.x, next_u = 0;
     if (lane == 0) next_u = (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
     next_u = __shfl_sync(0xffffffffu, next_u, 0);
-    int it = 0;
+    int q = 0, par = 0, round0 = 1;  // sub-stage cursor: slot, parity of its use count, first trip round the ring
+    int chunk_it = 0, rbase = 0;
     while (cur_u < total_units) {
-      // ---- unit geometry (all lanes compute it: cheap, keeps the copy loop uniform) ---------
+      // ---- unit geometry (all lanes compute it: cheap, keeps the copy code uniform) ---------
       const int j = job_of_unit(jobs, n_jobs, CLS, cur_u);
       const DevJob *jp = jobs + j;
       const int local = cur_u - jp->unit_base[CLS];
       const int strip = local % jp->strips_x, seg = local / jp->strips_x;
-      const int W = jp->W, H = jp->H, S = jp->seg_rows, ch = jp->chunk_rows, n_src = jp->n_src;
+      const int W = jp->W, H = jp->H, S = jp->seg_rows, n_src = jp->n_src;
       const int x0 = strip * STRIP_W, tw = min(STRIP_W, W - x0);
       const int Y0 = seg * S, Y1 = min(Y0 + S, H);
       const int L0 = Y0 - HALO, need_end = min(Y1 + HALO, H);
-      const int nchunks = (need_end - L0 + ch - 1) / ch;
+      const int nchunks = (need_end - L0 + CHUNK_ROWS - 1) / CHUNK_ROWS;
       const int tma = jp->tma_ok;
-      const int staged_composite = tma && n_src > 1;
+      const int n_staged = tma ? n_src : 1;
+      const int dep_staged = (jp->dy != nullptr) || n_src > 1;
       const int nbands = (H + (1 << MASK_BAND_SHIFT) - 1) >> MASK_BAND_SHIFT;
-      for (int k = 0; k < nchunks; k++, it++) {
-        const int b = it & 1;
-        if (it >= 2) mbar_wait(&s_empty[b], (uint32_t)((it >> 1) - 1) & 1u);
-        const int yc0 = L0 + k * ch;
-        const int ra = max(yc0, 0), rb = min(yc0 + ch, need_end);
+      const uint32_t tx_bytes = (uint32_t)(n_staged * SUB_ROWS) * (uint32_t)(ROWB + (dep_staged ? DEP_ROWB : 0));
+      // which plane this lane copies: lanes [0, n) the pixel planes, lanes [n, 2n) the depth planes
+      const TMap *my_map = nullptr;
+      uint32_t my_off = 0;
+      int my_x = 0;
+      if (tma) {
+        if (lane < n_staged) {
+          my_map = &jp->tmap_px[lane]; my_off = (uint32_t)(lane * SUB_ROWS) * ROWB; my_x = (x0 * BPP) >> 2;
+        } else if (dep_staged && lane < 2 * n_staged) {
+          my_map = &jp->tmap_dep[lane - n_staged];
+          my_off = (uint32_t)(n_staged * SUB_ROWS) * ROWB + (uint32_t)((lane - n_staged) * SUB_ROWS) * DEP_ROWB;
+          my_x = x0 >> 2;
+        }
+      }
+      for (int k = 0; k < nchunks; k++, chunk_it++) {
+        const int yc0 = L0 + k * CHUNK_ROWS;
+        const int ra = max(yc0, 0), rb = min(yc0 + CHUNK_ROWS, need_end);
         const bool last_k = (k == nchunks - 1);
         if (lane == 0) {
-          ChunkCtx &c = s_ctx[b];
+          // the context slot was last used NCTX chunks ago; the consumers are at most
+          // NS_MAX/2 + 2 chunks behind (they must release sub-stages for us to get here)
+          ChunkCtx &c = *(ChunkCtx *)(smem + L::OFF_CTX + (chunk_it & (NCTX - 1)) * L::CTX_BYTES);
           int stamp = 0;
           if (jp->n_glyphs > 0) {
             stamp = 1;
@@ -361,19 +393,20 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
           c.last = last_k && next_u >= total_units;
           c.tma = tma;
           c.stamp = stamp;
-          c.mode = staged_composite ? (stamp ? MODE_MATERIALIZED : MODE_SELECT) : MODE_ROWS;
-          c.n_src = n_src; c.job = j; c.ch = ch;
+          c.mode = (tma && n_src > 1) ? (stamp ? MODE_MATERIALIZED : MODE_SELECT) : MODE_ROWS;
+          c.n_src = n_src; c.job = j; c.n_staged = n_staged;
           c.x0 = x0; c.tw = tw; c.yc0 = yc0; c.ra = ra; c.rb = rb;
           c.ya = max(ra, Y0); c.yb = min(rb, Y1);
-          const int cA = (k == 0) ? (Y0 >> 1) : (Y0 >> 1) + ((k * ch) >> 1) - 3;
-          const int cB = last_k ? (Y1 >> 1) : (Y0 >> 1) + (((k + 1) * ch) >> 1) - 3;
+          const int cA = (k == 0) ? (Y0 >> 1) : (Y0 >> 1) + ((k * CHUNK_ROWS) >> 1) - 3;
+          const int cB = last_k ? (Y1 >> 1) : (Y0 >> 1) + (((k + 1) * CHUNK_ROWS) >> 1) - 3;
           c.cA = cA; c.cB = cB; c.H = H;
           c.edge = (2 * cA - 3 < 0) || (2 * (cB - 1) + 4 > H - 1);
-          c.carry = !last_k;
-          c.vec_in = jp->in_vec; c.vec_out = jp->out_vec;
-          c.a_shift = jp->a_off > 0 ? 8 * jp->a_off : 0;
+          c.rbase = rbase;
+          c.vec_out = jp->out_vec;
+          c.fullw = jp->out_vec && tw == STRIP_W;
+          c.a_mask = jp->a_off >= 0 ? (0xFFu << (8 * jp->a_off)) : 0xFFFFFFFFu;
           c.rgb_base = jp->rgb_base;
-          c.depth_regs = jp->dy && n_src == 1 && jp->in_vec && jp->out_vec && (tw & 7) == 0;
+          c.dep_staged = dep_staged;
           if (BPP == 3) {
 #pragma unroll
             for (int i = 0; i < 4; i++) c.ky[i] = jp->ky3[i];
@@ -388,35 +421,24 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
           c.dy = jp->dy ? jp->dy + x0 : nullptr;
           c.du = jp->dy ? jp->du + (x0 >> 1) : nullptr;
           c.dv = jp->dy ? jp->dv + (x0 >> 1) : nullptr;
-          for (int s = 0; s < n_src; s++) {
-            c.rgb[s] = jp->src[s].rgb + (size_t)x0 * BPP;
-            c.dep[s] = jp->src[s].depth ? jp->src[s].depth + x0 : nullptr;
-            c.rs[s] = jp->src[s].rgb_stride; c.ds[s] = jp->src[s].depth_stride;
-          }
         }
         __syncwarp();
-        if (tma) {
-          const uint32_t px0 = smem_base + b * L::STAGE + CARRY_ALLOC * ROWB;
-          const uint32_t dep0 = smem_base + b * L::STAGE + L::PX_BYTES;
-          const uint32_t rowb = (uint32_t)tw * BPP;
-          const int nrows = rb - ra;
-          uint32_t bytes = 0;
-          for (int s = 0; s < n_src; s++) {
-            const uint8_t *src = jp->src[s].rgb + (size_t)x0 * BPP;
-            const int stride = jp->src[s].rgb_stride;
-            for (int y = ra + lane; y < rb; y += 32) bulk_g2s(px0 + (uint32_t)(s * ch + (y - yc0)) * ROWB, src + (size_t)y * stride, rowb, &s_full[b]);
-            bytes += rowb * (uint32_t)nrows;
-            if (staged_composite) {
-              const uint8_t *dsrc = jp->src[s].depth + x0;
-              const int dstride = jp->src[s].depth_stride;
-              for (int y = ra + lane; y < rb; y += 32) bulk_g2s(dep0 + (uint32_t)(s * ch + (y - yc0)) * STRIP_W, dsrc + (size_t)y * dstride, (uint32_t)tw, &s_full[b]);
-              bytes += (uint32_t)tw * (uint32_t)nrows;
-            }
+#pragma unroll 1
+        for (int sub = 0; sub < CHUNK_ROWS / SUB_ROWS; sub++) {
+          if (!round0) mbar_wait(&s_empty[q], (uint32_t)(par ^ 1));
+          const int ys = yc0 + sub * SUB_ROWS;
+          const bool wanted = tma && ys < rb && ys + SUB_ROWS > ra;  // else nothing of this sub-stage is read
+          if (wanted) {
+            if (lane == 0) mbar_arrive_expect_tx(&s_full[q], tx_bytes);
+            __syncwarp();
+            if (my_map) tma_load_2d(smem_base + (uint32_t)(q * slot_bytes) + my_off, my_map, my_x, ys, &s_full[q]);
+          } else if (lane == 0) {
+            mbar_arrive(&s_full[q]);  // nothing in flight (the consumers fill the rows themselves, or skip them)
           }
-          if (lane == 0) mbar_arrive_expect_tx(&s_full[b], bytes);
-        } else if (lane == 0) {
-          mbar_arrive(&s_full[b]);  // nothing in flight: the consumers fill the rows themselves
+          if (++q == ns) { q = 0; par ^= 1; round0 = 0; }
         }
+        rbase += CHUNK_ROWS;
+        if (rbase >= RING_ROWS) rbase -= RING_ROWS;
       }
       cur_u = next_u;
       if (lane == 0 && cur_u < total_units) next_u = (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
@@ -431,182 +453,177 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
   }
 
   // ============================= consumer warps ===========================================
-  for (int it = 0;; it++) {
-    const int cur = it & 1;
-    mbar_wait(&s_full[cur], (uint32_t)(it >> 1) & 1u);
-    const ChunkCtx &c = s_ctx[cur];
+  const uint32_t ring0 = smem_base + L::OFF_RING;
+  int q0 = 0, par = 0;
+  for (int chunk_it = 0;; chunk_it++) {
+    mbar_wait(&s_full[q0], (uint32_t)par);
+    const ChunkCtx &c = *(const ChunkCtx *)(smem + L::OFF_CTX + (chunk_it & (NCTX - 1)) * L::CTX_BYTES);
     const int last = c.last;
     {
-      const uint32_t stage = smem_base + cur * L::STAGE;
-      const uint32_t px0 = stage + CARRY_ALLOC * ROWB;  // chunk-local row 0 of source 0
-      const uint32_t dep0 = stage + L::PX_BYTES;
-      uint8_t *const rows0 = smem + cur * L::STAGE + CARRY_ALLOC * ROWB;
-      const int x0 = c.x0, tw = c.tw, yc0 = c.yc0, ra = c.ra, rb = c.rb, ya = c.ya, yb = c.yb, ch = c.ch;
+      const uint32_t sb0 = smem_base + (uint32_t)(q0 * slot_bytes);
+      const uint32_t dep_off = (uint32_t)(c.n_staged * SUB_ROWS) * ROWB;
+      const int x0 = c.x0, tw = c.tw, yc0 = c.yc0, ra = c.ra, rb = c.rb, ya = c.ya, yb = c.yb;
       const int n_src = c.n_src;
-      const int mode = c.mode;
-      const bool vec_out = c.vec_out != 0;
+      int mode = c.mode;
+      const bool fullw = c.fullw != 0, vec_out = c.vec_out != 0;
+      const bool dep_staged = c.dep_staged != 0;
       uint8_t *const dy = c.dy;
       const int dys = c.dys;
+      bool have1 = false;  // sub-stage 1 already waited for
 
-      // ---- depth loads of a single-source chunk (consumed after phase A) -------------------
-      constexpr int RPW = CHUNK_ROWS_MAX / NW;  // rows per warp
-      uint2 dreg[RPW];
-      const bool depth_regs = c.depth_regs != 0;  // CTA-uniform
-      const bool depth_lane = depth_regs && lane * 8 < tw;
-      if (depth_lane) {
-        const uint8_t *dsrc = c.dep[0] + lane * 8;
-        const int dstride = c.ds[0];
-#pragma unroll
-        for (int i = 0; i < RPW; i++) {
-          const int y = yc0 + warp + i * NW;
-          if (y >= ya && y < yb) dreg[i] = __ldg((const uint2 *)(dsrc + y * dstride));
-        }
-      }
-
-      // ---- fill the rows ourselves when they were not staged by bulk copies ----------------
-      if (!c.tma) {
-        for (int y = ra + warp; y < rb; y += NW) {
-          uint8_t *s = rows0 + (y - yc0) * ROWB;
-          if (n_src == 1) {
-            const uint8_t *g = c.rgb[0] + (size_t)y * c.rs[0];
-            const int nbytes = tw * BPP;
-            for (int i = lane; i < nbytes; i += 32) s[i] = g[i];
-          } else {
-            const bool core = (y >= ya) && (y < yb);
-            const DevJob &jb = jobs[c.job];
-            for (int x = lane; x < tw; x += 32) {
-              uint32_t d;
-              composite_px<BPP>(jb, x0 + x, y, s + x * BPP, &d);
-              if (core && dy) dy[(size_t)y * dys + x] = (uint8_t)gray_y(d);
+      if (!c.tma || mode == MODE_MATERIALIZED || c.stamp) {
+        mbar_wait(&s_full[q0 + 1], (uint32_t)par);
+        have1 = true;
+        uint8_t *const g0 = smem + q0 * slot_bytes;
+        // ---- fill our rows ourselves when they were not staged by TMA ------------------------
+        if (!c.tma) {
+          const DevJob &jb = jobs[c.job];
+#pragma unroll 1
+          for (int i = 0; i < CHUNK_ROWS / SUB_ROWS; i++) {
+            const int y = yc0 + warp + i * SUB_ROWS;
+            if (y < ra || y >= rb) continue;
+            uint8_t *s = g0 + i * slot_bytes + warp * ROWB;
+            uint8_t *sd = g0 + i * slot_bytes + SUB_ROWS * ROWB + warp * DEP_ROWB;
+            if (n_src == 1) {
+              const uint8_t *g = jb.src[0].rgb + (size_t)y * jb.src[0].rgb_stride + (size_t)x0 * BPP;
+              const int nbytes = tw * BPP;
+              for (int b = lane; b < nbytes; b += 32) s[b] = g[b];
+              if (dep_staged) {
+                const uint8_t *gd = jb.src[0].depth + (size_t)y * jb.src[0].depth_stride + x0;
+                for (int x = lane; x < tw; x += 32) sd[x] = gd[x];
+              }
+            } else {
+              for (int x = lane; x < tw; x += 32) {
+                uint32_t d;
+                composite_px<BPP>(jb, x0 + x, y, s + x * BPP, &d);
+                sd[x] = (uint8_t)d;
+              }
             }
           }
         }
-        consumer_sync();
-      }
-      // ---- staged composite under text: materialise the select into source 0's rows ----------
-      if (BPP == 4 && mode == MODE_MATERIALIZED) {
-        for (int r = warp; r < ch; r += NW) {
-          const int y = yc0 + r;
-          if (y < ra || y >= rb) continue;
-          uint32_t p[8], d4[2];
-          select_staged<ROWB>(px0, dep0, r, ch, n_src, c.a_shift, lane, p, d4);
-          __syncwarp();
-          sts128(px0 + r * ROWB + lane * 16, p[0], p[1], p[2], p[3]);
-          sts128(px0 + r * ROWB + 512 + lane * 16, p[4], p[5], p[6], p[7]);
-          sts32(dep0 + r * STRIP_W + lane * 4, d4[0]);
-          sts32(dep0 + r * STRIP_W + 128 + lane * 4, d4[1]);
+        // ---- staged composite under text: materialise the select into source 0's rows ----------
+        if (BPP == 4 && mode == MODE_MATERIALIZED) {
+#pragma unroll 1
+          for (int i = 0; i < CHUNK_ROWS / SUB_ROWS; i++) {
+            const int y = yc0 + warp + i * SUB_ROWS;
+            if (y < ra || y >= rb) continue;
+            const uint32_t px = sb0 + (uint32_t)(i * slot_bytes) + warp * ROWB;
+            const uint32_t dp = sb0 + (uint32_t)(i * slot_bytes) + dep_off + warp * DEP_ROWB;
+            uint32_t p[8], d4[2];
+            select_staged<ROWB>(px, dp, n_src, c.a_mask, lane, p, d4);
+            __syncwarp();
+            sts128(px + lane * 16, p[0], p[1], p[2], p[3]);
+            sts128(px + 512 + lane * 16, p[4], p[5], p[6], p[7]);
+            sts32(dp + lane * 4, d4[0]);
+            sts32(dp + 128 + lane * 4, d4[1]);
+          }
+          mode = MODE_ROWS;
         }
-      }
-      // ---- text overlay, stamped into the staged rows of source 0 ----------------------------
-      if (c.stamp) {
-        stamp_chunk<BPP>(jobs[c.job], rows0, x0, x0 + tw, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
+        __syncwarp();
+        // ---- text overlay, stamped into the staged rows of source 0 ----------------------------
+        if (c.stamp) stamp_chunk<BPP>(jobs[c.job], g0, g0 + slot_bytes, x0, x0 + tw, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
+        fence_proxy_async();  // our generic-proxy writes to the stage come before the TMA refill
       }
 
-      // ---- phase A: per source row: Y out, pair-summed chroma (u14 | v14<<16) in place --------
+      // ---- phase A: per source row: Y out, pair-summed chroma (u14 | v14<<16) to the ring ------
       {
         uint8_t *const sy = c.sy;
         const int sys = c.sys;
+        const int rbase = c.rbase;
 #pragma unroll 1
-        for (int i = 0; i < RPW; i++) {
-          const int r = warp + i * NW;
+        for (int i = 0; i < CHUNK_ROWS / SUB_ROWS; i++) {
+          const int r = warp + i * SUB_ROWS;
           const int y = yc0 + r;
-          if (r >= ch || y < ra || y >= rb) continue;
-          const uint32_t row = px0 + r * ROWB;
-          const bool core = (y >= ya) && (y < yb);
-          uint32_t uv[4];
-          uint32_t yw0 = 0, yw1 = 0;
-          if (BPP == 3) {
-            // lane owns pixels 8*lane .. 8*lane+7 = 6 raw words (8-byte loads at 24-byte stride are
-            // conflict free); the coefficient pairs are laid out per byte phase, so nothing is unpacked
-            const uint2 a = lds64(row + lane * 24), b = lds64(row + lane * 24 + 8), d = lds64(row + lane * 24 + 16);
-            const uint32_t w[6] = {a.x, a.y, b.x, b.y, d.x, d.y};
-            __syncwarp();  // every lane has read its pixels before anyone overwrites the row
-            const uint32_t u01 = c.ku[0], u20 = c.ku[1], u12 = c.ku[2], v01 = c.kv[0], v20 = c.kv[1], v12 = c.kv[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const uint32_t w0 = w[3 * h], w1 = w[3 * h + 1], w2 = w[3 * h + 2];
-              const int su0 = dp2a_lo(u12, w1, dp2a_hi(u20, w0, dp2a_lo(u01, w0, C_BIAS)));
-              const int sv0 = dp2a_lo(v12, w1, dp2a_hi(v20, w0, dp2a_lo(v01, w0, C_BIAS)));
-              const int su1 = dp2a_hi(u12, w2, dp2a_lo(u20, w2, dp2a_hi(u01, w1, C_BIAS)));
-              const int sv1 = dp2a_hi(v12, w2, dp2a_lo(v20, w2, dp2a_hi(v01, w1, C_BIAS)));
-              uv[2 * h] = pack_uv14(su0, sv0);
-              uv[2 * h + 1] = pack_uv14(su1, sv1);
-            }
-            sts128(row + lane * 16, uv[0], uv[1], uv[2], uv[3]);  // chroma cols 4*lane..+3
-            if (core) {
-              const uint32_t y01 = c.ky[0], y2_ = c.ky[1], y_0 = c.ky[2], y12 = c.ky[3];
-              uint32_t s[8];
+          if (i == 1 && !have1) mbar_wait(&s_full[q0 + 1], (uint32_t)par);
+          if (y >= ra && y < rb) {
+            const uint32_t row = sb0 + (uint32_t)(i * slot_bytes) + warp * ROWB;
+            const uint32_t drow = sb0 + (uint32_t)(i * slot_bytes) + dep_off + warp * DEP_ROWB;
+            int slot = rbase + r;
+            if (slot >= RING_ROWS) slot -= RING_ROWS;
+            const uint32_t crow = ring0 + slot * RING_ROWB;
+            const bool core = (y >= ya) && (y < yb);
+            uint32_t uv[4];
+            if (BPP == 3) {
+              // lane owns pixels 8*lane .. 8*lane+7 = 6 raw words (8-byte loads at 24-byte stride are
+              // conflict free); the coefficient pairs are laid out per byte phase, so nothing is unpacked
+              const uint2 a = lds64(row + lane * 24), b = lds64(row + lane * 24 + 8), d = lds64(row + lane * 24 + 16);
+              const uint32_t w[6] = {a.x, a.y, b.x, b.y, d.x, d.y};
+              const uint32_t u01 = c.ku[0], u20 = c.ku[1], u12 = c.ku[2], v01 = c.kv[0], v20 = c.kv[1], v12 = c.kv[2];
 #pragma unroll
               for (int h = 0; h < 2; h++) {
                 const uint32_t w0 = w[3 * h], w1 = w[3 * h + 1], w2 = w[3 * h + 2];
-                s[4 * h] = dp2a_hi_uu(y2_, w0, dp2a_lo_uu(y01, w0, 2 * Y_BIAS));
-                s[4 * h + 1] = dp2a_lo_uu(y12, w1, dp2a_hi_uu(y_0, w0, 2 * Y_BIAS));
-                s[4 * h + 2] = dp2a_lo_uu(y2_, w2, dp2a_hi_uu(y01, w1, 2 * Y_BIAS));
-                s[4 * h + 3] = dp2a_hi_uu(y12, w2, dp2a_lo_uu(y_0, w2, 2 * Y_BIAS));
+                const int su0 = dp2a_lo(u12, w1, dp2a_hi(u20, w0, dp2a_lo(u01, w0, C_BIAS)));
+                const int sv0 = dp2a_lo(v12, w1, dp2a_hi(v20, w0, dp2a_lo(v01, w0, C_BIAS)));
+                const int su1 = dp2a_hi(u12, w2, dp2a_lo(u20, w2, dp2a_hi(u01, w1, C_BIAS)));
+                const int sv1 = dp2a_hi(v12, w2, dp2a_lo(v20, w2, dp2a_hi(v01, w1, C_BIAS)));
+                uv[2 * h] = pack_uv14(su0, sv0);
+                uv[2 * h + 1] = pack_uv14(su1, sv1);
               }
-              yw0 = pack_b2(s[0], s[1], s[2], s[3]);
-              yw1 = pack_b2(s[4], s[5], s[6], s[7]);
-              store8(sy + y * sys, lane * 8, yw0, yw1, tw, vec_out);
-            }
-          } else {
-            // lane owns pixels 4*lane..+3 and 128+4*lane..+3 (16-byte accesses at 16-byte stride)
-            uint32_t p[8];
-            uint32_t d4[2];
-            if (mode == MODE_SELECT) {
-              select_staged<ROWB>(px0, dep0, r, ch, n_src, c.a_shift, lane, p, d4);
+              sts128(crow + lane * 16, uv[0], uv[1], uv[2], uv[3]);  // chroma cols 4*lane..+3
+              if (core) {
+                const uint32_t y01 = c.ky[0], y2_ = c.ky[1], y_0 = c.ky[2], y12 = c.ky[3];
+                uint32_t s[8];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                  const uint32_t w0 = w[3 * h], w1 = w[3 * h + 1], w2 = w[3 * h + 2];
+                  s[4 * h] = dp2a_hi_uu(y2_, w0, dp2a_lo_uu(y01, w0, 2 * Y_BIAS));
+                  s[4 * h + 1] = dp2a_lo_uu(y12, w1, dp2a_hi_uu(y_0, w0, 2 * Y_BIAS));
+                  s[4 * h + 2] = dp2a_lo_uu(y2_, w2, dp2a_hi_uu(y01, w1, 2 * Y_BIAS));
+                  s[4 * h + 3] = dp2a_hi_uu(y12, w2, dp2a_lo_uu(y_0, w2, 2 * Y_BIAS));
+                }
+                const uint32_t yw0 = pack_b2(s[0], s[1], s[2], s[3]), yw1 = pack_b2(s[4], s[5], s[6], s[7]);
+                if (fullw) stg64(sy + y * sys + lane * 8, yw0, yw1);
+                else store8(sy + y * sys, lane * 8, yw0, yw1, tw, vec_out);
+                if (dy) {
+                  const uint2 dd = lds64(drow + lane * 8);
+                  const uint32_t g0 = gray_y4_packed(dd.x), g1 = gray_y4_packed(dd.y);
+                  if (fullw) stg64(dy + y * dys + lane * 8, g0, g1);
+                  else store8(dy + y * dys, lane * 8, g0, g1, tw, vec_out);
+                }
+              }
             } else {
-              const uint4 a = lds128(row + lane * 16), b = lds128(row + 512 + lane * 16);
-              p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
-              if (mode == MODE_MATERIALIZED) { d4[0] = lds32(dep0 + r * STRIP_W + lane * 4); d4[1] = lds32(dep0 + r * STRIP_W + 128 + lane * 4); }
-            }
-            __syncwarp();
-            const uint32_t kua = c.ku[0], kub = c.ku[1], kva = c.kv[0], kvb = c.kv[1];
+              // lane owns pixels 4*lane..+3 and 128+4*lane..+3 (16-byte accesses at 16-byte stride)
+              uint32_t p[8];
+              uint32_t d4[2] = {0, 0};
+              if (mode == MODE_SELECT) {
+                select_staged<ROWB>(row, drow, n_src, c.a_mask, lane, p, d4);
+              } else {
+                const uint4 a = lds128(row + lane * 16), b = lds128(row + 512 + lane * 16);
+                p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+                if (dep_staged) { d4[0] = lds32(drow + lane * 4); d4[1] = lds32(drow + 128 + lane * 4); }
+              }
+              const uint32_t kua = c.ku[0], kub = c.ku[1], kva = c.kv[0], kvb = c.kv[1];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              int su = dp2a_lo(kua, p[2 * j], C_BIAS); su = dp2a_hi(kub, p[2 * j], su);
-              su = dp2a_lo(kua, p[2 * j + 1], su); su = dp2a_hi(kub, p[2 * j + 1], su);
-              int sv = dp2a_lo(kva, p[2 * j], C_BIAS); sv = dp2a_hi(kvb, p[2 * j], sv);
-              sv = dp2a_lo(kva, p[2 * j + 1], sv); sv = dp2a_hi(kvb, p[2 * j + 1], sv);
-              uv[j] = pack_uv14(su, sv);
-            }
-            sts64(row + lane * 8, uv[0], uv[1]);        // chroma cols 2*lane, 2*lane+1
-            sts64(row + 256 + lane * 8, uv[2], uv[3]);  // chroma cols 64+2*lane, +1
-            if (core) {
-              const uint32_t kya = c.ky[0], kyb = c.ky[1];
-              uint32_t s[8];
+              for (int j = 0; j < 4; j++) {
+                int su = dp2a_lo(kua, p[2 * j], C_BIAS); su = dp2a_hi(kub, p[2 * j], su);
+                su = dp2a_lo(kua, p[2 * j + 1], su); su = dp2a_hi(kub, p[2 * j + 1], su);
+                int sv = dp2a_lo(kva, p[2 * j], C_BIAS); sv = dp2a_hi(kvb, p[2 * j], sv);
+                sv = dp2a_lo(kva, p[2 * j + 1], sv); sv = dp2a_hi(kvb, p[2 * j + 1], sv);
+                uv[j] = pack_uv14(su, sv);
+              }
+              sts64(crow + lane * 8, uv[0], uv[1]);        // chroma cols 2*lane, 2*lane+1
+              sts64(crow + 256 + lane * 8, uv[2], uv[3]);  // chroma cols 64+2*lane, +1
+              if (core) {
+                const uint32_t kya = c.ky[0], kyb = c.ky[1];
+                uint32_t s[8];
 #pragma unroll
-              for (int k = 0; k < 8; k++) s[k] = dp2a_hi_uu(kyb, p[k], dp2a_lo_uu(kya, p[k], 2 * Y_BIAS));
-              yw0 = pack_b2(s[0], s[1], s[2], s[3]);
-              yw1 = pack_b2(s[4], s[5], s[6], s[7]);
-              uint8_t *o = sy + y * sys;
-              store4(o, lane * 4, yw0, tw, vec_out);
-              store4(o, 128 + lane * 4, yw1, tw, vec_out);
-              if (mode != MODE_ROWS && dy) {
-                uint8_t *od = dy + y * dys;
-                store4(od, lane * 4, gray_y4_packed(d4[0]), tw, vec_out);
-                store4(od, 128 + lane * 4, gray_y4_packed(d4[1]), tw, vec_out);
+                for (int k = 0; k < 8; k++) s[k] = dp2a_hi_uu(kyb, p[k], dp2a_lo_uu(kya, p[k], 2 * Y_BIAS));
+                const uint32_t yw0 = pack_b2(s[0], s[1], s[2], s[3]), yw1 = pack_b2(s[4], s[5], s[6], s[7]);
+                uint8_t *o = sy + y * sys;
+                if (fullw) { stg32(o + lane * 4, yw0); stg32(o + 128 + lane * 4, yw1); }
+                else { store4(o, lane * 4, yw0, tw, vec_out); store4(o, 128 + lane * 4, yw1, tw, vec_out); }
+                if (dy) {
+                  uint8_t *od = dy + y * dys;
+                  const uint32_t g0 = gray_y4_packed(d4[0]), g1 = gray_y4_packed(d4[1]);
+                  if (fullw) { stg32(od + lane * 4, g0); stg32(od + 128 + lane * 4, g1); }
+                  else { store4(od, lane * 4, g0, tw, vec_out); store4(od, 128 + lane * 4, g1, tw, vec_out); }
+                }
               }
             }
           }
-        }
-      }
-
-      // ---- depth stream of a single source: Y = range-compressed gray -------------------------
-      if (dy && n_src == 1) {
-        if (depth_regs) {
-          if (depth_lane) {
-            uint8_t *o = dy + lane * 8;
-#pragma unroll
-            for (int i = 0; i < RPW; i++) {
-              const int y = yc0 + warp + i * NW;
-              if (y >= ya && y < yb) *(uint2 *)(o + y * dys) = make_uint2(gray_y4_packed(dreg[i].x), gray_y4_packed(dreg[i].y));
-            }
-          }
-        } else {
-          const uint8_t *dsrc = c.dep[0];
-          const int dstride = c.ds[0];
-          for (int y = ya + warp; y < yb; y += NW)
-            for (int x = lane; x < tw; x += 32) dy[(size_t)y * dys + x] = (uint8_t)gray_y(dsrc[(size_t)y * dstride + x]);
+          // this warp is done with its row of the sub-stage: release it to the producer
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[q0 + i]);
         }
       }
       consumer_sync();
@@ -625,24 +642,30 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
         const int dus = c.dus, dvs = c.dvs;
         const int cA = c.cA, cB = c.cB, H = c.H;
         const bool edge = c.edge != 0;
-        const uint32_t col = px0 + cc * 4;
+        const int rbase = c.rbase;
+        const uint32_t col = ring0 + cc * 4;
         if (cc < cw) {
 #pragma unroll 1
           for (int ci = cA + warp; ci < cB; ci += NW) {
             uint32_t t[8][4];
             if (!edge) {
-              const uint32_t base = col + (uint32_t)((2 * ci - 3 - yc0) * ROWB);
+              int s0 = rbase + (2 * ci - 3 - yc0);  // >= rbase - 6
+              if (s0 < 0) s0 += RING_ROWS;
 #pragma unroll
               for (int j = 0; j < 8; j++) {
-                const uint4 q = lds128(base + j * ROWB);
-                t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
+                int sj = s0 + j;
+                if (sj >= RING_ROWS) sj -= RING_ROWS;
+                const uint4 qv = lds128(col + (uint32_t)(sj * RING_ROWB));
+                t[j][0] = qv.x; t[j][1] = qv.y; t[j][2] = qv.z; t[j][3] = qv.w;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 8; j++) {
-                const int sr = min(max(2 * ci - 3 + j, 0), H - 1) - yc0;
-                const uint4 q = lds128(col + (uint32_t)(sr * ROWB));
-                t[j][0] = q.x; t[j][1] = q.y; t[j][2] = q.z; t[j][3] = q.w;
+                int sj = rbase + min(max(2 * ci - 3 + j, 0), H - 1) - yc0;
+                if (sj < 0) sj += RING_ROWS;
+                if (sj >= RING_ROWS) sj -= RING_ROWS;
+                const uint4 qv = lds128(col + (uint32_t)(sj * RING_ROWB));
+                t[j][0] = qv.x; t[j][1] = qv.y; t[j][2] = qv.z; t[j][3] = qv.w;
               }
             }
             uint32_t us[4], vs[4];
@@ -662,33 +685,28 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
             }
             const uint32_t ub = __byte_perm(__byte_perm(us[0], us[1], 0x0040), __byte_perm(us[2], us[3], 0x0040), 0x5410);
             const uint32_t vb = __byte_perm(__byte_perm(vs[0], vs[1], 0x0040), __byte_perm(vs[2], vs[3], 0x0040), 0x5410);
-            store4(su_ + ci * sus, cc, ub, cw, vec_out);
-            store4(sv_ + ci * svs, cc, vb, cw, vec_out);
-            if (dy) {  // depth chroma planes are constant 128
-              store4(du + ci * dus, cc, 0x80808080u, cw, vec_out);
-              store4(dv + ci * dvs, cc, 0x80808080u, cw, vec_out);
+            if (fullw) {
+              stg32(su_ + ci * sus + cc, ub);
+              stg32(sv_ + ci * svs + cc, vb);
+              if (dy) {  // depth chroma planes are constant 128
+                stg32(du + ci * dus + cc, 0x80808080u);
+                stg32(dv + ci * dvs + cc, 0x80808080u);
+              }
+            } else {
+              store4(su_ + ci * sus, cc, ub, cw, vec_out);
+              store4(sv_ + ci * svs, cc, vb, cw, vec_out);
+              if (dy) {
+                store4(du + ci * dus, cc, 0x80808080u, cw, vec_out);
+                store4(dv + ci * dvs, cc, 0x80808080u, cw, vec_out);
+              }
             }
-          }
-        }
-        // the next chunk of this segment still needs the chroma of our last CARRY_ROWS rows
-        if (c.carry) {
-          const uint32_t from = px0 + (uint32_t)((ch - CARRY_ROWS) * ROWB);
-          const uint32_t to = smem_base + (cur ^ 1) * L::STAGE + (CARRY_ALLOC - CARRY_ROWS) * ROWB;
-#pragma unroll
-          for (int q = 0; q < (CARRY_ROWS * (STRIP_W / 2)) / (32 * NW); q++) {
-            const int idx = tid + q * 32 * NW;
-            const uint32_t off = (uint32_t)(idx >> 7) * ROWB + (uint32_t)(idx & 127) * 4;
-            sts32(to + off, lds32(from + off));
           }
         }
       }
     }
-    // release the stage: order our generic-proxy writes (in-place chroma, stamps) before the
-    // bulk copies that will refill it
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[cur]);
     if (last) break;
+    q0 += CHUNK_ROWS / SUB_ROWS;
+    if (q0 >= ns) { q0 = 0; par ^= 1; }
   }
 }
 
@@ -713,16 +731,17 @@ int frame_strips_init() {
   return 0;
 }
 
-// Host-side planning of a launch: chunk height per job (by source count), one segment height
-// per bpp class (trade: 6 halo rows per segment against the one-unit tail of the persistent
-// grid), unit numbering.  Jobs of the other class (and general jobs) take no units.
+// Host-side planning of a launch: one segment height per bpp class (trade: 6 halo rows per
+// segment against the one-unit tail of the persistent grid; seg_rows + 6 is a multiple of the
+// chunk height so that no staged row is wasted), unit numbering.  Jobs of the other class
+// (and general jobs) take no units.
 void plan_frame_strips(DevJob *jobs, int n_jobs) {
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
   for (int cls = 0; cls < 2; cls++) {
     const int grid = sms * (g_ctas_per_sm[cls] > 0 ? g_ctas_per_sm[cls] : (cls == 0 ? 3 : 2));
-    int best_s = 26;
+    int best_s = CHUNK_ROWS * 2 - 2 * HALO;
     double best_cost = 1e30;
-    for (int S = 26; S <= 250; S += 32) {
+    for (int S = CHUNK_ROWS * 2 - 2 * HALO; S <= 256; S += CHUNK_ROWS) {
       double work = 0;
       long units = 0;
       for (int j = 0; j < n_jobs; j++) {
@@ -742,7 +761,6 @@ void plan_frame_strips(DevJob *jobs, int n_jobs) {
       DevJob &jb = jobs[j];
       jb.unit_base[cls] = base;
       if (jb.general || jb.bpp != 3 + cls) continue;
-      jb.chunk_rows = jb.n_src <= 1 ? 32 : (jb.n_src == 2 ? 16 : 8);
       jb.seg_rows = best_s;
       jb.strips_x = (jb.W + STRIP_W - 1) / STRIP_W;
       jb.segs_y = (jb.H + best_s - 1) / best_s;
@@ -753,20 +771,30 @@ void plan_frame_strips(DevJob *jobs, int n_jobs) {
 }
 
 int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream) {
-  int total[2] = {0, 0};
+  int total[2] = {0, 0}, staged[2] = {1, 1};
   for (int j = 0; j < n_jobs; j++) {
     const DevJob &jb = jobs_host[j];
-    if (!jb.general) total[jb.bpp - 3] += jb.n_units;
+    if (jb.general) continue;
+    total[jb.bpp - 3] += jb.n_units;
+    if (jb.tma_ok && jb.n_src > staged[jb.bpp - 3]) staged[jb.bpp - 3] = jb.n_src;
   }
   int launches = 0;
   if (total[0] > 0) {
+    // one sub-stage slot size per launch (the largest any job needs), so that a slot index means
+    // the same shared-memory range for every unit a CTA walks through
+    const int slot = StripSmem<3>::slot_bytes(staged[0]);
+    const int ns = std::min(NS_MAX, StripSmem<3>::STAGE_BYTES / slot) & ~1;
+    if (ns < 2) return -1;
     const int grid = total[0] < g_num_sms * g_ctas_per_sm[0] ? total[0] : g_num_sms * g_ctas_per_sm[0];
-    k_frame_strips<3><<<grid, CTA_THREADS, StripSmem<3>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[0], counters);
+    k_frame_strips<3><<<grid, CTA_THREADS, StripSmem<3>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[0], counters, ns, slot);
     launches++;
   }
   if (total[1] > 0) {
+    const int slot = StripSmem<4>::slot_bytes(staged[1]);
+    const int ns = std::min(NS_MAX, StripSmem<4>::STAGE_BYTES / slot) & ~1;
+    if (ns < 2) return -1;
     const int grid = total[1] < g_num_sms * g_ctas_per_sm[1] ? total[1] : g_num_sms * g_ctas_per_sm[1];
-    k_frame_strips<4><<<grid, CTA_THREADS, StripSmem<4>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[1], counters + 2);
+    k_frame_strips<4><<<grid, CTA_THREADS, StripSmem<4>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[1], counters + 2, ns, slot);
     launches++;
   }
   return launches;

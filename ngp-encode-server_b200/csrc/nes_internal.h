@@ -12,15 +12,19 @@ namespace nes {
 // Same-size fused kernel geometry (frame_strips.cu, k_frame_strips).  A frame is cut into
 // column strips of STRIP_W pixels; a strip is cut into segments of `seg_rows` output rows
 // (one work unit = one segment of one strip); a CTA walks a segment top to bottom in chunks of
-// `chunk_rows` source rows, carrying the chroma rows the 8-tap vertical filter still needs
-// from chunk to chunk, so the 3+3 halo rows are paid once per segment, not once per chunk.
+// CHUNK_ROWS source rows.  Source rows travel through a ring of SUB_ROWS-row sub-stages filled
+// by 2D tensor-map TMA; the pair-summed chroma rows live in a separate ring of RING_ROWS rows,
+// so the 3+3 halo rows of the 8-tap vertical filter are paid once per segment, not per chunk.
 constexpr int STRIP_W = 256;
 constexpr int HALO = 3;
-constexpr int CHUNK_ROWS_MAX = 32;  // chunk_rows = 32 (1 source), 16 (2 sources), 8 (3-4 sources)
-constexpr int CARRY_ROWS = 6;       // chroma rows of the previous chunk the filter still reads
-constexpr int CARRY_ALLOC = 8;
+constexpr int CHUNK_ROWS = 16;     // source rows per compute chunk (= 2 sub-stages)
+constexpr int SUB_ROWS = 8;        // source rows per TMA sub-stage (one row per consumer warp)
+constexpr int RING_ROWS = 40;      // chroma ring: >= 6 carried rows + 2 chunks
+constexpr int NS_MAX = 8;          // sub-stages in the ring (launch-wide, even, >= 2)
+constexpr int NCTX = 8;            // chunk contexts in flight
+constexpr int TMA_MAX_SOURCES = 4; // composites of more sources are filled by the consumer warps
 constexpr int CONSUMER_WARPS = 8;
-constexpr int CTA_THREADS = 32 * (CONSUMER_WARPS + 1);  // + one producer warp (bulk copies, chunk contexts)
+constexpr int CTA_THREADS = 32 * (CONSUMER_WARPS + 1);  // + one producer warp (TMA, chunk contexts)
 constexpr int HIT_CAP = 256;  // glyph rect tests per overlay chunk
 constexpr int MASK_WORDS = 128;  // per-job bitmap: (32-row band, strip) cells touched by text
 constexpr int MASK_BAND_SHIFT = 5;
@@ -54,7 +58,15 @@ struct DevFilter {
   int32_t pad;
 };
 
-struct DevJob {
+// A CUtensorMap (128 bytes, 64-byte aligned) without dragging <cuda.h> into this header.
+struct alignas(64) TMap {
+  uint64_t opaque[16];
+};
+
+struct alignas(64) DevJob {
+  // 2D tensor maps of the staged planes (u32 elements): packed pixels and GRAY8 depth per source
+  TMap tmap_px[TMA_MAX_SOURCES];
+  TMap tmap_dep[TMA_MAX_SOURCES];
   DevSource src[NES_MAX_SOURCES];
   int32_t n_src;
   int32_t bpp;       // 3 or 4
@@ -74,7 +86,7 @@ struct DevJob {
   const DevPlaced *glyphs;
   const uint8_t *atlas;
   int32_t n_glyphs;
-  int32_t tma_ok;     // single source, 16-byte aligned rows: tiles are staged with bulk async copies
+  int32_t tma_ok;     // 16-byte aligned rows, <= TMA_MAX_SOURCES sources: rows are staged by tensor-map TMA
   int32_t use_mask;   // tile_mask valid (tiles_x*tiles_y <= 32*MASK_WORDS)
   int32_t pad1;
   uint32_t tile_mask[MASK_WORDS];  // bit (band * strips_x + strip) set: a placed glyph intersects that cell
@@ -82,7 +94,6 @@ struct DevJob {
   // k_frame_strips work (same-size jobs only)
   int32_t strips_x, segs_y;
   int32_t seg_rows;    // output rows per segment (even)
-  int32_t chunk_rows;  // source rows per chunk
   int32_t unit_base[2];  // [bpp-3]: units of that bpp class ahead of this job in the batch
   int32_t n_units;
   // dp2a operands for packed 3-byte pixels read as raw words (frame_strips.cu phase A)
@@ -101,7 +112,7 @@ struct DevJob {
 
 // Launchers (kernels.cu).  jobs: device pointer to n_jobs descriptors.
 int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream);
-// Assigns seg_rows / chunk_rows / unit_base of the same-size jobs of a launch (host).
+// Assigns seg_rows / unit_base of the same-size jobs of a launch (host).
 void plan_frame_strips(DevJob *jobs_host, int n_jobs);
 int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
 int launch_composite(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);

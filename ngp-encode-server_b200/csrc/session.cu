@@ -7,6 +7,7 @@
 // the host does: pen arithmetic for the text runs (text.cc), one descriptor (DevJob),
 // at most one pinned staging memcpy each way (none when the caller's buffers are pinned),
 // and 1-3 kernel launches (kernels.cu).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -17,6 +18,7 @@
 #include <mutex>
 #include <string>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include "filter.h"
@@ -83,6 +85,9 @@ struct nes_gpu_session {
   uint8_t *d_atlas = nullptr;
   uint32_t *d_counters = nullptr;  // k_frame_strips work counters (self re-arming), [2] per bpp class
   std::map<std::tuple<int, int, int, int>, FilterSet> filters;
+  // tensor maps of staged planes, keyed by (pointer, stride, width in bytes, rows): a streaming
+  // session cycles through a handful of ring buffers, so encoding happens once per buffer
+  std::map<std::tuple<const void *, int, int, int>, TMap> tmaps;
   nes_timing last{};
   std::string err;
   int sticky = 0;
@@ -341,8 +346,62 @@ void job_alignment(DevJob *jb) {
   if (jb->dy) ov = ov && aligned16(jb->dy, jb->dys) && aligned16(jb->du, jb->dus) && aligned16(jb->dv, jb->dvs);
   jb->in_vec = iv;
   jb->out_vec = ov;
-  // rows staged with bulk async copies: 16-byte aligned rows; composites only for 4-byte pixels
-  jb->tma_ok = iv && (jb->W % 16) == 0 && (jb->n_src == 1 || jb->bpp == 4);
+  // rows staged by tensor-map TMA: 16-byte aligned rows; composites only for 4-byte pixels
+  jb->tma_ok = iv && (jb->W % 16) == 0 && jb->n_src <= TMA_MAX_SOURCES && (jb->n_src == 1 || jb->bpp == 4);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// 2D tensor map over a plane of `rows` rows of `width_bytes` bytes (u32 elements), box =
+// SUB_ROWS rows x one strip (box_bytes).  Rows / columns outside the plane read as zero.
+int plane_tmap(nes_gpu_session *s, const uint8_t *base, int stride, int width_bytes, int rows, int box_bytes, TMap *out) {
+  static_assert(sizeof(TMap) == sizeof(CUtensorMap) && alignof(TMap) >= alignof(CUtensorMap), "TMap mirrors CUtensorMap");
+  const auto key = std::make_tuple((const void *)base, stride, width_bytes, rows);
+  auto it = s->tmaps.find(key);
+  if (it != s->tmaps.end()) { *out = it->second; return NES_OK; }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) { s->err = "cuTensorMapEncodeTiled unavailable"; return NES_ERR_CUDA; }
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {(cuuint64_t)(width_bytes / 4), (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)stride};
+  const cuuint32_t box[2] = {(cuuint32_t)(box_bytes / 4), (cuuint32_t)SUB_ROWS};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { s->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return NES_ERR_CUDA; }
+  if (s->tmaps.size() > 4096) s->tmaps.clear();
+  TMap t;
+  std::memcpy(&t, &m, sizeof(t));
+  s->tmaps.emplace(key, t);
+  *out = t;
+  return NES_OK;
+}
+
+// Tensor maps of every plane the fused kernel stages for this job.
+int job_tmaps(nes_gpu_session *s, DevJob *jb) {
+  if (jb->general || !jb->tma_ok) return NES_OK;
+  const bool dep = jb->dy != nullptr || jb->n_src > 1;
+  for (int k = 0; k < jb->n_src; k++) {
+    int st = plane_tmap(s, jb->src[k].rgb, jb->src[k].rgb_stride, jb->W * jb->bpp, jb->H, STRIP_W * jb->bpp, &jb->tmap_px[k]);
+    if (st) return st;
+    if (dep && (st = plane_tmap(s, jb->src[k].depth, jb->src[k].depth_stride, jb->W, jb->H, STRIP_W, &jb->tmap_dep[k]))) return st;
+  }
+  return NES_OK;
 }
 
 // Text runs -> placed glyph descriptors at dst[0..].  Returns count or negative status.
@@ -368,7 +427,8 @@ int place_text(nes_gpu_session *s, int W, int H, const nes_text_run *runs, int n
 int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, int n, cudaStream_t st) {
   int l = 0;
   l += launch_composite(d_jobs, h_jobs, n, st);
-  l += launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, st);
+  const int r0 = launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, st);
+  if (r0 > 0) l += r0;
   const int r = launch_resize_tiles(d_jobs, h_jobs, n, st);
   if (r > 0) l += r;
   s->launches += (uint64_t)l;
@@ -711,6 +771,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   }
   job_tiles(jb, 0);
   job_alignment(jb);
+  if ((st = job_tmaps(s, jb))) return st;
   job_tile_mask(jb, sl.h_glyphs);
   plan_frame_strips(jb, 1);
 
@@ -854,6 +915,7 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
     job_tiles(jb, tile_base);
     tile_base += jb->tiles_x * jb->tiles_y;
     job_alignment(jb);
+    if ((st = job_tmaps(s, jb))) return st;
     job_tile_mask(jb, bt.h_glyphs + gl_used - n_gl);
   }
   plan_frame_strips(bt.h_jobs, n_frames);
