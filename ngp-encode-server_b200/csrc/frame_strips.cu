@@ -48,6 +48,10 @@ namespace {
 enum { MODE_ROWS = 0, MODE_SELECT = 1, MODE_MATERIALIZED = 2 };
 
 constexpr int DEP_ROWB = STRIP_W;  // bytes of a staged depth row
+// The chroma ring has RING_ROWS logical slots; slots [0, RING_MIRROR) are written twice (also
+// RING_ROWS rows further) so that the 8 consecutive rows a vertical tap window reads never wrap.
+constexpr int RING_MIRROR = 8;
+constexpr int RING_PHYS = RING_ROWS + 8;
 
 // Everything the consumer warps need to know about one chunk, written to shared memory by
 // lane 0 of the producer warp while earlier chunks are being computed.  Plane pointers are
@@ -81,7 +85,7 @@ struct StripSmem {
   static constexpr int STAGE_BYTES = (BPP == 4 ? 80 : 48) * 1024;  // the sub-stage ring
   static constexpr int OFF_RING = STAGE_BYTES;
   static constexpr int RING_ROWB = (STRIP_W / 2) * 4;
-  static constexpr int OFF_CTX = OFF_RING + RING_ROWS * RING_ROWB;
+  static constexpr int OFF_CTX = OFF_RING + RING_PHYS * RING_ROWB;
   static constexpr int CTX_BYTES = ((int)sizeof(ChunkCtx) + 15) & ~15;
   static constexpr int OFF_BAR = OFF_CTX + NCTX * CTX_BYTES;
   static constexpr int OFF_HITS = OFF_BAR + 2 * NS_MAX * 8;
@@ -192,14 +196,11 @@ __device__ __forceinline__ uint32_t pack_b2(uint32_t s0, uint32_t s1, uint32_t s
 }
 
 // GRAY8 -> limited-range luma for the 4 bytes of a word:
-//   Y = (d*219 + 127)/255 + 16, two pixels per multiply in 16-bit lanes;
-//   floor(t/255) == (t + (t >> 8) + 1) >> 8 for every t = d*219 + 127, d in 0..255
+//   Y = (d*219 + 127)/255 + 16 == (d*56282 + 1081500) >> 16 for every d in 0..255 (exhaustive
+//   check in tests/test_host.py); one dp2a per pixel straight from the packed word, Y is byte 2
 __device__ __forceinline__ uint32_t gray_y4_packed(uint32_t w) {
-  const uint32_t p01 = __byte_perm(w, 0u, 0x4140), p23 = __byte_perm(w, 0u, 0x4342);  // d0 | d1<<16 ; d2 | d3<<16
-  const uint32_t t01 = p01 * 219u + 0x007F007Fu, t23 = p23 * 219u + 0x007F007Fu;
-  const uint32_t s01 = t01 + __byte_perm(t01, 0u, 0x4341) + 0x10011001u;  // + (t>>8) + 1 + (16<<8) per lane
-  const uint32_t s23 = t23 + __byte_perm(t23, 0u, 0x4341) + 0x10011001u;
-  return __byte_perm(s01, s23, 0x7531);  // byte 1 of every 16-bit lane
+  constexpr uint32_t A = 56282u, B = 1081500u;
+  return pack_b2(dp2a_lo_uu(A, w, B), dp2a_lo_uu(A << 16, w, B), dp2a_hi_uu(A, w, B), dp2a_hi_uu(A << 16, w, B));
 }
 
 // pair-summed chroma of a horizontal pixel pair -> packed 14-bit (u | v<<16); su, sv include C_BIAS
@@ -454,13 +455,16 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
 
   // ============================= consumer warps ===========================================
   const uint32_t ring0 = smem_base + L::OFF_RING;
-  int q0 = 0, par = 0;
+  int q0 = 0, par0 = 0;  // sub-stage cursor of the chunk's first sub-stage: slot, parity of its use count
   for (int chunk_it = 0;; chunk_it++) {
-    mbar_wait(&s_full[q0], (uint32_t)par);
+    // the second sub-stage of this chunk (the ring may wrap between the two)
+    int q1 = q0 + 1, par1 = par0;
+    if (q1 == ns) { q1 = 0; par1 ^= 1; }
+    mbar_wait(&s_full[q0], (uint32_t)par0);
     const ChunkCtx &c = *(const ChunkCtx *)(smem + L::OFF_CTX + (chunk_it & (NCTX - 1)) * L::CTX_BYTES);
     const int last = c.last;
     {
-      const uint32_t sb0 = smem_base + (uint32_t)(q0 * slot_bytes);
+      const uint32_t sb[2] = {smem_base + (uint32_t)(q0 * slot_bytes), smem_base + (uint32_t)(q1 * slot_bytes)};
       const uint32_t dep_off = (uint32_t)(c.n_staged * SUB_ROWS) * ROWB;
       const int x0 = c.x0, tw = c.tw, yc0 = c.yc0, ra = c.ra, rb = c.rb, ya = c.ya, yb = c.yb;
       const int n_src = c.n_src;
@@ -469,12 +473,11 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
       const bool dep_staged = c.dep_staged != 0;
       uint8_t *const dy = c.dy;
       const int dys = c.dys;
-      bool have1 = false;  // sub-stage 1 already waited for
 
       if (!c.tma || mode == MODE_MATERIALIZED || c.stamp) {
-        mbar_wait(&s_full[q0 + 1], (uint32_t)par);
-        have1 = true;
-        uint8_t *const g0 = smem + q0 * slot_bytes;
+        // whole-chunk work on the staged rows: needs both sub-stages
+        mbar_wait(&s_full[q1], (uint32_t)par1);
+        uint8_t *const g[2] = {smem + q0 * slot_bytes, smem + q1 * slot_bytes};
         // ---- fill our rows ourselves when they were not staged by TMA ------------------------
         if (!c.tma) {
           const DevJob &jb = jobs[c.job];
@@ -482,12 +485,13 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
           for (int i = 0; i < CHUNK_ROWS / SUB_ROWS; i++) {
             const int y = yc0 + warp + i * SUB_ROWS;
             if (y < ra || y >= rb) continue;
-            uint8_t *s = g0 + i * slot_bytes + warp * ROWB;
-            uint8_t *sd = g0 + i * slot_bytes + SUB_ROWS * ROWB + warp * DEP_ROWB;
+            uint8_t *const gi = i ? g[1] : g[0];
+            uint8_t *sp = gi + warp * ROWB;
+            uint8_t *sd = gi + SUB_ROWS * ROWB + warp * DEP_ROWB;
             if (n_src == 1) {
-              const uint8_t *g = jb.src[0].rgb + (size_t)y * jb.src[0].rgb_stride + (size_t)x0 * BPP;
+              const uint8_t *gp = jb.src[0].rgb + (size_t)y * jb.src[0].rgb_stride + (size_t)x0 * BPP;
               const int nbytes = tw * BPP;
-              for (int b = lane; b < nbytes; b += 32) s[b] = g[b];
+              for (int bb = lane; bb < nbytes; bb += 32) sp[bb] = gp[bb];
               if (dep_staged) {
                 const uint8_t *gd = jb.src[0].depth + (size_t)y * jb.src[0].depth_stride + x0;
                 for (int x = lane; x < tw; x += 32) sd[x] = gd[x];
@@ -495,7 +499,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
             } else {
               for (int x = lane; x < tw; x += 32) {
                 uint32_t d;
-                composite_px<BPP>(jb, x0 + x, y, s + x * BPP, &d);
+                composite_px<BPP>(jb, x0 + x, y, sp + x * BPP, &d);
                 sd[x] = (uint8_t)d;
               }
             }
@@ -507,8 +511,9 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
           for (int i = 0; i < CHUNK_ROWS / SUB_ROWS; i++) {
             const int y = yc0 + warp + i * SUB_ROWS;
             if (y < ra || y >= rb) continue;
-            const uint32_t px = sb0 + (uint32_t)(i * slot_bytes) + warp * ROWB;
-            const uint32_t dp = sb0 + (uint32_t)(i * slot_bytes) + dep_off + warp * DEP_ROWB;
+            const uint32_t sbi = i ? sb[1] : sb[0];
+            const uint32_t px = sbi + warp * ROWB;
+            const uint32_t dp = sbi + dep_off + warp * DEP_ROWB;
             uint32_t p[8], d4[2];
             select_staged<ROWB>(px, dp, n_src, c.a_mask, lane, p, d4);
             __syncwarp();
@@ -521,7 +526,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
         }
         __syncwarp();
         // ---- text overlay, stamped into the staged rows of source 0 ----------------------------
-        if (c.stamp) stamp_chunk<BPP>(jobs[c.job], g0, g0 + slot_bytes, x0, x0 + tw, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
+        if (c.stamp) stamp_chunk<BPP>(jobs[c.job], g[0], g[1], x0, x0 + tw, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
         fence_proxy_async();  // our generic-proxy writes to the stage come before the TMA refill
       }
 
@@ -530,17 +535,18 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
         uint8_t *const sy = c.sy;
         const int sys = c.sys;
         const int rbase = c.rbase;
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < CHUNK_ROWS / SUB_ROWS; i++) {
           const int r = warp + i * SUB_ROWS;
           const int y = yc0 + r;
-          if (i == 1 && !have1) mbar_wait(&s_full[q0 + 1], (uint32_t)par);
+          if (i == 1) mbar_wait(&s_full[q1], (uint32_t)par1);
           if (y >= ra && y < rb) {
-            const uint32_t row = sb0 + (uint32_t)(i * slot_bytes) + warp * ROWB;
-            const uint32_t drow = sb0 + (uint32_t)(i * slot_bytes) + dep_off + warp * DEP_ROWB;
+            const uint32_t row = sb[i] + warp * ROWB;
+            const uint32_t drow = sb[i] + dep_off + warp * DEP_ROWB;
             int slot = rbase + r;
             if (slot >= RING_ROWS) slot -= RING_ROWS;
             const uint32_t crow = ring0 + slot * RING_ROWB;
+            const bool mirror = slot < RING_MIRROR;
             const bool core = (y >= ya) && (y < yb);
             uint32_t uv[4];
             if (BPP == 3) {
@@ -560,24 +566,26 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
                 uv[2 * h + 1] = pack_uv14(su1, sv1);
               }
               sts128(crow + lane * 16, uv[0], uv[1], uv[2], uv[3]);  // chroma cols 4*lane..+3
+              if (mirror) sts128(crow + RING_ROWS * RING_ROWB + lane * 16, uv[0], uv[1], uv[2], uv[3]);
               if (core) {
                 const uint32_t y01 = c.ky[0], y2_ = c.ky[1], y_0 = c.ky[2], y12 = c.ky[3];
-                uint32_t s[8];
+                uint32_t sm[8];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                   const uint32_t w0 = w[3 * h], w1 = w[3 * h + 1], w2 = w[3 * h + 2];
-                  s[4 * h] = dp2a_hi_uu(y2_, w0, dp2a_lo_uu(y01, w0, 2 * Y_BIAS));
-                  s[4 * h + 1] = dp2a_lo_uu(y12, w1, dp2a_hi_uu(y_0, w0, 2 * Y_BIAS));
-                  s[4 * h + 2] = dp2a_lo_uu(y2_, w2, dp2a_hi_uu(y01, w1, 2 * Y_BIAS));
-                  s[4 * h + 3] = dp2a_hi_uu(y12, w2, dp2a_lo_uu(y_0, w2, 2 * Y_BIAS));
+                  sm[4 * h] = dp2a_hi_uu(y2_, w0, dp2a_lo_uu(y01, w0, 2 * Y_BIAS));
+                  sm[4 * h + 1] = dp2a_lo_uu(y12, w1, dp2a_hi_uu(y_0, w0, 2 * Y_BIAS));
+                  sm[4 * h + 2] = dp2a_lo_uu(y2_, w2, dp2a_hi_uu(y01, w1, 2 * Y_BIAS));
+                  sm[4 * h + 3] = dp2a_hi_uu(y12, w2, dp2a_lo_uu(y_0, w2, 2 * Y_BIAS));
                 }
-                const uint32_t yw0 = pack_b2(s[0], s[1], s[2], s[3]), yw1 = pack_b2(s[4], s[5], s[6], s[7]);
-                if (fullw) stg64(sy + y * sys + lane * 8, yw0, yw1);
+                const uint32_t yw0 = pack_b2(sm[0], sm[1], sm[2], sm[3]), yw1 = pack_b2(sm[4], sm[5], sm[6], sm[7]);
+                const uint32_t o = (uint32_t)(y * sys + lane * 8);
+                if (fullw) stg64(sy + o, yw0, yw1);
                 else store8(sy + y * sys, lane * 8, yw0, yw1, tw, vec_out);
                 if (dy) {
                   const uint2 dd = lds64(drow + lane * 8);
                   const uint32_t g0 = gray_y4_packed(dd.x), g1 = gray_y4_packed(dd.y);
-                  if (fullw) stg64(dy + y * dys + lane * 8, g0, g1);
+                  if (fullw) stg64(dy + (uint32_t)(y * dys + lane * 8), g0, g1);
                   else store8(dy + y * dys, lane * 8, g0, g1, tw, vec_out);
                 }
               }
@@ -603,27 +611,39 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
               }
               sts64(crow + lane * 8, uv[0], uv[1]);        // chroma cols 2*lane, 2*lane+1
               sts64(crow + 256 + lane * 8, uv[2], uv[3]);  // chroma cols 64+2*lane, +1
+              if (mirror) {
+                sts64(crow + RING_ROWS * RING_ROWB + lane * 8, uv[0], uv[1]);
+                sts64(crow + RING_ROWS * RING_ROWB + 256 + lane * 8, uv[2], uv[3]);
+              }
               if (core) {
                 const uint32_t kya = c.ky[0], kyb = c.ky[1];
-                uint32_t s[8];
+                uint32_t sm[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) s[k] = dp2a_hi_uu(kyb, p[k], dp2a_lo_uu(kya, p[k], 2 * Y_BIAS));
-                const uint32_t yw0 = pack_b2(s[0], s[1], s[2], s[3]), yw1 = pack_b2(s[4], s[5], s[6], s[7]);
-                uint8_t *o = sy + y * sys;
-                if (fullw) { stg32(o + lane * 4, yw0); stg32(o + 128 + lane * 4, yw1); }
-                else { store4(o, lane * 4, yw0, tw, vec_out); store4(o, 128 + lane * 4, yw1, tw, vec_out); }
+                for (int k = 0; k < 8; k++) sm[k] = dp2a_hi_uu(kyb, p[k], dp2a_lo_uu(kya, p[k], 2 * Y_BIAS));
+                const uint32_t yw0 = pack_b2(sm[0], sm[1], sm[2], sm[3]), yw1 = pack_b2(sm[4], sm[5], sm[6], sm[7]);
+                if (fullw) {
+                  uint8_t *o = sy + (uint32_t)(y * sys + lane * 4);
+                  stg32(o, yw0); stg32(o + 128, yw1);
+                } else {
+                  uint8_t *o = sy + y * sys;
+                  store4(o, lane * 4, yw0, tw, vec_out); store4(o, 128 + lane * 4, yw1, tw, vec_out);
+                }
                 if (dy) {
-                  uint8_t *od = dy + y * dys;
                   const uint32_t g0 = gray_y4_packed(d4[0]), g1 = gray_y4_packed(d4[1]);
-                  if (fullw) { stg32(od + lane * 4, g0); stg32(od + 128 + lane * 4, g1); }
-                  else { store4(od, lane * 4, g0, tw, vec_out); store4(od, 128 + lane * 4, g1, tw, vec_out); }
+                  if (fullw) {
+                    uint8_t *od = dy + (uint32_t)(y * dys + lane * 4);
+                    stg32(od, g0); stg32(od + 128, g1);
+                  } else {
+                    uint8_t *od = dy + y * dys;
+                    store4(od, lane * 4, g0, tw, vec_out); store4(od, 128 + lane * 4, g1, tw, vec_out);
+                  }
                 }
               }
             }
           }
           // this warp is done with its row of the sub-stage: release it to the producer
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[q0 + i]);
+          if (lane == 0) mbar_arrive(&s_empty[i ? q1 : q0]);
         }
       }
       consumer_sync();
@@ -636,29 +656,41 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
       {
         const int cc = lane * 4;  // chroma column inside the strip
         const int cw = tw >> 1;
-        uint8_t *const su_ = c.su, *const sv_ = c.sv;
-        const int sus = c.sus, svs = c.svs;
+        const int cA = c.cA, cB = c.cB;
+        const int rbase = c.rbase;
         uint8_t *const du = c.du, *const dv = c.dv;
         const int dus = c.dus, dvs = c.dvs;
-        const int cA = c.cA, cB = c.cB, H = c.H;
-        const bool edge = c.edge != 0;
-        const int rbase = c.rbase;
-        const uint32_t col = ring0 + cc * 4;
+        // depth chroma planes are constant 128: 16-byte stores, one
+        // warp-store covers 4 rows x 128 bytes of one plane
+        if (dy && fullw) {
+          const int ngroups = (cB - cA + 3) >> 2;
+          for (int t = warp; t < 2 * ngroups; t += NW) {
+            const int row = cA + 4 * (t >> 1) + (lane >> 3);
+            if (row < cB) {
+              uint8_t *o = (t & 1) ? dv + (uint32_t)(row * dvs) : du + (uint32_t)(row * dus);
+              *(uint4 *)(o + (lane & 7) * 16) = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+            }
+          }
+        }
         if (cc < cw) {
+          uint8_t *const su_ = c.su, *const sv_ = c.sv;
+          const int sus = c.sus, svs = c.svs;
+          const bool edge = c.edge != 0;
+          const uint32_t col = ring0 + cc * 4;
 #pragma unroll 1
           for (int ci = cA + warp; ci < cB; ci += NW) {
             uint32_t t[8][4];
             if (!edge) {
-              int s0 = rbase + (2 * ci - 3 - yc0);  // >= rbase - 6
+              int s0 = rbase + (2 * ci - 3 - yc0);  // in [rbase - 6, rbase + 8]: rows s0..s0+7 <= 47 never wrap (mirror)
               if (s0 < 0) s0 += RING_ROWS;
+              const uint32_t base = col + (uint32_t)(s0 * RING_ROWB);
 #pragma unroll
               for (int j = 0; j < 8; j++) {
-                int sj = s0 + j;
-                if (sj >= RING_ROWS) sj -= RING_ROWS;
-                const uint4 qv = lds128(col + (uint32_t)(sj * RING_ROWB));
+                const uint4 qv = lds128(base + j * RING_ROWB);
                 t[j][0] = qv.x; t[j][1] = qv.y; t[j][2] = qv.z; t[j][3] = qv.w;
               }
             } else {
+              const int H = c.H;
 #pragma unroll
               for (int j = 0; j < 8; j++) {
                 int sj = rbase + min(max(2 * ci - 3 + j, 0), H - 1) - yc0;
@@ -686,12 +718,8 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
             const uint32_t ub = __byte_perm(__byte_perm(us[0], us[1], 0x0040), __byte_perm(us[2], us[3], 0x0040), 0x5410);
             const uint32_t vb = __byte_perm(__byte_perm(vs[0], vs[1], 0x0040), __byte_perm(vs[2], vs[3], 0x0040), 0x5410);
             if (fullw) {
-              stg32(su_ + ci * sus + cc, ub);
-              stg32(sv_ + ci * svs + cc, vb);
-              if (dy) {  // depth chroma planes are constant 128
-                stg32(du + ci * dus + cc, 0x80808080u);
-                stg32(dv + ci * dvs + cc, 0x80808080u);
-              }
+              stg32(su_ + (uint32_t)(ci * sus + cc), ub);
+              stg32(sv_ + (uint32_t)(ci * svs + cc), vb);
             } else {
               store4(su_ + ci * sus, cc, ub, cw, vec_out);
               store4(sv_ + ci * svs, cc, vb, cw, vec_out);
@@ -705,8 +733,8 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
       }
     }
     if (last) break;
-    q0 += CHUNK_ROWS / SUB_ROWS;
-    if (q0 >= ns) { q0 = 0; par ^= 1; }
+    q0 = q1 + 1; par0 = par1;
+    if (q0 == ns) { q0 = 0; par0 ^= 1; }
   }
 }
 
@@ -783,7 +811,7 @@ int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_j
     // one sub-stage slot size per launch (the largest any job needs), so that a slot index means
     // the same shared-memory range for every unit a CTA walks through
     const int slot = StripSmem<3>::slot_bytes(staged[0]);
-    const int ns = std::min(NS_MAX, StripSmem<3>::STAGE_BYTES / slot) & ~1;
+    const int ns = std::min(NS_MAX, StripSmem<3>::STAGE_BYTES / slot);
     if (ns < 2) return -1;
     const int grid = total[0] < g_num_sms * g_ctas_per_sm[0] ? total[0] : g_num_sms * g_ctas_per_sm[0];
     k_frame_strips<3><<<grid, CTA_THREADS, StripSmem<3>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[0], counters, ns, slot);
@@ -791,7 +819,7 @@ int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_j
   }
   if (total[1] > 0) {
     const int slot = StripSmem<4>::slot_bytes(staged[1]);
-    const int ns = std::min(NS_MAX, StripSmem<4>::STAGE_BYTES / slot) & ~1;
+    const int ns = std::min(NS_MAX, StripSmem<4>::STAGE_BYTES / slot);
     if (ns < 2) return -1;
     const int grid = total[1] < g_num_sms * g_ctas_per_sm[1] ? total[1] : g_num_sms * g_ctas_per_sm[1];
     k_frame_strips<4><<<grid, CTA_THREADS, StripSmem<4>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[1], counters + 2, ns, slot);

@@ -20,7 +20,7 @@ constexpr int HALO = 3;
 constexpr int CHUNK_ROWS = 16;     // source rows per compute chunk (= 2 sub-stages)
 constexpr int SUB_ROWS = 8;        // source rows per TMA sub-stage (one row per consumer warp)
 constexpr int RING_ROWS = 40;      // chroma ring: >= 6 carried rows + 2 chunks
-constexpr int NS_MAX = 8;          // sub-stages in the ring (launch-wide, even, >= 2)
+constexpr int NS_MAX = 8;          // sub-stages in the ring (launch-wide, >= 2)
 constexpr int NCTX = 8;            // chunk contexts in flight
 constexpr int TMA_MAX_SOURCES = 4; // composites of more sources are filled by the consumer warps
 constexpr int CONSUMER_WARPS = 8;

@@ -91,3 +91,13 @@ def test_bench_reference_arm_line():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["config"]["workload"] == "c2_1080p_2src_composite" and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+
+
+def test_gray_luma_dp2a_constants():
+    """k_frame_strips computes the GRAY8 range compression with one dp2a per pixel:
+    (d*56282 + 1081500) >> 16 must equal libswscale's ((((d<<7)*14071 + 33561472) >> 14) + 64) >> 7
+     for every byte, and stay below 2^24 (Y is byte 2 of the sum)."""
+    for d in range(256):
+        want = ((((d << 7) * 14071 + 33561472) >> 14) + 64) >> 7
+        s = d * 56282 + 1081500
+        assert s < (1 << 24) and (s >> 16) == want == (d * 219 + 127) // 255 + 16
