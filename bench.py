@@ -243,7 +243,7 @@ def main():
     ysz, csz = n.align32(wd) * hd, n.align32(wd // 2) * (hd // 2)
     out_bytes = 2 * (ysz + 2 * csz)
     B = max(2, min(64, int(np.ceil(RING_TARGET_BYTES / (in_bytes + out_bytes)))))
-    composite_resize = wl["n_src"] > 1 and (w != wd or h != hd)  # needs the per-slot scratch frame -> submit path only
+    composite_resize = False  # composite + resize is one fused kernel now: every workload takes the batched path
 
     # ---- B distinct frames: pinned host copies + device copies
     host_frames, dev_frames, fins_dev, fouts_dev, fins_host, fouts_host, runs_made = [], [], [], [], [], [], []
@@ -403,7 +403,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload)
-    kernel = "k_resize_tiles" if (w != wd or h != hd) else f"k_frame_strips<{bpp}>"
+    kernel = f"k_resize_tiles<{bpp}>" if (w != wd or h != hd) else f"k_frame_strips<{bpp}>"
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "kernel": kernel, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg * B, "launch_us": round(launch_s * 1e6, 2)}
 

@@ -1,4 +1,4 @@
-// nes_internal.h -- device-visible job descriptors shared by kernels.cu and session.cu.
+// nes_internal.h -- device-visible job descriptors shared by the kernel files and session.cu.
 // Not part of the public ABI (include/nes_gpu.h is).
 #ifndef NES_INTERNAL_H_
 #define NES_INTERNAL_H_
@@ -29,9 +29,39 @@ constexpr int HIT_CAP = 256;  // glyph rect tests per overlay chunk
 constexpr int MASK_WORDS = 128;  // per-job bitmap: (32-row band, strip) cells touched by text
 constexpr int MASK_BAND_SHIFT = 5;
 
-// Resize tile geometry (k_resize_tiles): destination pixels per CTA.
-constexpr int RS_TILE_W = 64;
-constexpr int RS_TILE_H = 16;
+// Resize kernel (resize_tiles.cu, k_resize_tiles): one CTA per destination tile of rs_tw x rs_th
+// luma samples (per size pair, chosen on the host so that two CTAs fit an SM when possible).
+constexpr int RS_THREADS = 256;
+constexpr int RS_SMEM_MAX = 200 * 1024;   // one tile must fit this
+constexpr int RS_SMEM_GOAL = 104 * 1024;  // two CTAs per SM
+
+#if defined(__CUDACC__)
+#define NES_HD __host__ __device__
+#else
+#define NES_HD
+#endif
+// Shared-memory layout of one resize tile (byte offsets; every region 16-byte aligned).
+struct RsLayout {
+  int y14, u14, v14, hy, hu, hv, dep, mask, hits, total;
+};
+// wh x ww: union source window (ww multiple of 4), cww: chroma plane row stride, nl / nc: luma /
+// chroma source rows fed to the vertical pass, dwp / dcwp: padded destination widths
+NES_HD inline RsLayout rs_layout(int wh, int ww, int cww, int nl, int nc, int dwp, int dcwp, int hit_cap) {
+  RsLayout L;
+  int o = 0;
+  auto take = [&](int bytes) { const int at = o; o += (bytes + 16 + 15) & ~15; return at; };  // +16: tap loops may over-read
+  L.y14 = take(wh * ww * 2);
+  L.u14 = take(wh * cww * 2);
+  L.v14 = take(wh * cww * 2);
+  L.hy = take(nl * dwp * 2);
+  L.hu = take(nc * dcwp * 2);
+  L.hv = take(nc * dcwp * 2);
+  L.dep = take(wh * ww);
+  L.mask = take(wh * ((ww >> 5) + 1) * 4);
+  L.hits = take(hit_cap * 4 + 16);
+  L.total = o;
+  return L;
+}
 // Below this source height libswscale's vertical chroma filter has fewer than 8 taps
 // (initFilter clamps the size to srcH-2), so the fused same-size kernel does not apply.
 constexpr int MIN_FUSED_H = 12;
@@ -105,17 +135,16 @@ struct alignas(64) DevJob {
   int32_t csW;   // chroma source width fed to the H pass
   int32_t rs_smem;  // shared memory the resize kernel needs for this job's worst tile (host use)
   int32_t general;  // 1: k_resize_tiles (any size change, or H < 12 where libswscale's chroma filter is truncated)
-  // composite scratch (resize of a composite goes through a scratch frame)
-  uint8_t *scratch_rgb;
-  uint8_t *scratch_depth;
+  int32_t rs_tw, rs_th;     // destination tile of the resize kernel
+  const int32_t *rs_win_x;  // [tiles_x][4]: luma source columns [lc0, lc1), chroma source columns [cc0, cc1)
+  const int32_t *rs_win_y;  // [tiles_y][4]: luma source rows [lr0, lr1), chroma source rows [cr0, cr1)
 };
 
-// Launchers (kernels.cu).  jobs: device pointer to n_jobs descriptors.
+// Launchers (frame_strips.cu, resize_tiles.cu).  jobs: device pointer to n_jobs descriptors.
 int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream);
 // Assigns seg_rows / unit_base of the same-size jobs of a launch (host).
 void plan_frame_strips(DevJob *jobs_host, int n_jobs);
 int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
-int launch_composite(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
 int kernels_init();  // opt-in shared memory sizes; returns cudaError_t
 int frame_strips_init();
 

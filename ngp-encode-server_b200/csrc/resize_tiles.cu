@@ -1,0 +1,399 @@
+// resize_tiles.cu -- k_resize_tiles: the general bicubic path (any size change, and frames
+// under 12 rows where libswscale truncates the vertical chroma filter).
+//
+// What it computes: libswscale's generic C path as the reference drives it
+// (/root/reference/src/base/video/type_managers.cc:143-155 via rendered_frame.h:24-33, after the
+// overlay of render_text.cc:81-110); integer spec in SURVEY.md Appendix A.3 / A.4:
+//   scene : RGB(A) -> 14-bit Y / (pair-summed) U,V -> horizontal polyphase (>>13, 15 bit)
+//           -> vertical polyphase (>>19) -> 8 bit planes
+//   depth : GRAY8 -> horizontal polyphase (>>7) -> range compression -> vertical; U = V = 128
+// with the filter tables of csrc/filter.cc (bit-identical to initFilter's).
+//
+// Shape (HBM-bound in principle: every source byte is read once from DRAM, halos hit L2):
+//   * one CTA per destination tile (rs_tw x rs_th luma samples, chosen per size pair so that
+//     two CTAs fit an SM); the source window of a tile comes from per-tile-column / per-tile-row
+//     tables built on the host with the filter (no scanning on the device);
+//   * stage A reads the window straight from global memory, 4 pixels per lane (16-byte loads of
+//     every source + 4 depth bytes), does the depth-select composite in registers and the glyph
+//     overlay from a per-tile bit mask, and writes 14-bit planes (int16) + depth bytes to shared
+//     memory: no packed-pixel tile, no scratch frame, the composite costs no extra pass;
+//   * stage H: lane = destination column (its taps live in registers), warp = source row;
+//   * stage V: lane = 4 adjacent destination columns (8-byte shared loads), 4-byte stores.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_common.cuh"
+#include "nes_internal.h"
+
+namespace nes {
+
+namespace {
+
+__device__ __forceinline__ int dp2a_lo_s(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi_s(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// coefficient . colour bytes of one pixel word (k0: bytes 0,1; k1: bytes 2,3; non-colour bytes carry 0)
+__device__ __forceinline__ int dot_px(uint32_t k0, uint32_t k1, uint32_t px, int acc) { return dp2a_hi_s(k1, px, dp2a_lo_s(k0, px, acc)); }
+
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ int sext_lo(uint32_t w) {  // sign-extended low half (prmt: selector bit 3 replicates the sign of the byte)
+  int d;
+  asm("prmt.b32 %0, %1, %1, 0x9910;" : "=r"(d) : "r"(w));
+  return d;
+}
+__device__ __forceinline__ int sext_hi(uint32_t w) { return (int)w >> 16; }
+
+// 4 pixels at columns x..x+3 of row y as pixel words (3-byte pixels: r | g<<8 | b<<16 | junk<<24,
+// the junk byte has coefficient 0) + their 4 depth bytes, after the depth-select composite.
+template <int BPP>
+__device__ __forceinline__ void load_group(const DevJob &jb, int x, int y, bool want_depth, uint32_t (&px)[4], uint32_t *d4) {
+  const int W = jb.W;
+  if (jb.in_vec && x + 4 <= W && (BPP == 4 || jb.n_src == 1)) {
+    if (jb.n_src == 1) {
+      const uint8_t *p = jb.src[0].rgb + (size_t)y * jb.src[0].rgb_stride + (size_t)x * BPP;
+      if (BPP == 4) {
+        const uint4 q = __ldg((const uint4 *)p);
+        px[0] = q.x; px[1] = q.y; px[2] = q.z; px[3] = q.w;
+      } else {
+        const uint32_t w0 = __ldg((const uint32_t *)p), w1 = __ldg((const uint32_t *)p + 1), w2 = __ldg((const uint32_t *)p + 2);
+        px[0] = w0;
+        px[1] = __funnelshift_r(w0, w1, 24);
+        px[2] = __funnelshift_r(w1, w2, 16);
+        px[3] = w2 >> 8;
+      }
+      *d4 = want_depth ? __ldg((const uint32_t *)(jb.src[0].depth + (size_t)y * jb.src[0].depth_stride + x)) : 0u;
+    } else {
+      uint4 q;
+      composite_px4(jb, x, y, &q, d4);
+      px[0] = q.x; px[1] = q.y; px[2] = q.z; px[3] = q.w;
+    }
+    return;
+  }
+  // unaligned sources, 3-byte composites, the ragged right edge: per pixel
+  *d4 = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    px[i] = 0;
+    if (x + i >= W) continue;
+    uint8_t b[4] = {0, 0, 0, 0};
+    uint32_t d = 0;
+    if (jb.n_src == 1) {
+      const uint8_t *p = jb.src[0].rgb + (size_t)y * jb.src[0].rgb_stride + (size_t)(x + i) * BPP;
+#pragma unroll
+      for (int c = 0; c < BPP; c++) b[c] = p[c];
+      if (want_depth) d = jb.src[0].depth[(size_t)y * jb.src[0].depth_stride + x + i];
+    } else {
+      composite_px<BPP>(jb, x + i, y, b, &d);
+    }
+    px[i] = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
+    *d4 |= d << (8 * i);
+  }
+}
+
+struct Tile {
+  int dx0, dw, dwp, dy0, dh;      // destination luma block (dwp: row stride of the H-pass output, multiple of 4)
+  int cx0, dcw, dcwp, cy0, dch;   // destination chroma block
+  int lc0, lc1, lr0, lr1;         // luma source columns / rows
+  int cc0, cc1, cr0, cr1;         // chroma source columns (chroma-source units) / rows
+  int wx0, ww, wy0, wh;           // union source window in pixels (wx0, ww multiples of 4)
+  int cww;                        // chroma plane row stride (ww/2 when pair-summed, else ww)
+};
+
+// horizontal polyphase of one plane: out[row][dx] = min((sum_j in[row][pos[dx]+j] * f[dx][j]) >> SH, 32767)
+template <int T, typename LoadFn, typename StoreFn>
+__device__ __forceinline__ void hpass(const DevFilter &f, int d0, int n_dst, int n_rows, int lane, int warp, LoadFn load, StoreFn store) {
+  for (int db = 0; db < n_dst; db += 32) {
+    const int dx = db + lane;
+    if (dx >= n_dst) continue;
+    const int pos = f.pos[d0 + dx];
+    const int16_t *cf = f.coef + (size_t)(d0 + dx) * f.size;
+    if (T > 0) {
+      int c[T > 0 ? T : 1];
+#pragma unroll
+      for (int j = 0; j < T; j++) c[j] = j < f.size ? (int)cf[j] : 0;
+      for (int row = warp; row < n_rows; row += RS_THREADS / 32) {
+        int v = 0;
+#pragma unroll
+        for (int j = 0; j < T; j++) v += load(row, pos + j) * c[j];
+        store(row, dx, v);
+      }
+    } else {
+      for (int row = warp; row < n_rows; row += RS_THREADS / 32) {
+        int v = 0;
+        for (int j = 0; j < f.size; j++) v += load(row, pos + j) * (int)cf[j];
+        store(row, dx, v);
+      }
+    }
+  }
+}
+
+template <typename LoadFn, typename StoreFn>
+__device__ __forceinline__ void hpass_any(const DevFilter &f, int d0, int n_dst, int n_rows, int lane, int warp, LoadFn load, StoreFn store) {
+  if (f.size <= 4) hpass<4>(f, d0, n_dst, n_rows, lane, warp, load, store);
+  else if (f.size <= 6) hpass<6>(f, d0, n_dst, n_rows, lane, warp, load, store);
+  else if (f.size <= 8) hpass<8>(f, d0, n_dst, n_rows, lane, warp, load, store);
+  else if (f.size <= 12) hpass<12>(f, d0, n_dst, n_rows, lane, warp, load, store);
+  else hpass<0>(f, d0, n_dst, n_rows, lane, warp, load, store);
+}
+
+// vertical polyphase of one 15-bit plane (row stride `stride` int16, origin row r0) to an 8-bit
+// plane: 4 adjacent columns per thread
+__device__ __forceinline__ void vpass(const DevFilter &f, const int16_t *s_in, int stride, int r0, int d0y, int n_rows, int n_cols, uint8_t *dst,
+                                      int dst_stride, bool vec, int tid) {
+  const int ngrp = (n_cols + 3) >> 2;
+  const int total = n_rows * ngrp;
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_in);
+  for (int idx = tid; idx < total; idx += RS_THREADS) {
+    const int ry = idx / ngrp, gx = idx - ry * ngrp;
+    const int yy = d0y + ry;
+    const int pos = f.pos[yy] - r0;
+    uint32_t a = s_base + (uint32_t)(pos * stride + 4 * gx) * 2;
+    int o[4];
+    if (f.size == 1) {
+      uint2 w;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(a));
+      o[0] = (sext_lo(w.x) + 64) >> 7; o[1] = (sext_hi(w.x) + 64) >> 7; o[2] = (sext_lo(w.y) + 64) >> 7; o[3] = (sext_hi(w.y) + 64) >> 7;
+    } else {
+      const int16_t *cf = f.coef + (size_t)yy * f.size;
+      int v0 = 64 << 12, v1 = 64 << 12, v2 = 64 << 12, v3 = 64 << 12;
+      for (int j = 0; j < f.size; j++, a += stride * 2) {
+        const int c = cf[j];
+        uint2 w;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(a));
+        v0 += sext_lo(w.x) * c; v1 += sext_hi(w.x) * c; v2 += sext_lo(w.y) * c; v3 += sext_hi(w.y) * c;
+      }
+      o[0] = v0 >> 19; o[1] = v1 >> 19; o[2] = v2 >> 19; o[3] = v3 >> 19;
+    }
+    uint8_t *p = dst + (size_t)yy * dst_stride + 4 * gx;
+    if (vec && 4 * gx + 4 <= n_cols) {
+      *(uint32_t *)p = (uint32_t)clip8(o[0]) | ((uint32_t)clip8(o[1]) << 8) | ((uint32_t)clip8(o[2]) << 16) | ((uint32_t)clip8(o[3]) << 24);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (4 * gx + k < n_cols) p[k] = (uint8_t)clip8(o[k]);
+    }
+  }
+}
+
+}  // namespace
+
+template <int BPP>
+__global__ void __launch_bounds__(RS_THREADS, 2) k_resize_tiles(const DevJob *__restrict__ jobs, int n_jobs, int smem_cap) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  int tile;
+  const DevJob *jp = find_job(jobs, n_jobs, blockIdx.x, &tile);
+  if (!jp->general || jp->bpp != BPP) return;
+  const DevJob &jb = *jp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARP = RS_THREADS / 32;
+  const int tx = tile % jb.tiles_x, ty = tile / jb.tiles_x;
+  const int W = jb.W, Wd = jb.Wd, Hd = jb.Hd;
+  const int cdW = (Wd + 1) >> 1, cdH = (Hd + 1) >> 1;
+  const bool half = jb.half != 0;
+  const bool want_depth = jb.dy != nullptr;
+
+  Tile t;
+  t.dx0 = tx * jb.rs_tw; t.dw = min(jb.rs_tw, Wd - t.dx0); t.dwp = (t.dw + 3) & ~3;
+  t.dy0 = ty * jb.rs_th; t.dh = min(jb.rs_th, Hd - t.dy0);
+  t.cx0 = t.dx0 >> 1; t.dcw = min((t.dx0 + t.dw + 1) >> 1, cdW) - t.cx0; t.dcwp = (t.dcw + 3) & ~3;
+  t.cy0 = t.dy0 >> 1; t.dch = min((t.dy0 + t.dh + 1) >> 1, cdH) - t.cy0;
+  {
+    const int4 wx = __ldg((const int4 *)jb.rs_win_x + tx), wy = __ldg((const int4 *)jb.rs_win_y + ty);
+    t.lc0 = wx.x; t.lc1 = wx.y; t.cc0 = wx.z; t.cc1 = wx.w;
+    t.lr0 = wy.x; t.lr1 = wy.y; t.cr0 = wy.z; t.cr1 = wy.w;
+  }
+  const int pc0 = half ? t.cc0 * 2 : t.cc0, pc1 = half ? t.cc1 * 2 : t.cc1;
+  t.wx0 = min(t.lc0, pc0) & ~3;
+  t.ww = ((max(t.lc1, pc1) - t.wx0) + 3) & ~3;
+  t.wy0 = min(t.lr0, t.cr0);
+  t.wh = max(t.lr1, t.cr1) - t.wy0;
+  t.cww = half ? t.ww >> 1 : t.ww;
+  const int nl = t.lr1 - t.lr0, nc = t.cr1 - t.cr0;
+
+  // shared memory carve-up (rs_layout is shared with the host's sizing code)
+  const RsLayout L = rs_layout(t.wh, t.ww, t.cww, nl, nc, t.dwp, t.dcwp, HIT_CAP);
+  int16_t *s_y14 = (int16_t *)(smem + L.y14);  // [wh][ww]
+  int16_t *s_u14 = (int16_t *)(smem + L.u14);  // [wh][cww]
+  int16_t *s_v14 = (int16_t *)(smem + L.v14);
+  int16_t *s_hy = (int16_t *)(smem + L.hy);    // [nl][dwp]
+  int16_t *s_hu = (int16_t *)(smem + L.hu);    // [nc][dcwp]
+  int16_t *s_hv = (int16_t *)(smem + L.hv);
+  uint8_t *s_dep = smem + L.dep;               // [wh][ww]
+  const int mw = (t.ww >> 5) + 1;
+  uint32_t *s_mask = (uint32_t *)(smem + L.mask);  // [wh][mw] overlay bits
+  int *s_hits = (int *)(smem + L.hits);
+  int *s_nhits = s_hits + HIT_CAP;
+  if (L.total > smem_cap) { __trap(); }
+
+  // ---- overlay bit mask of the window (render_text.cc:94-106: coverage != 0 -> white) --------
+  bool has_text = false;
+  if (jb.n_glyphs > 0) {
+    for (int i = tid; i < t.wh * mw; i += RS_THREADS) s_mask[i] = 0;
+    const int x1 = t.wx0 + t.ww, y1 = t.wy0 + t.wh;
+    int any = 0;
+    for (int base = 0; base < jb.n_glyphs; base += HIT_CAP) {
+      if (tid == 0) *s_nhits = 0;
+      __syncthreads();
+      for (int g = base + tid; g < min(base + HIT_CAP, jb.n_glyphs); g += RS_THREADS) {
+        const DevPlaced pg = jb.glyphs[g];
+        if (pg.x < x1 && pg.x + pg.w > t.wx0 && pg.y < y1 && pg.y + pg.h > t.wy0) s_hits[atomicAdd(s_nhits, 1)] = g;
+      }
+      __syncthreads();
+      const int nh = *s_nhits;
+      any |= nh;
+      for (int h = warp; h < nh; h += NWARP) {
+        const DevPlaced pg = jb.glyphs[s_hits[h]];
+        const uint8_t *cov = jb.atlas + pg.atlas_off;
+        const int q0 = max(0, t.wy0 - pg.y), q1 = min(pg.h, y1 - pg.y);
+        const int p0 = max(0, t.wx0 - pg.x), p1 = min(pg.w, x1 - pg.x);
+        for (int q = q0; q < q1; q++)
+          for (int p = p0 + lane; p < p1; p += 32)
+            if (cov[q * pg.pitch + p]) {
+              const int xx = pg.x + p - t.wx0;
+              atomicOr(&s_mask[(pg.y + q - t.wy0) * mw + (xx >> 5)], 1u << (xx & 31));
+            }
+      }
+      __syncthreads();
+    }
+    has_text = any != 0;
+  }
+
+  // ---- stage A: source window -> 14-bit planes + depth bytes ------------------------------------
+  {
+    const uint32_t ky0 = jb.ky[0], ky1 = jb.ky[1], ku0 = jb.ku[0], ku1 = jb.ku[1], kv0 = jb.kv[0], kv1 = jb.kv[1];
+    const uint32_t white = BPP == 4 ? (0x00FFFFFFu << (8 * jb.rgb_base)) : 0x00FFFFFFu;
+    const int ngrp = t.ww >> 2;
+    for (int r = warp; r < t.wh; r += NWARP) {
+      const int y = t.wy0 + r;
+      for (int g = lane; g < ngrp; g += 32) {
+        uint32_t px[4], d4;
+        load_group<BPP>(jb, t.wx0 + 4 * g, y, want_depth, px, &d4);
+        if (has_text) {
+          const uint32_t m = (s_mask[r * mw + (g >> 3)] >> ((4 * g) & 31)) & 15u;
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if ((m >> i) & 1u) px[i] |= white;
+        }
+        int yv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) yv[i] = dot_px(ky0, ky1, px[i], (32 << 14) + (1 << 8)) >> 9;
+        *(uint2 *)(s_y14 + r * t.ww + 4 * g) = make_uint2(pack16(yv[0], yv[1]), pack16(yv[2], yv[3]));
+        if (half) {
+          int u[2], v[2];
+#pragma unroll
+          for (int p = 0; p < 2; p++) {
+            u[p] = dot_px(ku0, ku1, px[2 * p + 1], dot_px(ku0, ku1, px[2 * p], C_BIAS)) >> 10;
+            v[p] = dot_px(kv0, kv1, px[2 * p + 1], dot_px(kv0, kv1, px[2 * p], C_BIAS)) >> 10;
+          }
+          *(uint32_t *)(s_u14 + r * t.cww + 2 * g) = pack16(u[0], u[1]);
+          *(uint32_t *)(s_v14 + r * t.cww + 2 * g) = pack16(v[0], v[1]);
+        } else {
+          int u[4], v[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            u[i] = dot_px(ku0, ku1, px[i], C1_BIAS) >> 9;
+            v[i] = dot_px(kv0, kv1, px[i], C1_BIAS) >> 9;
+          }
+          *(uint2 *)(s_u14 + r * t.cww + 4 * g) = make_uint2(pack16(u[0], u[1]), pack16(u[2], u[3]));
+          *(uint2 *)(s_v14 + r * t.cww + 4 * g) = make_uint2(pack16(v[0], v[1]), pack16(v[2], v[3]));
+        }
+        if (want_depth) *(uint32_t *)(s_dep + r * t.ww + 4 * g) = d4;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- stage H: horizontal polyphase, hScale16To15 (>>13, clamp 32767) ----------------------------
+  {
+    const int16_t *ly = s_y14 + (t.lr0 - t.wy0) * t.ww - t.wx0;
+    hpass_any(jb.hl, t.dx0, t.dw, nl, lane, warp,
+              [&](int row, int x) { return (int)(uint16_t)ly[row * t.ww + x]; },
+              [&](int row, int dx, int v) { s_hy[row * t.dwp + dx] = (int16_t)min(v >> 13, 32767); });
+    const int corg = half ? (t.wx0 >> 1) : t.wx0;
+    const int16_t *lu = s_u14 + (t.cr0 - t.wy0) * t.cww - corg, *lv = s_v14 + (t.cr0 - t.wy0) * t.cww - corg;
+    hpass_any(jb.hc, t.cx0, t.dcw, nc, lane, warp,
+              [&](int row, int x) { return (int)(uint16_t)lu[row * t.cww + x]; },
+              [&](int row, int dx, int v) { s_hu[row * t.dcwp + dx] = (int16_t)min(v >> 13, 32767); });
+    hpass_any(jb.hc, t.cx0, t.dcw, nc, lane, warp,
+              [&](int row, int x) { return (int)(uint16_t)lv[row * t.cww + x]; },
+              [&](int row, int dx, int v) { s_hv[row * t.dcwp + dx] = (int16_t)min(v >> 13, 32767); });
+  }
+  __syncthreads();
+
+  // ---- stage V: vertical polyphase to 8 bit (yuv2planeX / yuv2plane1) ----------------------------
+  const bool vec = jb.out_vec != 0;
+  vpass(jb.vl, s_hy, t.dwp, t.lr0, t.dy0, t.dh, t.dw, jb.sy + t.dx0, jb.sys, vec, tid);
+  vpass(jb.vc, s_hu, t.dcwp, t.cr0, t.cy0, t.dch, t.dcw, jb.su + t.cx0, jb.sus, vec, tid);
+  vpass(jb.vc, s_hv, t.dcwp, t.cr0, t.cy0, t.dch, t.dcw, jb.sv + t.cx0, jb.svs, vec, tid);
+
+  // ---- depth: hScale8To15 (>>7) -> range compression -> vertical; U = V = 128 ----------------------
+  if (want_depth) {
+    __syncthreads();  // s_hy is reused
+    const uint8_t *ld = s_dep + (t.lr0 - t.wy0) * t.ww - t.wx0;
+    hpass_any(jb.hl, t.dx0, t.dw, nl, lane, warp,
+              [&](int row, int x) { return (int)ld[row * t.ww + x]; },
+              [&](int row, int dx, int v) {
+                v = min(v >> 7, 32767);
+                s_hy[row * t.dwp + dx] = (int16_t)((v * 14071 + 33561472) >> 14);
+              });
+    __syncthreads();
+    vpass(jb.vl, s_hy, t.dwp, t.lr0, t.dy0, t.dh, t.dw, jb.dy + t.dx0, jb.dys, vec, tid);
+    const int ngrp = (t.dcw + 3) >> 2;
+    for (int idx = tid; idx < t.dch * ngrp; idx += RS_THREADS) {
+      const int ry = idx / ngrp, gx = idx - ry * ngrp;
+      uint8_t *pu = jb.du + (size_t)(t.cy0 + ry) * jb.dus + t.cx0 + 4 * gx, *pv = jb.dv + (size_t)(t.cy0 + ry) * jb.dvs + t.cx0 + 4 * gx;
+      if (vec && 4 * gx + 4 <= t.dcw) {
+        *(uint32_t *)pu = 0x80808080u; *(uint32_t *)pv = 0x80808080u;
+      } else {
+        for (int k = 0; k < 4; k++)
+          if (4 * gx + k < t.dcw) { pu[k] = 128; pv[k] = 128; }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+static int g_resize_smem_cap = 0;
+
+int kernels_init() {
+  cudaError_t e;
+  if (int r = frame_strips_init()) return r;
+  g_resize_smem_cap = RS_SMEM_MAX;
+  e = cudaFuncSetAttribute(k_resize_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_resize_smem_cap);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_resize_tiles<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_resize_smem_cap);
+  if (e != cudaSuccess) return (int)e;
+  return 0;
+}
+
+int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream) {
+  int total = 0, smem[2] = {0, 0};
+  bool any[2] = {false, false};
+  for (int j = 0; j < n_jobs; j++) {
+    const DevJob &jb = jobs_host[j];
+    total = jb.tile_base + jb.tiles_x * jb.tiles_y;
+    if (jb.general) { any[jb.bpp - 3] = true; smem[jb.bpp - 3] = jb.rs_smem > smem[jb.bpp - 3] ? jb.rs_smem : smem[jb.bpp - 3]; }
+  }
+  if (total == 0) return 0;
+  int launches = 0;
+  for (int cls = 0; cls < 2; cls++) {
+    if (!any[cls]) continue;
+    const int sm = (smem[cls] + 1023) & ~1023;
+    if (sm > g_resize_smem_cap) return -1;
+    if (cls == 0) k_resize_tiles<3><<<total, RS_THREADS, sm, (cudaStream_t)stream>>>(jobs_dev, n_jobs, sm);
+    else k_resize_tiles<4><<<total, RS_THREADS, sm, (cudaStream_t)stream>>>(jobs_dev, n_jobs, sm);
+    launches++;
+  }
+  return launches;
+}
+
+}  // namespace nes

@@ -6,7 +6,7 @@
 // frame f+1, the kernels of frame f and the download of frame f-1 overlap.  Per frame
 // the host does: pen arithmetic for the text runs (text.cc), one descriptor (DevJob),
 // at most one pinned staging memcpy each way (none when the caller's buffers are pinned),
-// and 1-3 kernel launches (kernels.cu).
+// and 1 kernel launch (frame_strips.cu or resize_tiles.cu).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -32,6 +32,7 @@ namespace {
 
 constexpr int kMaxBatch = 256;
 constexpr int kBatchRing = 8;
+constexpr int kBatchGlyphFactor = 8;  // placed glyphs per batched launch = this x cfg.max_glyphs
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -40,7 +41,9 @@ struct FilterSet {  // device tables for one (W,H,Wd,Hd)
   FilterTable h_hl, h_hc, h_vl, h_vc;
   void *blob = nullptr;
   int half = 0, csW = 0;
-  int smem_need[2] = {0, 0};  // bpp 3 / 4
+  int tw = 0, th = 0;      // destination tile of the resize kernel for this size pair
+  int smem_need = 0;       // shared memory of its worst tile
+  const int32_t *win_x = nullptr, *win_y = nullptr;  // device: per tile column / row source windows
 };
 
 struct StagedCopy {  // pinned staging -> caller memory, done in wait()
@@ -50,8 +53,8 @@ struct StagedCopy {  // pinned staging -> caller memory, done in wait()
 };
 
 struct Slot {
-  uint8_t *d_in = nullptr, *d_out = nullptr, *d_scratch = nullptr;
-  size_t d_in_cap = 0, d_out_cap = 0, d_scratch_cap = 0;
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  size_t d_in_cap = 0, d_out_cap = 0;
   uint8_t *h_in = nullptr, *h_out = nullptr;
   size_t h_in_cap = 0, h_out_cap = 0;
   DevJob *h_job = nullptr, *d_job = nullptr;
@@ -147,36 +150,39 @@ int fmt_info(int fmt, int *bpp, int *base, int *a_off, bool *bgr) {
   }
 }
 
-// shared memory the resize kernel needs for its worst tile (mirrors k_resize_tiles)
-int resize_smem_need(const FilterSet &fs, int W, int Wd, int Hd, int bpp) {
+// Source windows of the resize tiles for one tile size: per tile column {lc0, lc1, cc0, cc1}, per tile
+// row {lr0, lr1, cr0, cr1} (filter positions are monotone except at fixed-up borders, so scan), and
+// the shared memory the worst tile needs (rs_layout, the same function the kernel carves with).
+int resize_windows(const FilterSet &fs, int Wd, int Hd, int tw, int th, std::vector<int32_t> *wx, std::vector<int32_t> *wy) {
   const int cdW = (Wd + 1) >> 1, cdH = (Hd + 1) >> 1;
-  (void)W;
-  int worst = 0;
-  for (int dy0 = 0; dy0 < Hd; dy0 += RS_TILE_H) {
-    const int dy1 = std::min(dy0 + RS_TILE_H, Hd);
+  wx->clear(); wy->clear();
+  for (int dx0 = 0; dx0 < Wd; dx0 += tw) {
+    const int dx1 = std::min(dx0 + tw, Wd);
+    const int cx0 = dx0 >> 1, cx1 = std::min((dx1 + 1) >> 1, cdW);
+    int lc0 = 1 << 30, lc1 = 0, cc0 = 1 << 30, cc1 = 0;
+    for (int i = dx0; i < dx1; i++) { lc0 = std::min(lc0, fs.h_hl.pos[i]); lc1 = std::max(lc1, fs.h_hl.pos[i] + fs.hl.size); }
+    for (int i = cx0; i < cx1; i++) { cc0 = std::min(cc0, fs.h_hc.pos[i]); cc1 = std::max(cc1, fs.h_hc.pos[i] + fs.hc.size); }
+    wx->insert(wx->end(), {lc0, lc1, cc0, cc1});
+  }
+  for (int dy0 = 0; dy0 < Hd; dy0 += th) {
+    const int dy1 = std::min(dy0 + th, Hd);
     const int cy0 = dy0 >> 1, cy1 = std::min((dy1 + 1) >> 1, cdH);
     int lr0 = 1 << 30, lr1 = 0, cr0 = 1 << 30, cr1 = 0;
     for (int i = dy0; i < dy1; i++) { lr0 = std::min(lr0, fs.h_vl.pos[i]); lr1 = std::max(lr1, fs.h_vl.pos[i] + fs.vl.size); }
     for (int i = cy0; i < cy1; i++) { cr0 = std::min(cr0, fs.h_vc.pos[i]); cr1 = std::max(cr1, fs.h_vc.pos[i] + fs.vc.size); }
-    for (int dx0 = 0; dx0 < Wd; dx0 += RS_TILE_W) {
-      const int dx1 = std::min(dx0 + RS_TILE_W, Wd);
-      const int cx0 = dx0 >> 1, cx1 = std::min((dx1 + 1) >> 1, cdW);
-      int lc0 = 1 << 30, lc1 = 0, cc0 = 1 << 30, cc1 = 0;
-      for (int i = dx0; i < dx1; i++) { lc0 = std::min(lc0, fs.h_hl.pos[i]); lc1 = std::max(lc1, fs.h_hl.pos[i] + fs.hl.size); }
-      for (int i = cx0; i < cx1; i++) { cc0 = std::min(cc0, fs.h_hc.pos[i]); cc1 = std::max(cc1, fs.h_hc.pos[i] + fs.hc.size); }
-      const int pc0 = fs.half ? cc0 * 2 : cc0, pc1 = fs.half ? cc1 * 2 : cc1;
-      const int wx0 = std::min(lc0, pc0), wx1 = std::max(lc1, pc1);
-      const int wy0 = std::min(lr0, cr0), wy1 = std::max(lr1, cr1);
-      const int ww = wx1 - wx0, wh = wy1 - wy0, lw = lc1 - lc0, cw = cc1 - cc0, dw = dx1 - dx0, dcw = cx1 - cx0;
-      size_t need = (size_t)((wh * ww * bpp + 15) & ~15);
-      need += 2 * (size_t)(((lr1 - lr0) * lw + 7) & ~7);
-      need += 2 * 2 * (size_t)(((cr1 - cr0) * cw + 7) & ~7);
-      need += 2 * (size_t)(((lr1 - lr0) * dw + 7) & ~7);
-      need += 2 * 2 * (size_t)(((cr1 - cr0) * dcw + 7) & ~7);
-      need += HIT_CAP * 4 + 32;
-      worst = std::max(worst, (int)need);
-    }
+    wy->insert(wy->end(), {lr0, lr1, cr0, cr1});
   }
+  int worst = 0;
+  for (size_t ty = 0; ty * 4 < wy->size(); ty++)
+    for (size_t tx = 0; tx * 4 < wx->size(); tx++) {
+      const int32_t *X = &(*wx)[tx * 4], *Y = &(*wy)[ty * 4];
+      const int dx0 = (int)tx * tw, dw = std::min(tw, Wd - dx0), dcw = std::min((dx0 + dw + 1) >> 1, cdW) - (dx0 >> 1);
+      const int pc0 = fs.half ? X[2] * 2 : X[2], pc1 = fs.half ? X[3] * 2 : X[3];
+      const int wx0 = std::min(X[0], pc0) & ~3, ww = ((std::max(X[1], pc1) - wx0) + 3) & ~3;
+      const int wy0 = std::min(Y[0], Y[2]), wh = std::max(Y[1], Y[3]) - wy0;
+      const RsLayout L = rs_layout(wh, ww, fs.half ? ww >> 1 : ww, Y[1] - Y[0], Y[3] - Y[2], (dw + 3) & ~3, (dcw + 3) & ~3, HIT_CAP);
+      worst = std::max(worst, L.total);
+    }
   return worst;
 }
 
@@ -210,8 +216,24 @@ int get_filters(nes_gpu_session *s, int W, int H, int Wd, int Hd, FilterSet **ou
     d[i]->pos = (const int32_t *)((uint8_t *)fs.blob + off[i][1]);
     d[i]->size = t[i]->size;
   }
-  fs.smem_need[0] = resize_smem_need(fs, W, Wd, Hd, 3);
-  fs.smem_need[1] = resize_smem_need(fs, W, Wd, Hd, 4);
+  // destination tile: the largest that leaves room for two CTAs per SM, else the largest that fits at all
+  static const int kTiles[][2] = {{128, 32}, {64, 32}, {64, 16}, {32, 16}, {32, 8}, {16, 8}, {16, 4}, {8, 4}};
+  std::vector<int32_t> wx, wy;
+  int pick = -1;
+  for (int pass = 0; pass < 2 && pick < 0; pass++)
+    for (int i = 0; i < (int)(sizeof(kTiles) / sizeof(kTiles[0])); i++) {
+      const int need = resize_windows(fs, Wd, Hd, kTiles[i][0], kTiles[i][1], &wx, &wy);
+      if (need <= (pass == 0 ? RS_SMEM_GOAL : RS_SMEM_MAX)) { pick = i; fs.smem_need = need; break; }
+    }
+  if (pick < 0) { cudaFree(fs.blob); return NES_ERR_TOO_LARGE; }  // scale ratio beyond what one tile can stage
+  fs.tw = kTiles[pick][0]; fs.th = kTiles[pick][1];
+  {
+    int32_t *dw_ = nullptr;
+    CU_TRY(s, cudaMalloc((void **)&dw_, (wx.size() + wy.size()) * 4 + 32));
+    CU_TRY(s, cudaMemcpy(dw_, wx.data(), wx.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(s, cudaMemcpy(dw_ + wx.size(), wy.data(), wy.size() * 4, cudaMemcpyHostToDevice));
+    fs.win_x = dw_; fs.win_y = dw_ + wx.size();
+  }
   auto ins = s->filters.emplace(key, std::move(fs));
   *out = &ins.first->second;
   return NES_OK;
@@ -330,8 +352,8 @@ void job_tile_mask(DevJob *jb, const DevPlaced *placed) {
 void job_tiles(DevJob *jb, int tile_base) {
   jb->tiles_x = jb->tiles_y = 0;
   if (jb->general) {
-    jb->tiles_x = (jb->Wd + RS_TILE_W - 1) / RS_TILE_W;
-    jb->tiles_y = (jb->Hd + RS_TILE_H - 1) / RS_TILE_H;
+    jb->tiles_x = (jb->Wd + jb->rs_tw - 1) / jb->rs_tw;
+    jb->tiles_y = (jb->Hd + jb->rs_th - 1) / jb->rs_th;
   }
   jb->tile_base = tile_base;
 }
@@ -426,7 +448,6 @@ int place_text(nes_gpu_session *s, int W, int H, const nes_text_run *runs, int n
 
 int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, int n, cudaStream_t st) {
   int l = 0;
-  l += launch_composite(d_jobs, h_jobs, n, st);
   const int r0 = launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, st);
   if (r0 > 0) l += r0;
   const int r = launch_resize_tiles(d_jobs, h_jobs, n, st);
@@ -511,7 +532,7 @@ void nes_gpu_session_destroy(nes_gpu_session *s) {
   if (s->st_k) cudaStreamSynchronize(s->st_k);
   if (s->st_out) cudaStreamSynchronize(s->st_out);
   for (Slot &sl : s->slots) {
-    cudaFree(sl.d_in); cudaFree(sl.d_out); cudaFree(sl.d_scratch);
+    cudaFree(sl.d_in); cudaFree(sl.d_out);
     cudaFreeHost(sl.h_in); cudaFreeHost(sl.h_out);
     cudaFreeHost(sl.h_job); cudaFree(sl.d_job);
     cudaFreeHost(sl.h_glyphs); cudaFree(sl.d_glyphs);
@@ -524,7 +545,7 @@ void nes_gpu_session_destroy(nes_gpu_session *s) {
     if (b.done) cudaEventDestroy(b.done);
     if (b.up) cudaEventDestroy(b.up);
   }
-  for (auto &kv : s->filters) cudaFree(kv.second.blob);
+  for (auto &kv : s->filters) { cudaFree(kv.second.blob); cudaFree((void *)kv.second.win_x); }
   cudaFree(s->d_atlas);
   cudaFree(s->d_counters);
   if (s->st_in) cudaStreamDestroy(s->st_in);
@@ -759,15 +780,9 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   if (resize) {
     FilterSet *fs;
     if ((st = get_filters(s, W, H, Wd, Hd, &fs))) return st;
-    if (fs->smem_need[bpp - 3] > 200 * 1024) return NES_ERR_TOO_LARGE;  // scale ratio beyond what one tile can stage
     jb->hl = fs->hl; jb->hc = fs->hc; jb->vl = fs->vl; jb->vc = fs->vc;
-    jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need[bpp - 3];
-    if (in->n_sources > 1) {
-      const size_t need = (size_t)W * H * (bpp + 1);
-      if ((st = ensure_dev(s, &sl.d_scratch, &sl.d_scratch_cap, need))) return st;
-      jb->scratch_rgb = sl.d_scratch;
-      jb->scratch_depth = sl.d_scratch + (size_t)W * H * bpp;
-    }
+    jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need;
+    jb->rs_tw = fs->tw; jb->rs_th = fs->th; jb->rs_win_x = fs->win_x; jb->rs_win_y = fs->win_y;
   }
   job_tiles(jb, 0);
   job_alignment(jb);
@@ -863,7 +878,8 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
   if (s->sticky) return s->sticky;
   CU_TRY(s, cudaSetDevice(s->cfg.device));
   BatchTables &bt = s->batch[s->batch_seq++ % kBatchRing];
-  const size_t gl_bytes = (size_t)s->cfg.max_glyphs * sizeof(DevPlaced);
+  const int gl_cap = s->cfg.max_glyphs * kBatchGlyphFactor;
+  const size_t gl_bytes = (size_t)gl_cap * sizeof(DevPlaced);
   if (!bt.h_jobs) {
     CU_TRY(s, cudaHostAlloc((void **)&bt.h_jobs, sizeof(DevJob) * kMaxBatch, cudaHostAllocDefault));
     CU_TRY(s, cudaMalloc((void **)&bt.d_jobs, sizeof(DevJob) * kMaxBatch));
@@ -882,11 +898,10 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
     if (st) return st;
     const int W = in[f].width, H = in[f].height;
     const bool general = W != out[f].width || H != out[f].height || H < MIN_FUSED_H;
-    if (general && in[f].n_sources > 1) return NES_ERR_INVALID_ARG;  // composite+resize needs a slot's scratch frame: use submit
     const bool want_depth = out[f].depth[0] != nullptr;
     DevJob *jb = &bt.h_jobs[f];
     job_common(jb, &in[f], &out[f], bpp, base, a_off, bgr);
-    const int n_gl = place_text(s, W, H, runs ? runs[f] : nullptr, (runs && n_runs) ? n_runs[f] : 0, bt.h_glyphs + gl_used, s->cfg.max_glyphs - gl_used);
+    const int n_gl = place_text(s, W, H, runs ? runs[f] : nullptr, (runs && n_runs) ? n_runs[f] : 0, bt.h_glyphs + gl_used, std::min(s->cfg.max_glyphs, gl_cap - gl_used));
     if (n_gl < 0) return n_gl;
     jb->glyphs = bt.d_glyphs + gl_used;
     jb->atlas = s->d_atlas;
@@ -908,9 +923,9 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
     if (general) {
       FilterSet *fs;
       if ((st = get_filters(s, W, H, out[f].width, out[f].height, &fs))) return st;
-      if (fs->smem_need[bpp - 3] > 200 * 1024) return NES_ERR_TOO_LARGE;
       jb->hl = fs->hl; jb->hc = fs->hc; jb->vl = fs->vl; jb->vc = fs->vc;
-      jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need[bpp - 3];
+      jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need;
+      jb->rs_tw = fs->tw; jb->rs_th = fs->th; jb->rs_win_x = fs->win_x; jb->rs_win_y = fs->win_y;
     }
     job_tiles(jb, tile_base);
     tile_base += jb->tiles_x * jb->tiles_y;
