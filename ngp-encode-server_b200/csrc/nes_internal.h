@@ -33,7 +33,8 @@ constexpr int MASK_BAND_SHIFT = 5;
 // luma samples (per size pair, chosen on the host so that two CTAs fit an SM when possible).
 constexpr int RS_THREADS = 256;
 constexpr int RS_SMEM_MAX = 200 * 1024;   // one tile must fit this
-constexpr int RS_SMEM_GOAL = 104 * 1024;  // two CTAs per SM
+constexpr int RS_SMEM_GOAL = 72 * 1024;   // three CTAs per SM
+constexpr int GLYPH_BANDS = 256;          // placed glyphs of a resize job are bucketed by row band (counting sort on the host)
 
 #if defined(__CUDACC__)
 #define NES_HD __host__ __device__
@@ -135,6 +136,10 @@ struct alignas(64) DevJob {
   int32_t csW;   // chroma source width fed to the H pass
   int32_t rs_smem;  // shared memory the resize kernel needs for this job's worst tile (host use)
   int32_t general;  // 1: k_resize_tiles (any size change, or H < 12 where libswscale's chroma filter is truncated)
+  // placed glyphs sorted by band = clamp(y, 0, H-1) >> glyph_band_shift: band b holds glyphs
+  // [glyph_band[b], glyph_band[b+1]); a tile only tests the bands its source window can touch
+  int32_t glyph_band_shift, glyph_max_h;
+  int32_t glyph_band[GLYPH_BANDS + 1];
   int32_t rs_tw, rs_th;     // destination tile of the resize kernel
   const int32_t *rs_win_x;  // [tiles_x][4]: luma source columns [lc0, lc1), chroma source columns [cc0, cc1)
   const int32_t *rs_win_y;  // [tiles_y][4]: luma source rows [lr0, lr1), chroma source rows [cr0, cr1)

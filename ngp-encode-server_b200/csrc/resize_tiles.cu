@@ -70,9 +70,36 @@ __device__ __forceinline__ void load_group(const DevJob &jb, int x, int y, bool 
       }
       *d4 = want_depth ? __ldg((const uint32_t *)(jb.src[0].depth + (size_t)y * jb.src[0].depth_stride + x)) : 0u;
     } else {
-      uint4 q;
-      composite_px4(jb, x, y, &q, d4);
-      px[0] = q.x; px[1] = q.y; px[2] = q.z; px[3] = q.w;
+      // depth-select composite (device_common.cuh composite_px for the semantics): all loads of the
+      // first four sources are issued before the first compare
+      uint4 q[4];
+      uint32_t dw[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (k < jb.n_src) {
+          q[k] = __ldg((const uint4 *)(jb.src[k].rgb + (size_t)y * jb.src[k].rgb_stride + (size_t)x * 4));
+          dw[k] = __ldg((const uint32_t *)(jb.src[k].depth + (size_t)y * jb.src[k].depth_stride + x));
+        }
+      const uint32_t am = 0xFFu << (8 * jb.a_off);
+      uint32_t bd[4] = {256, 256, 256, 256};
+      px[0] = px[1] = px[2] = px[3] = 0;
+      auto consider = [&](const uint4 &p, uint32_t d) {
+        const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t di = (d >> (8 * i)) & 255u;
+          const bool take = (w[i] & am) != 0 && di < bd[i];
+          bd[i] = take ? di : bd[i];
+          px[i] = take ? w[i] : px[i];
+        }
+      };
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (k < jb.n_src) consider(q[k], dw[k]);
+      for (int k = 4; k < jb.n_src; k++)
+        consider(__ldg((const uint4 *)(jb.src[k].rgb + (size_t)y * jb.src[k].rgb_stride + (size_t)x * 4)),
+                 __ldg((const uint32_t *)(jb.src[k].depth + (size_t)y * jb.src[k].depth_stride + x)));
+      *d4 = min(bd[0], 255u) | (min(bd[1], 255u) << 8) | (min(bd[2], 255u) << 16) | (min(bd[3], 255u) << 24);
     }
     return;
   }
@@ -185,7 +212,7 @@ __device__ __forceinline__ void vpass(const DevFilter &f, const int16_t *s_in, i
 }  // namespace
 
 template <int BPP>
-__global__ void __launch_bounds__(RS_THREADS, 2) k_resize_tiles(const DevJob *__restrict__ jobs, int n_jobs, int smem_cap) {
+__global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__restrict__ jobs, int n_jobs, int smem_cap) {
   extern __shared__ __align__(16) uint8_t smem[];
   int tile;
   const DevJob *jp = find_job(jobs, n_jobs, blockIdx.x, &tile);
@@ -238,10 +265,13 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_resize_tiles(const DevJob *__
     for (int i = tid; i < t.wh * mw; i += RS_THREADS) s_mask[i] = 0;
     const int x1 = t.wx0 + t.ww, y1 = t.wy0 + t.wh;
     int any = 0;
-    for (int base = 0; base < jb.n_glyphs; base += HIT_CAP) {
+    // only the row bands this window can touch (the host bucketed the glyph list by band)
+    const int b0 = max(t.wy0 - jb.glyph_max_h, 0) >> jb.glyph_band_shift, b1 = (y1 - 1) >> jb.glyph_band_shift;
+    const int g_begin = jb.glyph_band[b0], g_end = jb.glyph_band[b1 + 1];
+    for (int base = g_begin; base < g_end; base += HIT_CAP) {
       if (tid == 0) *s_nhits = 0;
       __syncthreads();
-      for (int g = base + tid; g < min(base + HIT_CAP, jb.n_glyphs); g += RS_THREADS) {
+      for (int g = base + tid; g < min(base + HIT_CAP, g_end); g += RS_THREADS) {
         const DevPlaced pg = jb.glyphs[g];
         if (pg.x < x1 && pg.x + pg.w > t.wx0 && pg.y < y1 && pg.y + pg.h > t.wy0) s_hits[atomicAdd(s_nhits, 1)] = g;
       }

@@ -95,6 +95,7 @@ struct nes_gpu_session {
   std::string err;
   int sticky = 0;
   std::vector<nes_placed_glyph> scratch_placed;
+  std::vector<DevPlaced> scratch_banded;
 };
 
 namespace {
@@ -446,6 +447,22 @@ int place_text(nes_gpu_session *s, int W, int H, const nes_text_run *runs, int n
   return n;
 }
 
+// Resize jobs: bucket the placed glyphs by row band (stable counting sort; stamps are order-free)
+// so that a tile tests only the glyphs near its source window instead of the whole list.
+void band_glyphs(DevJob *jb, DevPlaced *gl, int n, std::vector<DevPlaced> *tmp) {
+  int shift = 5;
+  while (((jb->H - 1) >> shift) >= GLYPH_BANDS) shift++;
+  jb->glyph_band_shift = shift;
+  jb->glyph_max_h = 0;
+  int count[GLYPH_BANDS + 1] = {0};
+  auto band_of = [&](const DevPlaced &p) { return std::min(std::max(p.y, 0), jb->H - 1) >> shift; };
+  for (int i = 0; i < n; i++) { count[band_of(gl[i]) + 1]++; jb->glyph_max_h = std::max(jb->glyph_max_h, gl[i].h); }
+  for (int b = 0; b < GLYPH_BANDS; b++) count[b + 1] += count[b];
+  for (int b = 0; b <= GLYPH_BANDS; b++) jb->glyph_band[b] = count[b];
+  tmp->assign(gl, gl + n);
+  for (int i = 0; i < n; i++) gl[count[band_of((*tmp)[i])]++] = (*tmp)[i];
+}
+
 int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, int n, cudaStream_t st) {
   int l = 0;
   const int r0 = launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, st);
@@ -777,6 +794,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   jb->dys = out->depth_linesize[0]; jb->dus = out->depth_linesize[1]; jb->dvs = out->depth_linesize[2];
 
   jb->general = resize;
+  if (resize && n_gl > 0) band_glyphs(jb, sl.h_glyphs, n_gl, &s->scratch_banded);
   if (resize) {
     FilterSet *fs;
     if ((st = get_filters(s, W, H, Wd, Hd, &fs))) return st;
@@ -920,6 +938,7 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
       jb->dys = out[f].depth_linesize[0]; jb->dus = out[f].depth_linesize[1]; jb->dvs = out[f].depth_linesize[2];
     }
     jb->general = general;
+    if (general && n_gl > 0) band_glyphs(jb, bt.h_glyphs + gl_used - n_gl, n_gl, &s->scratch_banded);
     if (general) {
       FilterSet *fs;
       if ((st = get_filters(s, W, H, out[f].width, out[f].height, &fs))) return st;
