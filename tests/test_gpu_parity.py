@@ -370,3 +370,118 @@ def test_cpp_shim_process_frame(N, O, port, glyphs, tmp_path):
     assert (tmp_path / "o.scene.yuv").read_bytes() == want_s
     assert (tmp_path / "o.depth.yuv").read_bytes() == want_d
     assert (tmp_path / "o.sws.yuv").read_bytes() == want_s
+
+
+# ------------------------------------------------------------------ wider coverage of the kernels' paths
+def _rgba_sources(O, rng, n, w, h, fmt="rgba"):
+    srcs, rgbs, deps = [], [], []
+    for k in range(n):
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        alpha = np.where(rng.integers(0, 3, (h, w)) == 0, 0, 255).astype(np.uint8)
+        img = O.to_fmt(rgb, fmt, alpha)
+        dep = np.ascontiguousarray(rng.integers(0, 16, (h, w), dtype=np.uint8) * 16)
+        srcs.append((img, dep)); rgbs.append(img); deps.append(dep)
+    return srcs, rgbs, deps
+
+
+@pytest.mark.parametrize("n,w,h,wd,hd", [(5, 512, 64, 512, 64), (8, 320, 48, 320, 48), (6, 384, 216, 256, 144)])
+def test_composite_more_than_four_sources(N, O, port, glyphs, n, w, h, wd, hd):
+    """5..8 renderer inputs: the fused kernel stages at most 4 sources by TMA, beyond that the
+    consumer warps composite into the stage themselves; the resize kernel loops past 4."""
+    s = N.Session(device=0, max_width=w, max_height=h, max_sources=8)
+    try:
+        rng = np.random.default_rng(n)
+        srcs, rgbs, deps = _rgba_sources(O, rng, n, w, h)
+        comp, cdep = port.composite(rgbs, deps, "rgba")
+        sc, dp = run_gpu(N, s, "rgba", srcs, w, h, wd, hd)
+        assert sc.cropped() == port.rgb_to_yuv420p(comp, "rgba", wd, hd).cropped()
+        assert dp.cropped() == port.gray_to_yuv420p(cdep, wd, hd).cropped()
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("w,h,wd,hd", [(1536, 384, 256, 64), (960, 540, 320, 180), (128, 96, 640, 480), (720, 486, 1280, 720)])
+def test_resize_large_ratios(N, O, port, session, w, h, wd, hd):
+    """6:1 and 3:1 reductions (24- and 11-tap filters: smaller destination tiles are picked so that
+    the source window fits shared memory) and 5x enlargements."""
+    rng = np.random.default_rng(w * 3 + hd)
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    dep = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    sc, dp = run_gpu(N, session, "rgb24", [(rgb, dep)], w, h, wd, hd)
+    want_s, want_d = port.rgb_to_yuv420p(rgb, "rgb24", wd, hd), port.gray_to_yuv420p(dep, wd, hd)
+    assert sc.cropped() == want_s.cropped(), first_diff(sc.cropped(), want_s.cropped())
+    assert dp.cropped() == want_d.cropped(), first_diff(dp.cropped(), want_d.cropped())
+
+
+def _device_job(N, session, fmt, srcs, w, h, wd, hd):
+    """Upload sources, allocate device planes; returns (frame_in, frame_out, (scene_ptr, depth_ptr), all_ptrs)."""
+    bpp = N.PIX_BPP[fmt]
+    ptrs, sources = [], []
+    for img, dep in srcs:
+        d_rgb, d_dep = session.device_alloc(w * h * bpp), session.device_alloc(w * h)
+        session.h2d(d_rgb, np.ascontiguousarray(img)); session.h2d(d_dep, np.ascontiguousarray(dep))
+        ptrs += [d_rgb, d_dep]
+        sources.append(((d_rgb, w * h * bpp), (d_dep, w * h), 0, 0))
+    ysz, csz = N.align32(wd) * hd, N.align32(wd // 2) * (hd // 2)
+    d_s, d_d = session.device_alloc(ysz + 2 * csz), session.device_alloc(ysz + 2 * csz)
+    ptrs += [d_s, d_d]
+    fo = N.nes_frame_out(); fo.width, fo.height, fo.mem = wd, hd, N.NES_MEM_DEVICE
+    for p, (off, ls) in enumerate([(0, N.align32(wd)), (ysz, N.align32(wd // 2)), (ysz + csz, N.align32(wd // 2))]):
+        fo.scene[p], fo.scene_linesize[p], fo.depth[p], fo.depth_linesize[p] = d_s + off, ls, d_d + off, ls
+    return N.Session.frame_in(fmt, w, h, sources, mem=N.NES_MEM_DEVICE), fo, (d_s, d_d), ptrs
+
+
+def test_batch_mixed_jobs(N, O, port, glyphs, session):
+    """One batched call mixing what a multi-session server submits together: 3-byte and 4-byte
+    pixels, 1 / 2 / 4 sources (one sub-stage slot size per launch), same-size and resized outputs
+    (composite + overlay + resize is a single fused launch), with and without text."""
+    rng = np.random.default_rng(77)
+    text = [(O.POS_LEFT_TOP, b"mixed batch\nline two 0123456789"), (O.POS_CENTER, b"centre")]
+    specs = [("rgb24", 1, 512, 96, 512, 96, None), ("rgba", 2, 512, 96, 512, 96, text), ("rgba", 1, 768, 64, 768, 64, None),
+             ("rgba", 4, 480, 270, 320, 180, text), ("rgb24", 1, 384, 216, 256, 144, text), ("bgra", 3, 256, 48, 256, 48, None)]
+    jobs, wants = [], []
+    for fmt, n, w, h, wd, hd, runs in specs:
+        if n == 1 and N.PIX_BPP[fmt] == 3:
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            dep = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            srcs, comp, cdep = [(img, dep)], img, dep
+        else:
+            srcs, rgbs, deps = _rgba_sources(O, rng, n, w, h, fmt)
+            # a single source is converted as it is (alpha only matters to the composite)
+            comp, cdep = port.composite(rgbs, deps, fmt) if n > 1 else (rgbs[0], deps[0])
+        surf = np.ascontiguousarray(comp.copy())
+        for pos, txt in runs or []:
+            (port.render_string if surf.shape[2] == 3 else (lambda a, p, t, g: port.render_string4(a, p, t, g, fmt)))(surf, pos, txt, glyphs)
+        wants.append((port.rgb_to_yuv420p(surf, fmt, wd, hd).cropped(), port.gray_to_yuv420p(np.ascontiguousarray(cdep), wd, hd).cropped()))
+        jobs.append(_device_job(N, session, fmt, srcs, w, h, wd, hd) + (wd, hd, runs))
+    before = session.launches
+    session.convert_batch_device([j[0] for j in jobs], [j[6] for j in jobs], [j[1] for j in jobs], sync=True)
+    assert session.launches - before == 4  # two pixel-size classes x (same-size kernel, resize kernel)
+    for (fin, fo, (d_s, d_d), ptrs, wd, hd, runs), (want_s, want_d), spec in zip(jobs, wants, specs):
+        sc, dp = N.FrameManager(N.FrameContext(wd, hd, "yuv420p")), N.FrameManager(N.FrameContext(wd, hd, "yuv420p"))
+        session.d2h(sc.buffer, d_s); session.d2h(dp.buffer, d_d)
+        assert sc.cropped() == want_s, (spec[:6], first_diff(sc.cropped(), want_s))
+        assert dp.cropped() == want_d, (spec[:6], first_diff(dp.cropped(), want_d))
+        for p in ptrs:
+            session.device_free(p)
+
+
+def test_batch_many_units_per_cta(N, O, port, session):
+    """24 720p frames in one launch: far more work units than resident CTAs, so every CTA walks
+    several (strip, segment) units back to back through the same sub-stage ring and chroma ring."""
+    w, h, nf = 1280, 720, 24
+    base_rgb, base_dep = O.synth_rgb(w, h, 3), O.synth_depth(w, h, 3)
+    jobs = []
+    for f in range(nf):
+        rgb = np.roll(base_rgb, 37 * f, axis=1); dep = np.roll(base_dep, 11 * f, axis=0)
+        jobs.append(_device_job(N, session, "rgb24", [(rgb, dep)], w, h, w, h) + (rgb, dep))
+    session.convert_batch_device([j[0] for j in jobs], None, [j[1] for j in jobs], sync=True)
+    for f in (0, 7, 23):
+        fin, fo, (d_s, d_d), ptrs, rgb, dep = jobs[f]
+        sc, dp = N.FrameManager(N.FrameContext(w, h, "yuv420p")), N.FrameManager(N.FrameContext(w, h, "yuv420p"))
+        session.d2h(sc.buffer, d_s); session.d2h(dp.buffer, d_d)
+        assert sc.cropped() == port.rgb_to_yuv420p(np.ascontiguousarray(rgb), "rgb24").cropped()
+        assert dp.cropped() == port.gray_to_yuv420p(np.ascontiguousarray(dep)).cropped()
+    for j in jobs:
+        for p in j[3]:
+            session.device_free(p)
