@@ -191,6 +191,14 @@ def main():
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     warmup = max(args.warmup, 3)
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version
+    # banner, build output) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     import __graft_entry__ as g
     if rank == 0 or world == 1:
@@ -216,13 +224,13 @@ def main():
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": thr, "kind": r["kind"], "sample": r["sample"] + f"; step = one frame on each of {thr} threads (one hot-path thread per eye per session, main.cpp:274-282)"},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
     import torch
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the pixel pipeline has no CPU fallback"}), flush=True)
+        emit({"error": "no CUDA device: the pixel pipeline has no CPU fallback"})
         return 2
     torch.cuda.set_device(local)
     if world > 1:
@@ -422,7 +430,7 @@ def main():
         c1 = cpu_reference(args.workload, 1, max(3.0, args.cpu_seconds / 3))
         line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": thr, "kind": cb["kind"], "sample": cb["sample"], "per_core_value": c1["value"]}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
