@@ -37,6 +37,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "device_common.cuh"
 #include "nes_internal.h"
@@ -82,14 +83,14 @@ struct ChunkCtx {
 template <int BPP>
 struct StripSmem {
   static constexpr int ROWB = STRIP_W * BPP;
-  static constexpr int STAGE_BYTES = (BPP == 4 ? 80 : 48) * 1024;  // the sub-stage ring
-  static constexpr int OFF_RING = STAGE_BYTES;
   static constexpr int RING_ROWB = (STRIP_W / 2) * 4;
+  // fixed part first, the sub-stage ring (ns x slot_bytes, chosen per launch) at the end
+  static constexpr int OFF_RING = 0;
   static constexpr int OFF_CTX = OFF_RING + RING_PHYS * RING_ROWB;
   static constexpr int CTX_BYTES = ((int)sizeof(ChunkCtx) + 15) & ~15;
   static constexpr int OFF_BAR = OFF_CTX + NCTX * CTX_BYTES;
   static constexpr int OFF_HITS = OFF_BAR + 2 * NS_MAX * 8;
-  static constexpr int TOTAL = OFF_HITS + HIT_CAP * 4 + 16;
+  static constexpr int OFF_STAGE = (OFF_HITS + HIT_CAP * 4 + 16 + 1023) & ~1023;
   // bytes of one sub-stage holding n sources: 8 pixel rows + 8 depth rows per source
   static constexpr int slot_bytes(int n) { return n * SUB_ROWS * (ROWB + DEP_ROWB); }
 };
@@ -312,7 +313,7 @@ __device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *sub0, uin
 }  // namespace
 
 template <int BPP>
-__global__ void __launch_bounds__(CTA_THREADS, BPP == 3 ? 3 : 2)
+__global__ void __launch_bounds__(CTA_THREADS, 3)
 k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters, int ns, int slot_bytes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using L = StripSmem<BPP>;
@@ -432,7 +433,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
           if (wanted) {
             if (lane == 0) mbar_arrive_expect_tx(&s_full[q], tx_bytes);
             __syncwarp();
-            if (my_map) tma_load_2d(smem_base + (uint32_t)(q * slot_bytes) + my_off, my_map, my_x, ys, &s_full[q]);
+            if (my_map) tma_load_2d(smem_base + L::OFF_STAGE + (uint32_t)(q * slot_bytes) + my_off, my_map, my_x, ys, &s_full[q]);
           } else if (lane == 0) {
             mbar_arrive(&s_full[q]);  // nothing in flight (the consumers fill the rows themselves, or skip them)
           }
@@ -464,7 +465,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
     const ChunkCtx &c = *(const ChunkCtx *)(smem + L::OFF_CTX + (chunk_it & (NCTX - 1)) * L::CTX_BYTES);
     const int last = c.last;
     {
-      const uint32_t sb[2] = {smem_base + (uint32_t)(q0 * slot_bytes), smem_base + (uint32_t)(q1 * slot_bytes)};
+      const uint32_t sb[2] = {smem_base + L::OFF_STAGE + (uint32_t)(q0 * slot_bytes), smem_base + L::OFF_STAGE + (uint32_t)(q1 * slot_bytes)};
       const uint32_t dep_off = (uint32_t)(c.n_staged * SUB_ROWS) * ROWB;
       const int x0 = c.x0, tw = c.tw, yc0 = c.yc0, ra = c.ra, rb = c.rb, ya = c.ya, yb = c.yb;
       const int n_src = c.n_src;
@@ -477,7 +478,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
       if (!c.tma || mode == MODE_MATERIALIZED || c.stamp) {
         // whole-chunk work on the staged rows: needs both sub-stages
         mbar_wait(&s_full[q1], (uint32_t)par1);
-        uint8_t *const g[2] = {smem + q0 * slot_bytes, smem + q1 * slot_bytes};
+        uint8_t *const g[2] = {smem + L::OFF_STAGE + q0 * slot_bytes, smem + L::OFF_STAGE + q1 * slot_bytes};
         // ---- fill our rows ourselves when they were not staged by TMA ------------------------
         if (!c.tma) {
           const DevJob &jb = jobs[c.job];
@@ -738,25 +739,57 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
   }
 }
 
-static int g_ctas_per_sm[2] = {0, 0};
 static int g_num_sms = 0;
+static int g_smem_per_sm = 0, g_smem_reserved = 1024;
+static int g_force_ctas = 0;  // NES_STRIPS_CTAS=2|3 (experiments)
 
 int frame_strips_init() {
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_frame_strips<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripSmem<3>::TOTAL);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_frame_strips<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripSmem<4>::TOTAL);
-  if (e != cudaSuccess) return (int)e;
   int dev = 0;
   cudaGetDevice(&dev);
   e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return (int)e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas_per_sm[0], k_frame_strips<3>, CTA_THREADS, StripSmem<3>::TOTAL);
+  e = cudaDeviceGetAttribute(&g_smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   if (e != cudaSuccess) return (int)e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas_per_sm[1], k_frame_strips<4>, CTA_THREADS, StripSmem<4>::TOTAL);
+  cudaDeviceGetAttribute(&g_smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+  int optin = 0;
+  e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (e != cudaSuccess) return (int)e;
-  if (g_ctas_per_sm[0] < 1 || g_ctas_per_sm[1] < 1) return (int)cudaErrorLaunchOutOfResources;
+  const int two = std::min(optin, g_smem_per_sm / 2 - g_smem_reserved);
+  e = cudaFuncSetAttribute(k_frame_strips<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, two);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_frame_strips<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, two);
+  if (e != cudaSuccess) return (int)e;
+  if (const char *v = getenv("NES_STRIPS_CTAS")) g_force_ctas = atoi(v);
   return 0;
+}
+
+// Launch shape of one pixel-size class: the sub-stage slot is the largest any job of the launch
+// needs (so that a slot index means the same shared-memory range for every unit a CTA walks
+// through); three CTAs per SM when at least two slots fit a third of the SM's shared memory
+// (latency hiding by occupancy), else two CTAs with a deeper ring.
+struct StripsConfig {
+  int ns, slot, smem, ctas;
+};
+static StripsConfig strips_config(int cls, int staged) {
+  const int off = cls == 0 ? StripSmem<3>::OFF_STAGE : StripSmem<4>::OFF_STAGE;
+  const int slot = cls == 0 ? StripSmem<3>::slot_bytes(staged) : StripSmem<4>::slot_bytes(staged);
+  const int smem_sm = g_smem_per_sm > 0 ? g_smem_per_sm : 233472;
+  StripsConfig c{0, slot, 0, 0};
+  for (int ctas = 3; ctas >= 1; ctas--) {
+    if (g_force_ctas && ctas > g_force_ctas) continue;
+    const int budget = smem_sm / ctas - g_smem_reserved - off;
+    const int ns = std::min(NS_MAX, budget / slot);
+    if (ns >= 2) { c.ns = ns; c.ctas = ctas; c.smem = off + ns * slot; break; }
+  }
+  return c;
+}
+static void launch_staged(const DevJob *jobs, int n_jobs, int staged[2]) {
+  staged[0] = staged[1] = 1;
+  for (int j = 0; j < n_jobs; j++) {
+    const DevJob &jb = jobs[j];
+    if (!jb.general && jb.tma_ok && jb.n_src > staged[jb.bpp - 3]) staged[jb.bpp - 3] = jb.n_src;
+  }
 }
 
 // Host-side planning of a launch: one segment height per bpp class (trade: 6 halo rows per
@@ -765,8 +798,10 @@ int frame_strips_init() {
 // (and general jobs) take no units.
 void plan_frame_strips(DevJob *jobs, int n_jobs) {
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
+  int staged[2];
+  launch_staged(jobs, n_jobs, staged);
   for (int cls = 0; cls < 2; cls++) {
-    const int grid = sms * (g_ctas_per_sm[cls] > 0 ? g_ctas_per_sm[cls] : (cls == 0 ? 3 : 2));
+    const int grid = sms * std::max(1, strips_config(cls, staged[cls]).ctas);
     int best_s = CHUNK_ROWS * 2 - 2 * HALO;
     double best_cost = 1e30;
     for (int S = CHUNK_ROWS * 2 - 2 * HALO; S <= 256; S += CHUNK_ROWS) {
@@ -799,30 +834,20 @@ void plan_frame_strips(DevJob *jobs, int n_jobs) {
 }
 
 int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream) {
-  int total[2] = {0, 0}, staged[2] = {1, 1};
+  int total[2] = {0, 0}, staged[2];
+  launch_staged(jobs_host, n_jobs, staged);
   for (int j = 0; j < n_jobs; j++) {
     const DevJob &jb = jobs_host[j];
-    if (jb.general) continue;
-    total[jb.bpp - 3] += jb.n_units;
-    if (jb.tma_ok && jb.n_src > staged[jb.bpp - 3]) staged[jb.bpp - 3] = jb.n_src;
+    if (!jb.general) total[jb.bpp - 3] += jb.n_units;
   }
   int launches = 0;
-  if (total[0] > 0) {
-    // one sub-stage slot size per launch (the largest any job needs), so that a slot index means
-    // the same shared-memory range for every unit a CTA walks through
-    const int slot = StripSmem<3>::slot_bytes(staged[0]);
-    const int ns = std::min(NS_MAX, StripSmem<3>::STAGE_BYTES / slot);
-    if (ns < 2) return -1;
-    const int grid = total[0] < g_num_sms * g_ctas_per_sm[0] ? total[0] : g_num_sms * g_ctas_per_sm[0];
-    k_frame_strips<3><<<grid, CTA_THREADS, StripSmem<3>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[0], counters, ns, slot);
-    launches++;
-  }
-  if (total[1] > 0) {
-    const int slot = StripSmem<4>::slot_bytes(staged[1]);
-    const int ns = std::min(NS_MAX, StripSmem<4>::STAGE_BYTES / slot);
-    if (ns < 2) return -1;
-    const int grid = total[1] < g_num_sms * g_ctas_per_sm[1] ? total[1] : g_num_sms * g_ctas_per_sm[1];
-    k_frame_strips<4><<<grid, CTA_THREADS, StripSmem<4>::TOTAL, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[1], counters + 2, ns, slot);
+  for (int cls = 0; cls < 2; cls++) {
+    if (total[cls] == 0) continue;
+    const StripsConfig c = strips_config(cls, staged[cls]);
+    if (c.ns < 2) return -1;
+    const int grid = std::min(total[cls], g_num_sms * c.ctas);
+    if (cls == 0) k_frame_strips<3><<<grid, CTA_THREADS, c.smem, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[0], counters, c.ns, c.slot);
+    else k_frame_strips<4><<<grid, CTA_THREADS, c.smem, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[1], counters + 2, c.ns, c.slot);
     launches++;
   }
   return launches;
