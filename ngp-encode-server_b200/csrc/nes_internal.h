@@ -43,23 +43,25 @@ constexpr int GLYPH_BANDS = 256;          // placed glyphs of a resize job are b
 #endif
 // Shared-memory layout of one resize tile (byte offsets; every region 16-byte aligned).
 struct RsLayout {
-  int y14, u14, v14, hy, hu, hv, dep, mask, hits, total;
+  int y14, u14, v14, hy, hu, hv, dep, mask, hits, vtab, total;
 };
 // wh x ww: union source window (ww multiple of 4), cww: chroma plane row stride, nl / nc: luma /
 // chroma source rows fed to the vertical pass, dwp / dcwp: padded destination widths
-NES_HD inline RsLayout rs_layout(int wh, int ww, int cww, int nl, int nc, int dwp, int dcwp, int hit_cap) {
+// dh / dch: destination rows of the tile, vls / vcs: vertical filter sizes (their rows are staged)
+NES_HD inline RsLayout rs_layout(int wh, int ww, int cww, int nl, int nc, int dwp, int dcwp, int dh, int dch, int vls, int vcs, int hit_cap) {
   RsLayout L;
   int o = 0;
   auto take = [&](int bytes) { const int at = o; o += (bytes + 16 + 15) & ~15; return at; };  // +16: tap loops may over-read
   L.y14 = take(wh * ww * 2);
   L.u14 = take(wh * cww * 2);
   L.v14 = take(wh * cww * 2);
-  L.hy = take(nl * dwp * 2);
-  L.hu = take(nc * dcwp * 2);
-  L.hv = take(nc * dcwp * 2);
+  L.hy = take(nl * dwp * 4);  // H-pass output rows are int32
+  L.hu = take(nc * dcwp * 4);
+  L.hv = take(nc * dcwp * 4);
   L.dep = take(wh * ww);
   L.mask = take(wh * ((ww >> 5) + 1) * 4);
   L.hits = take(hit_cap * 4 + 16);
+  L.vtab = take(dh * ((4 + 2 * vls + 3) & ~3) + dch * ((4 + 2 * vcs + 3) & ~3));
   L.total = o;
   return L;
 }

@@ -133,79 +133,145 @@ struct Tile {
   int cww;                        // chroma plane row stride (ww/2 when pair-summed, else ww)
 };
 
-// horizontal polyphase of one plane: out[row][dx] = min((sum_j in[row][pos[dx]+j] * f[dx][j]) >> SH, 32767)
-template <int T, typename LoadFn, typename StoreFn>
-__device__ __forceinline__ void hpass(const DevFilter &f, int d0, int n_dst, int n_rows, int lane, int warp, LoadFn load, StoreFn store) {
+__device__ __forceinline__ int lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return (int)v;
+}
+__device__ __forceinline__ int lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return (int)v;
+}
+__device__ __forceinline__ int lds_s16(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_32(uint32_t a, int v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int4 lds_v4(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+
+enum { H_SCENE = 0, H_DEPTH = 1 };
+
+// Horizontal polyphase of NP planes that share one filter (NP = 2: U and V):
+//   out[row][dx] = fin( sum_j in[row][pos[dx] + j] * f[dx][j] )
+// lane = destination column (its T taps and its position live in registers), warp = source row;
+// the tap loads are one shared load each at an immediate offset.  ESZ: bytes per input sample
+// (2: 14-bit planes, 1: depth bytes).  Output is int32 so that the vertical pass needs no unpacking.
+//   H_SCENE: hScale16To15  min(v >> 13, 32767)
+//   H_DEPTH: hScale8To15   min(v >> 7, 32767), then the GRAY8 range compression (Appendix A.4)
+template <int T, int NP, int ESZ, int MODE>
+__device__ __forceinline__ void hpass(const DevFilter &f, int d0, int n_dst, int n_rows, const uint32_t (&in)[NP], int in_stride, int x_org,
+                                      const uint32_t (&out)[NP], int out_stride, int lane, int warp) {
+  constexpr int NWARP = RS_THREADS / 32;
   for (int db = 0; db < n_dst; db += 32) {
     const int dx = db + lane;
     if (dx >= n_dst) continue;
-    const int pos = f.pos[d0 + dx];
+    const int pos = f.pos[d0 + dx] - x_org;
     const int16_t *cf = f.coef + (size_t)(d0 + dx) * f.size;
+    int c[T > 0 ? T : 1];
     if (T > 0) {
-      int c[T > 0 ? T : 1];
 #pragma unroll
       for (int j = 0; j < T; j++) c[j] = j < f.size ? (int)cf[j] : 0;
-      for (int row = warp; row < n_rows; row += RS_THREADS / 32) {
-        int v = 0;
+    }
+    uint32_t a[NP], o[NP];
 #pragma unroll
-        for (int j = 0; j < T; j++) v += load(row, pos + j) * c[j];
-        store(row, dx, v);
-      }
-    } else {
-      for (int row = warp; row < n_rows; row += RS_THREADS / 32) {
+    for (int p = 0; p < NP; p++) { a[p] = in[p] + warp * in_stride + pos * ESZ; o[p] = out[p] + warp * out_stride + dx * 4; }
+    for (int row = warp; row < n_rows; row += NWARP) {
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
         int v = 0;
-        for (int j = 0; j < f.size; j++) v += load(row, pos + j) * (int)cf[j];
-        store(row, dx, v);
+        if (T > 0) {
+#pragma unroll
+          for (int j = 0; j < T; j++) v += (ESZ == 2 ? lds_u16(a[p] + 2 * j) : lds_u8(a[p] + j)) * c[j];
+        } else {
+          for (int j = 0; j < f.size; j++) v += (ESZ == 2 ? lds_u16(a[p] + 2 * j) : lds_u8(a[p] + j)) * (int)cf[j];
+        }
+        if (MODE == H_SCENE) v = min(v >> 13, 32767);
+        else { v = min(v >> 7, 32767); v = (v * 14071 + 33561472) >> 14; }
+        sts_32(o[p], v);
+        a[p] += NWARP * in_stride; o[p] += NWARP * out_stride;
       }
     }
   }
 }
 
-template <typename LoadFn, typename StoreFn>
-__device__ __forceinline__ void hpass_any(const DevFilter &f, int d0, int n_dst, int n_rows, int lane, int warp, LoadFn load, StoreFn store) {
-  if (f.size <= 4) hpass<4>(f, d0, n_dst, n_rows, lane, warp, load, store);
-  else if (f.size <= 6) hpass<6>(f, d0, n_dst, n_rows, lane, warp, load, store);
-  else if (f.size <= 8) hpass<8>(f, d0, n_dst, n_rows, lane, warp, load, store);
-  else if (f.size <= 12) hpass<12>(f, d0, n_dst, n_rows, lane, warp, load, store);
-  else hpass<0>(f, d0, n_dst, n_rows, lane, warp, load, store);
+template <int NP, int ESZ, int MODE>
+__device__ __forceinline__ void hpass_any(const DevFilter &f, int d0, int n_dst, int n_rows, const uint32_t (&in)[NP], int in_stride, int x_org,
+                                          const uint32_t (&out)[NP], int out_stride, int lane, int warp) {
+  if (f.size <= 4) hpass<4, NP, ESZ, MODE>(f, d0, n_dst, n_rows, in, in_stride, x_org, out, out_stride, lane, warp);
+  else if (f.size <= 6) hpass<6, NP, ESZ, MODE>(f, d0, n_dst, n_rows, in, in_stride, x_org, out, out_stride, lane, warp);
+  else if (f.size <= 8) hpass<8, NP, ESZ, MODE>(f, d0, n_dst, n_rows, in, in_stride, x_org, out, out_stride, lane, warp);
+  else if (f.size <= 12) hpass<12, NP, ESZ, MODE>(f, d0, n_dst, n_rows, in, in_stride, x_org, out, out_stride, lane, warp);
+  else hpass<0, NP, ESZ, MODE>(f, d0, n_dst, n_rows, in, in_stride, x_org, out, out_stride, lane, warp);
 }
 
-// vertical polyphase of one 15-bit plane (row stride `stride` int16, origin row r0) to an 8-bit
-// plane: 4 adjacent columns per thread
-__device__ __forceinline__ void vpass(const DevFilter &f, const int16_t *s_in, int stride, int r0, int d0y, int n_rows, int n_cols, uint8_t *dst,
-                                      int dst_stride, bool vec, int tid) {
+// Vertical polyphase of NP int32 planes (row stride `stride` bytes) to 8-bit planes: 4 adjacent
+// columns per thread (16-byte shared loads, 4-byte stores).  vtab: this tile's rows of the filter
+// staged in shared memory, per destination row [pos - r0, coef[0..size)] as int32 / int16.
+template <int NP>
+__device__ __forceinline__ void vpass(int size, uint32_t vtab, int vrow_bytes, const uint32_t (&in)[NP], int stride, int d0y, int n_rows, int n_cols,
+                                      uint8_t *const (&dst)[NP], const int (&dst_stride)[NP], bool vec, int tid) {
   const int ngrp = (n_cols + 3) >> 2;
   const int total = n_rows * ngrp;
-  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_in);
+  const int sh = (ngrp & (ngrp - 1)) == 0 ? __ffs(ngrp) - 1 : -1;
   for (int idx = tid; idx < total; idx += RS_THREADS) {
-    const int ry = idx / ngrp, gx = idx - ry * ngrp;
-    const int yy = d0y + ry;
-    const int pos = f.pos[yy] - r0;
-    uint32_t a = s_base + (uint32_t)(pos * stride + 4 * gx) * 2;
-    int o[4];
-    if (f.size == 1) {
-      uint2 w;
-      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(a));
-      o[0] = (sext_lo(w.x) + 64) >> 7; o[1] = (sext_hi(w.x) + 64) >> 7; o[2] = (sext_lo(w.y) + 64) >> 7; o[3] = (sext_hi(w.y) + 64) >> 7;
-    } else {
-      const int16_t *cf = f.coef + (size_t)yy * f.size;
-      int v0 = 64 << 12, v1 = 64 << 12, v2 = 64 << 12, v3 = 64 << 12;
-      for (int j = 0; j < f.size; j++, a += stride * 2) {
-        const int c = cf[j];
-        uint2 w;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(a));
-        v0 += sext_lo(w.x) * c; v1 += sext_hi(w.x) * c; v2 += sext_lo(w.y) * c; v3 += sext_hi(w.y) * c;
-      }
-      o[0] = v0 >> 19; o[1] = v1 >> 19; o[2] = v2 >> 19; o[3] = v3 >> 19;
-    }
-    uint8_t *p = dst + (size_t)yy * dst_stride + 4 * gx;
-    if (vec && 4 * gx + 4 <= n_cols) {
-      *(uint32_t *)p = (uint32_t)clip8(o[0]) | ((uint32_t)clip8(o[1]) << 8) | ((uint32_t)clip8(o[2]) << 16) | ((uint32_t)clip8(o[3]) << 24);
-    } else {
+    const int ry = sh >= 0 ? idx >> sh : idx / ngrp;
+    const int gx = idx - ry * ngrp;
+    const uint32_t vt = vtab + ry * vrow_bytes;
+    int pos;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(pos) : "r"(vt));
+    uint32_t a[NP];
+    int v[NP][4];
 #pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (4 * gx + k < n_cols) p[k] = (uint8_t)clip8(o[k]);
+    for (int p = 0; p < NP; p++) {
+      a[p] = in[p] + pos * stride + gx * 16;
+      v[p][0] = v[p][1] = v[p][2] = v[p][3] = size == 1 ? 64 : 64 << 12;
     }
+    if (size == 1) {
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        const int4 w = lds_v4(a[p]);
+        v[p][0] = (v[p][0] + w.x) >> 7; v[p][1] = (v[p][1] + w.y) >> 7; v[p][2] = (v[p][2] + w.z) >> 7; v[p][3] = (v[p][3] + w.w) >> 7;
+      }
+    } else {
+      for (int j = 0; j < size; j++) {
+        const int c = lds_s16(vt + 4 + 2 * j);
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+          const int4 w = lds_v4(a[p]);
+          v[p][0] += w.x * c; v[p][1] += w.y * c; v[p][2] += w.z * c; v[p][3] += w.w * c;
+          a[p] += stride;
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < NP; p++) { v[p][0] >>= 19; v[p][1] >>= 19; v[p][2] >>= 19; v[p][3] >>= 19; }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      uint8_t *q = dst[p] + (size_t)(d0y + ry) * dst_stride[p] + 4 * gx;
+      if (vec && 4 * gx + 4 <= n_cols) {
+        *(uint32_t *)q = (uint32_t)clip8(v[p][0]) | ((uint32_t)clip8(v[p][1]) << 8) | ((uint32_t)clip8(v[p][2]) << 16) | ((uint32_t)clip8(v[p][3]) << 24);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (4 * gx + k < n_cols) q[k] = (uint8_t)clip8(v[p][k]);
+      }
+    }
+  }
+}
+
+// stage this tile's rows of a vertical filter: per destination row {int32 pos - r0, int16 coef[size]}
+__device__ __forceinline__ void stage_vtab(const DevFilter &f, int d0y, int n_rows, int r0, uint8_t *tab, int vrow_bytes, int tid) {
+  const int per = 1 + f.size;
+  for (int i = tid; i < n_rows * per; i += RS_THREADS) {
+    const int ry = i / per, k = i - ry * per;
+    if (k == 0) *(int32_t *)(tab + ry * vrow_bytes) = f.pos[d0y + ry] - r0;
+    else *(int16_t *)(tab + ry * vrow_bytes + 4 + 2 * (k - 1)) = f.coef[(size_t)(d0y + ry) * f.size + k - 1];
   }
 }
 
@@ -245,13 +311,10 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
   const int nl = t.lr1 - t.lr0, nc = t.cr1 - t.cr0;
 
   // shared memory carve-up (rs_layout is shared with the host's sizing code)
-  const RsLayout L = rs_layout(t.wh, t.ww, t.cww, nl, nc, t.dwp, t.dcwp, HIT_CAP);
+  const RsLayout L = rs_layout(t.wh, t.ww, t.cww, nl, nc, t.dwp, t.dcwp, t.dh, t.dch, jb.vl.size, jb.vc.size, HIT_CAP);
   int16_t *s_y14 = (int16_t *)(smem + L.y14);  // [wh][ww]
   int16_t *s_u14 = (int16_t *)(smem + L.u14);  // [wh][cww]
   int16_t *s_v14 = (int16_t *)(smem + L.v14);
-  int16_t *s_hy = (int16_t *)(smem + L.hy);    // [nl][dwp]
-  int16_t *s_hu = (int16_t *)(smem + L.hu);    // [nc][dcwp]
-  int16_t *s_hv = (int16_t *)(smem + L.hv);
   uint8_t *s_dep = smem + L.dep;               // [wh][ww]
   const int mw = (t.ww >> 5) + 1;
   uint32_t *s_mask = (uint32_t *)(smem + L.mask);  // [wh][mw] overlay bits
@@ -340,41 +403,43 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
   }
   __syncthreads();
 
-  // ---- stage H: horizontal polyphase, hScale16To15 (>>13, clamp 32767) ----------------------------
+  // ---- stage H: horizontal polyphase, hScale16To15 (>>13, clamp 32767) -> int32 rows --------------
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+  const int vl_row = (4 + 2 * jb.vl.size + 3) & ~3, vc_row = (4 + 2 * jb.vc.size + 3) & ~3;
+  stage_vtab(jb.vl, t.dy0, t.dh, t.lr0, smem + L.vtab, vl_row, tid);
+  stage_vtab(jb.vc, t.cy0, t.dch, t.cr0, smem + L.vtab + t.dh * vl_row, vc_row, tid);
   {
-    const int16_t *ly = s_y14 + (t.lr0 - t.wy0) * t.ww - t.wx0;
-    hpass_any(jb.hl, t.dx0, t.dw, nl, lane, warp,
-              [&](int row, int x) { return (int)(uint16_t)ly[row * t.ww + x]; },
-              [&](int row, int dx, int v) { s_hy[row * t.dwp + dx] = (int16_t)min(v >> 13, 32767); });
+    const uint32_t in_y[1] = {sb + L.y14 + (uint32_t)((t.lr0 - t.wy0) * t.ww) * 2}, out_y[1] = {sb + L.hy};
+    hpass_any<1, 2, H_SCENE>(jb.hl, t.dx0, t.dw, nl, in_y, t.ww * 2, t.wx0, out_y, t.dwp * 4, lane, warp);
     const int corg = half ? (t.wx0 >> 1) : t.wx0;
-    const int16_t *lu = s_u14 + (t.cr0 - t.wy0) * t.cww - corg, *lv = s_v14 + (t.cr0 - t.wy0) * t.cww - corg;
-    hpass_any(jb.hc, t.cx0, t.dcw, nc, lane, warp,
-              [&](int row, int x) { return (int)(uint16_t)lu[row * t.cww + x]; },
-              [&](int row, int dx, int v) { s_hu[row * t.dcwp + dx] = (int16_t)min(v >> 13, 32767); });
-    hpass_any(jb.hc, t.cx0, t.dcw, nc, lane, warp,
-              [&](int row, int x) { return (int)(uint16_t)lv[row * t.cww + x]; },
-              [&](int row, int dx, int v) { s_hv[row * t.dcwp + dx] = (int16_t)min(v >> 13, 32767); });
+    const uint32_t in_c[2] = {sb + L.u14 + (uint32_t)((t.cr0 - t.wy0) * t.cww) * 2, sb + L.v14 + (uint32_t)((t.cr0 - t.wy0) * t.cww) * 2};
+    const uint32_t out_c[2] = {sb + L.hu, sb + L.hv};
+    hpass_any<2, 2, H_SCENE>(jb.hc, t.cx0, t.dcw, nc, in_c, t.cww * 2, corg, out_c, t.dcwp * 4, lane, warp);
   }
   __syncthreads();
 
   // ---- stage V: vertical polyphase to 8 bit (yuv2planeX / yuv2plane1) ----------------------------
   const bool vec = jb.out_vec != 0;
-  vpass(jb.vl, s_hy, t.dwp, t.lr0, t.dy0, t.dh, t.dw, jb.sy + t.dx0, jb.sys, vec, tid);
-  vpass(jb.vc, s_hu, t.dcwp, t.cr0, t.cy0, t.dch, t.dcw, jb.su + t.cx0, jb.sus, vec, tid);
-  vpass(jb.vc, s_hv, t.dcwp, t.cr0, t.cy0, t.dch, t.dcw, jb.sv + t.cx0, jb.svs, vec, tid);
+  {
+    const uint32_t in_y[1] = {sb + L.hy};
+    uint8_t *const dst_y[1] = {jb.sy + t.dx0};
+    const int ds_y[1] = {jb.sys};
+    vpass<1>(jb.vl.size, sb + L.vtab, vl_row, in_y, t.dwp * 4, t.dy0, t.dh, t.dw, dst_y, ds_y, vec, tid);
+    const uint32_t in_c[2] = {sb + L.hu, sb + L.hv};
+    uint8_t *const dst_c[2] = {jb.su + t.cx0, jb.sv + t.cx0};
+    const int ds_c[2] = {jb.sus, jb.svs};
+    vpass<2>(jb.vc.size, sb + L.vtab + t.dh * vl_row, vc_row, in_c, t.dcwp * 4, t.cy0, t.dch, t.dcw, dst_c, ds_c, vec, tid);
+  }
 
   // ---- depth: hScale8To15 (>>7) -> range compression -> vertical; U = V = 128 ----------------------
   if (want_depth) {
-    __syncthreads();  // s_hy is reused
-    const uint8_t *ld = s_dep + (t.lr0 - t.wy0) * t.ww - t.wx0;
-    hpass_any(jb.hl, t.dx0, t.dw, nl, lane, warp,
-              [&](int row, int x) { return (int)ld[row * t.ww + x]; },
-              [&](int row, int dx, int v) {
-                v = min(v >> 7, 32767);
-                s_hy[row * t.dwp + dx] = (int16_t)((v * 14071 + 33561472) >> 14);
-              });
+    __syncthreads();  // the luma H rows are reused
+    const uint32_t in_d[1] = {sb + L.dep + (uint32_t)((t.lr0 - t.wy0) * t.ww)}, out_d[1] = {sb + L.hy};
+    hpass_any<1, 1, H_DEPTH>(jb.hl, t.dx0, t.dw, nl, in_d, t.ww, t.wx0, out_d, t.dwp * 4, lane, warp);
     __syncthreads();
-    vpass(jb.vl, s_hy, t.dwp, t.lr0, t.dy0, t.dh, t.dw, jb.dy + t.dx0, jb.dys, vec, tid);
+    uint8_t *const dst_d[1] = {jb.dy + t.dx0};
+    const int ds_d[1] = {jb.dys};
+    vpass<1>(jb.vl.size, sb + L.vtab, vl_row, out_d, t.dwp * 4, t.dy0, t.dh, t.dw, dst_d, ds_d, vec, tid);
     const int ngrp = (t.dcw + 3) >> 2;
     for (int idx = tid; idx < t.dch * ngrp; idx += RS_THREADS) {
       const int ry = idx / ngrp, gx = idx - ry * ngrp;

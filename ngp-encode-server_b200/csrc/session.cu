@@ -181,7 +181,8 @@ int resize_windows(const FilterSet &fs, int Wd, int Hd, int tw, int th, std::vec
       const int pc0 = fs.half ? X[2] * 2 : X[2], pc1 = fs.half ? X[3] * 2 : X[3];
       const int wx0 = std::min(X[0], pc0) & ~3, ww = ((std::max(X[1], pc1) - wx0) + 3) & ~3;
       const int wy0 = std::min(Y[0], Y[2]), wh = std::max(Y[1], Y[3]) - wy0;
-      const RsLayout L = rs_layout(wh, ww, fs.half ? ww >> 1 : ww, Y[1] - Y[0], Y[3] - Y[2], (dw + 3) & ~3, (dcw + 3) & ~3, HIT_CAP);
+      const int dy0 = (int)ty * th, dh = std::min(th, Hd - dy0), dch = std::min((dy0 + dh + 1) >> 1, cdH) - (dy0 >> 1);
+      const RsLayout L = rs_layout(wh, ww, fs.half ? ww >> 1 : ww, Y[1] - Y[0], Y[3] - Y[2], (dw + 3) & ~3, (dcw + 3) & ~3, dh, dch, fs.vl.size, fs.vc.size, HIT_CAP);
       worst = std::max(worst, L.total);
     }
   return worst;
