@@ -272,6 +272,24 @@ typedef struct nes_unpacked_frame {
 NES_API int nes_unpack_rendered_frame(const uint8_t *buf, uint64_t len, int has_length_prefix,
                                       nes_unpacked_frame *out);
 
+/* ---- pinned receive ring: zero-copy ingest ----------------------------------
+ * Replaces the three payload copies of the reference's ingest chain
+ * (socket_receive_blocking_lpf server.cpp:91-112 -> ParseFromString :175 ->
+ * RenderedFrame ctor rendered_frame.cc:5-27): recv() each length-prefixed message
+ * straight into a slot of page-locked memory, commit it (parsed in place), pass the
+ * returned nes_source (pointers into the slot) to nes_gpu_submit, release the slot
+ * after nes_gpu_wait.  Thread-safe; slots are handed out round-robin. */
+typedef struct nes_ingest_ring nes_ingest_ring;
+NES_API int nes_ingest_ring_create(int n_slots, uint64_t slot_bytes, nes_ingest_ring **out);
+NES_API void nes_ingest_ring_destroy(nes_ingest_ring *r);
+/* Next free slot to receive into; NES_ERR_BUSY when every slot is still referenced. */
+NES_API int nes_ingest_acquire(nes_ingest_ring *r, int *slot, uint8_t **buf, uint64_t *cap);
+/* `len` bytes of one message are in the slot: locate the payload in place, check it against
+ * Camera.width/height (NES_ERR_SHORT_BUFFER; the reference does not check), fill *src. */
+NES_API int nes_ingest_commit(nes_ingest_ring *r, int slot, uint64_t len, int has_length_prefix,
+                              int bytes_per_pixel, nes_unpacked_frame *info, nes_source *src);
+NES_API int nes_ingest_release(nes_ingest_ring *r, int slot);
+
 #ifdef __cplusplus
 }
 #endif

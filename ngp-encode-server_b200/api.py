@@ -93,6 +93,7 @@ ABI_SYMBOLS = [
     "nes_gpu_memcpy_h2d", "nes_gpu_memcpy_d2h", "nes_gpu_atlas_set", "nes_gpu_atlas_load_font",
     "nes_font_rasterise", "nes_gpu_submit", "nes_gpu_wait", "nes_gpu_convert", "nes_gpu_convert_batch_device", "nes_gpu_last_timing",
     "nes_gpu_filter_table", "nes_gpu_text_layout", "nes_unpack_rendered_frame",
+    "nes_ingest_ring_create", "nes_ingest_ring_destroy", "nes_ingest_acquire", "nes_ingest_commit", "nes_ingest_release",
 ]
 
 _lib = None
@@ -138,6 +139,12 @@ def lib() -> C.CDLL:
     L.nes_gpu_filter_table.argtypes = [i32, i32, i32, C.POINTER(C.c_int16), i32, C.POINTER(C.c_int32), i32]
     L.nes_gpu_text_layout.argtypes = [vp, i32, i32, C.POINTER(nes_text_run), C.POINTER(nes_placed_glyph), i32]
     L.nes_unpack_rendered_frame.argtypes = [vp, u64, i32, C.POINTER(nes_unpacked_frame)]
+    L.nes_ingest_ring_create.argtypes = [i32, u64, C.POINTER(vp)]
+    L.nes_ingest_ring_destroy.argtypes = [vp]
+    L.nes_ingest_ring_destroy.restype = None
+    L.nes_ingest_acquire.argtypes = [vp, C.POINTER(i32), C.POINTER(vp), C.POINTER(u64)]
+    L.nes_ingest_commit.argtypes = [vp, i32, u64, i32, i32, C.POINTER(nes_unpacked_frame), C.POINTER(nes_source)]
+    L.nes_ingest_release.argtypes = [vp, i32]
     _lib = L
     return L
 
@@ -192,6 +199,46 @@ def unpack_rendered_frame(buf, prefix: bool = True) -> dict:
         "matrix": [u.matrix[i] for i in range(u.n_matrix)], "frame": (u.frame_off, u.frame_len), "depth": (u.depth_off, u.depth_len),
         "consumed": u.consumed,
     }
+
+
+class IngestRing:
+    """Pinned receive ring (nes_ingest_*): recv() a length-prefixed RenderedFrame straight into a
+    slot, commit (parsed in place), submit the returned source, release after wait.  Replaces the
+    three payload copies of server.cpp:91-112,175 + rendered_frame.cc:5-27."""
+
+    def __init__(self, n_slots: int, slot_bytes: int):
+        self.L = lib()
+        h = C.c_void_p()
+        r = self.L.nes_ingest_ring_create(n_slots, slot_bytes, C.byref(h))
+        if r:
+            raise NesGpuError(r, "nes_ingest_ring_create", strerror(r))
+        self.h = h
+
+    def acquire(self):
+        """-> (slot, uint8 view of the slot's pinned memory)"""
+        slot, buf, cap = C.c_int(), C.c_void_p(), C.c_uint64()
+        r = self.L.nes_ingest_acquire(self.h, C.byref(slot), C.byref(buf), C.byref(cap))
+        if r:
+            raise NesGpuError(r, "nes_ingest_acquire", strerror(r))
+        return slot.value, np.ctypeslib.as_array((C.c_uint8 * cap.value).from_address(buf.value))
+
+    def commit(self, slot: int, length: int, bytes_per_pixel: int = 3, prefix: bool = True):
+        """-> (nes_unpacked_frame, nes_source pointing into the slot)"""
+        info, src = nes_unpacked_frame(), nes_source()
+        r = self.L.nes_ingest_commit(self.h, slot, length, 1 if prefix else 0, bytes_per_pixel, C.byref(info), C.byref(src))
+        if r:
+            raise NesGpuError(r, "nes_ingest_commit", strerror(r))
+        return info, src
+
+    def release(self, slot: int):
+        r = self.L.nes_ingest_release(self.h, slot)
+        if r:
+            raise NesGpuError(r, "nes_ingest_release", strerror(r))
+
+    def close(self):
+        if self.h:
+            self.L.nes_ingest_ring_destroy(self.h)
+            self.h = None
 
 
 def font_rasterise(font_path: str, freetype_so: str | None = None):

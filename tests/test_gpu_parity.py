@@ -485,3 +485,42 @@ def test_batch_many_units_per_cta(N, O, port, session):
     for j in jobs:
         for p in j[3]:
             session.device_free(p)
+
+
+def test_ingest_ring_zero_copy(N, O, port, glyphs, session):
+    """server.cpp:91-112,172-194 replaced end to end: the wire message is received into a pinned
+    slot, parsed in place, and the frame is DMA'd from inside the slot (payload offsets inside a
+    protobuf message are unaligned) -- no host copy of the pixels."""
+    w, h = 640, 360
+    ring = N.IngestRing(3, 8 + 64 + w * h * 4)
+    try:
+        slots = []
+        for f in range(3):
+            rgb, dep = O.synth_rgb(w, h, f), O.synth_depth(w, h, f)
+            msg = O.pack_rendered_frame(f, bool(f & 1), w, h, O.KINITIAL_CAMERA_MATRIX, rgb.tobytes(), dep.tobytes())
+            slot, buf = ring.acquire()
+            buf[: len(msg)] = np.frombuffer(msg, np.uint8)  # stands for recv(fd, buf, len)
+            info, src = ring.commit(slot, len(msg))
+            assert (info.index, info.width, info.height, bool(info.is_left)) == (f, w, h, bool(f & 1))
+            fin = N.nes_frame_in(); fin.n_sources, fin.pix_fmt, fin.width, fin.height, fin.mem = 1, N.PIX_FMT["rgb24"], w, h, N.NES_MEM_HOST
+            fin.src[0] = src
+            sc, dp = N.FrameManager(N.FrameContext(w, h, "yuv420p"), session=session), N.FrameManager(N.FrameContext(w, h, "yuv420p"), session=session)
+            runs = O.reference_strings(index=f)
+            slots.append((slot, session.submit(fin, runs, N.api._frame_out(sc, dp)), sc, dp, rgb, dep, runs, fin))
+        with pytest.raises(N.NesGpuError) as e:
+            ring.acquire()
+        assert e.value.status == N.NES_ERR_BUSY
+        for slot, ticket, sc, dp, rgb, dep, runs, _ in slots:
+            session.wait(ticket)
+            ring.release(slot)
+            surf = np.ascontiguousarray(rgb.copy())
+            for pos, txt in runs:
+                port.render_string(surf, pos, txt, glyphs)
+            assert sc.cropped() == port.rgb_to_yuv420p(surf, "rgb24").cropped()
+            assert dp.cropped() == port.gray_to_yuv420p(dep).cropped()
+        slot, buf = ring.acquire()  # released slots come back
+        buf[:16] = 0
+        with pytest.raises(N.NesGpuError):
+            ring.commit(slot, 16)  # truncated message
+    finally:
+        ring.close()

@@ -101,3 +101,14 @@ def test_gray_luma_dp2a_constants():
         want = ((((d << 7) * 14071 + 33561472) >> 14) + 64) >> 7
         s = d * 56282 + 1081500
         assert s < (1 << 24) and (s >> 16) == want == (d * 219 + 127) // 255 + 16
+
+
+def test_ingest_ring_fails_loudly_without_gpu(N):
+    """The receive ring is page-locked memory for DMA: without a CUDA device it must refuse
+    (NES_ERR_CUDA), not hand out pageable memory silently."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(N.NesGpuError) as e:
+        N.IngestRing(2, 1 << 20)
+    assert e.value.status == N.NES_ERR_CUDA
