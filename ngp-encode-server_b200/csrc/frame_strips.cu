@@ -72,7 +72,7 @@ struct ChunkCtx {
   int32_t H;
   int32_t edge;      // a vertical tap of [cA, cB) is clamped at the frame border
   int32_t rbase;     // chroma-ring slot of chunk-local row 0
-  int32_t fullw;     // full-width strip, 16-byte aligned planes: unconditional vector stores
+  int32_t fullw;     // 16-byte aligned planes, strip width a multiple of 32: vector stores, lanes past the strip idle
   int32_t vec_out, rgb_base, dep_staged;
   uint32_t a_mask;   // alpha byte mask of a pixel word (composite validity)
   uint32_t ky[4], ku[3], kv[3];
@@ -405,7 +405,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
           c.edge = (2 * cA - 3 < 0) || (2 * (cB - 1) + 4 > H - 1);
           c.rbase = rbase;
           c.vec_out = jp->out_vec;
-          c.fullw = jp->out_vec && tw == STRIP_W;
+          c.fullw = jp->out_vec && (tw & 31) == 0;
           c.a_mask = jp->a_off >= 0 ? (0xFFu << (8 * jp->a_off)) : 0xFFFFFFFFu;
           c.rgb_base = jp->rgb_base;
           c.dep_staged = dep_staged;
@@ -581,12 +581,12 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
                 }
                 const uint32_t yw0 = pack_b2(sm[0], sm[1], sm[2], sm[3]), yw1 = pack_b2(sm[4], sm[5], sm[6], sm[7]);
                 const uint32_t o = (uint32_t)(y * sys + lane * 8);
-                if (fullw) stg64(sy + o, yw0, yw1);
+                if (fullw) { if (lane * 8 < tw) stg64(sy + o, yw0, yw1); }
                 else store8(sy + y * sys, lane * 8, yw0, yw1, tw, vec_out);
                 if (dy) {
                   const uint2 dd = lds64(drow + lane * 8);
                   const uint32_t g0 = gray_y4_packed(dd.x), g1 = gray_y4_packed(dd.y);
-                  if (fullw) stg64(dy + (uint32_t)(y * dys + lane * 8), g0, g1);
+                  if (fullw) { if (lane * 8 < tw) stg64(dy + (uint32_t)(y * dys + lane * 8), g0, g1); }
                   else store8(dy + y * dys, lane * 8, g0, g1, tw, vec_out);
                 }
               }
@@ -624,7 +624,8 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
                 const uint32_t yw0 = pack_b2(sm[0], sm[1], sm[2], sm[3]), yw1 = pack_b2(sm[4], sm[5], sm[6], sm[7]);
                 if (fullw) {
                   uint8_t *o = sy + (uint32_t)(y * sys + lane * 4);
-                  stg32(o, yw0); stg32(o + 128, yw1);
+                  if (lane * 4 < tw) stg32(o, yw0);
+                  if (128 + lane * 4 < tw) stg32(o + 128, yw1);
                 } else {
                   uint8_t *o = sy + y * sys;
                   store4(o, lane * 4, yw0, tw, vec_out); store4(o, 128 + lane * 4, yw1, tw, vec_out);
@@ -633,7 +634,8 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
                   const uint32_t g0 = gray_y4_packed(d4[0]), g1 = gray_y4_packed(d4[1]);
                   if (fullw) {
                     uint8_t *od = dy + (uint32_t)(y * dys + lane * 4);
-                    stg32(od, g0); stg32(od + 128, g1);
+                    if (lane * 4 < tw) stg32(od, g0);
+                    if (128 + lane * 4 < tw) stg32(od + 128, g1);
                   } else {
                     uint8_t *od = dy + y * dys;
                     store4(od, lane * 4, g0, tw, vec_out); store4(od, 128 + lane * 4, g1, tw, vec_out);
@@ -667,7 +669,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
           const int ngroups = (cB - cA + 3) >> 2;
           for (int t = warp; t < 2 * ngroups; t += NW) {
             const int row = cA + 4 * (t >> 1) + (lane >> 3);
-            if (row < cB) {
+            if (row < cB && (lane & 7) * 16 < cw) {
               uint8_t *o = (t & 1) ? dv + (uint32_t)(row * dvs) : du + (uint32_t)(row * dus);
               *(uint4 *)(o + (lane & 7) * 16) = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
             }
