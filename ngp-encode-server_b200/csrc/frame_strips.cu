@@ -243,10 +243,22 @@ template <int ROWB>
 __device__ __forceinline__ void select_staged(uint32_t px, uint32_t dep, int n_src, uint32_t a_mask, int lane, uint32_t (&p)[8],
                                               uint32_t (&d4)[2]) {
   uint32_t bd[8];
+  {  // source 0: taken wherever it is valid (nothing to compare against yet)
+    const uint4 q[2] = {lds128(px + lane * 16), lds128(px + 512 + lane * 16)};
+    const uint32_t dw[2] = {lds32(dep + lane * 4), lds32(dep + 128 + lane * 4)};
 #pragma unroll
-  for (int i = 0; i < 8; i++) { p[i] = 0; bd[i] = 256; }
+    for (int h = 0; h < 2; h++) {
+      const uint32_t w[4] = {q[h].x, q[h].y, q[h].z, q[h].w};
 #pragma unroll
-  for (int k = 0; k < TMA_MAX_SOURCES; k++) {
+      for (int i = 0; i < 4; i++) {
+        const bool valid = (w[i] & a_mask) != 0;
+        bd[4 * h + i] = valid ? __byte_perm(dw[h], 0u, 0x4440 + i) : 256u;
+        p[4 * h + i] = valid ? w[i] : 0u;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 1; k < TMA_MAX_SOURCES; k++) {
     if (k >= n_src) break;
     const uint32_t rp = px + (uint32_t)(k * SUB_ROWS) * ROWB + lane * 16;
     const uint32_t dp = dep + (uint32_t)(k * SUB_ROWS) * DEP_ROWB + lane * 4;
