@@ -148,6 +148,15 @@ typedef struct nes_frame_in {
   nes_source src[NES_MAX_SOURCES];
 } nes_frame_in;
 
+/* Destination pixel layouts.  YUV420P is what the reference hands to libavcodec
+ * (three planes).  NV12 (Y plane + one interleaved U0 V0 U1 V1 ... plane: [1] with
+ * linesize >= 2*ceil(width/2), [2] ignored) is the layout hardware encoders take; the
+ * sample values are identical, only the chroma storage differs. */
+typedef enum nes_out_fmt {
+  NES_OUT_YUV420P = 0,
+  NES_OUT_NV12 = 1
+} nes_out_fmt;
+
 /* Destination: two YUV420P images laid out like FrameManager::FrameData
  * (type_managers.h:166-169) after av_image_alloc(..., align 32).  depth[0] may be
  * NULL to skip the depth stream. */
@@ -155,7 +164,7 @@ typedef struct nes_frame_out {
   int32_t width;  /* encoder size (CodecInitInfo, type_managers.h:74-97)              */
   int32_t height;
   int32_t mem;    /* nes_mem_kind of the plane pointers                               */
-  int32_t reserved;
+  int32_t pix_fmt; /* nes_out_fmt: 0 = YUV420P (the reference's encoder input), 1 = NV12 */
   uint8_t *scene[3];
   int32_t scene_linesize[3];
   int32_t reserved2;

@@ -27,6 +27,7 @@ LIB_PATH = os.path.join(HERE, "libnes_gpu.so")
 
 NES_MAX_SOURCES = 8
 NES_MEM_HOST, NES_MEM_DEVICE = 0, 1
+NES_OUT_YUV420P, NES_OUT_NV12 = 0, 1
 
 PIX_FMT = {"rgb24": 0, "bgr24": 1, "rgba": 2, "bgra": 3, "argb": 4, "abgr": 5}
 PIX_BPP = {"rgb24": 3, "bgr24": 3, "rgba": 4, "bgra": 4, "argb": 4, "abgr": 4}
@@ -66,7 +67,7 @@ class nes_frame_in(C.Structure):
 
 
 class nes_frame_out(C.Structure):
-    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mem", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mem", C.c_int32), ("pix_fmt", C.c_int32),
                 ("scene", C.c_void_p * 3), ("scene_linesize", C.c_int32 * 3), ("reserved2", C.c_int32),
                 ("depth", C.c_void_p * 3), ("depth_linesize", C.c_int32 * 3), ("reserved3", C.c_int32)]
 
@@ -486,6 +487,16 @@ class FrameManager:
             o1, o2 = sizes[0], sizes[0] + sizes[1]
             self.planes = [buffer[:o1].reshape(h, self.linesize[0]), buffer[o1:o2].reshape(ch, self.linesize[1]), buffer[o2:o2 + sizes[2]].reshape(ch, self.linesize[2])]
             self.data = [p.ctypes.data for p in self.planes]
+        elif context.pix_fmt == "nv12":
+            # Y plane + one interleaved UV plane (the layout hardware encoders take)
+            cw, ch = (w + 1) // 2, (h + 1) // 2
+            self.linesize = [align32(w), align32(2 * cw), 0]
+            sizes = [self.linesize[0] * h, self.linesize[1] * ch]
+            if buffer is None:
+                buffer = session.host_array(sum(sizes)) if session is not None else np.zeros(sum(sizes), np.uint8)
+            self.buffer = buffer
+            self.planes = [buffer[:sizes[0]].reshape(h, self.linesize[0]), buffer[sizes[0]:sizes[0] + sizes[1]].reshape(ch, self.linesize[1])]
+            self.data = [p.ctypes.data for p in self.planes] + [0]
         else:
             bpp = 1 if context.pix_fmt == "gray" else PIX_BPP[context.pix_fmt]
             if buffer is None:
@@ -498,15 +509,18 @@ class FrameManager:
             self.data = [buffer.ctypes.data]
 
     def cropped(self) -> bytes:
-        """Y||U||V without stride padding (YUV420P frames only)."""
+        """Y||U||V (YUV420P) or Y||UV (NV12) without stride padding."""
         w, h = self.context.width, self.context.height
         cw = (w + 1) // 2
+        if self.context.pix_fmt == "nv12":
+            return self.planes[0][:, :w].tobytes() + self.planes[1][:, :2 * cw].tobytes()
         return self.planes[0][:, :w].tobytes() + self.planes[1][:, :cw].tobytes() + self.planes[2][:, :cw].tobytes()
 
 
 def _frame_out(scene: FrameManager, depth: FrameManager | None) -> nes_frame_out:
     fo = nes_frame_out()
     fo.width, fo.height, fo.mem = scene.context.width, scene.context.height, NES_MEM_HOST
+    fo.pix_fmt = NES_OUT_NV12 if scene.context.pix_fmt == "nv12" else NES_OUT_YUV420P
     for p in range(3):
         fo.scene[p] = scene.data[p]
         fo.scene_linesize[p] = scene.linesize[p]

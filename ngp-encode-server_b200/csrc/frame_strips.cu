@@ -74,6 +74,7 @@ struct ChunkCtx {
   int32_t rbase;     // chroma-ring slot of chunk-local row 0
   int32_t fullw;     // 16-byte aligned planes, strip width a multiple of 32: vector stores, lanes past the strip idle
   int32_t vec_out, rgb_base, dep_staged;
+  int32_t nv12;      // chroma interleaved into one plane (su / du)
   uint32_t a_mask;   // alpha byte mask of a pixel word (composite validity)
   uint32_t ky[4], ku[3], kv[3];
   int32_t sys, sus, svs, dys, dus, dvs;
@@ -431,10 +432,13 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
             c.ku[0] = jp->ku[0]; c.ku[1] = jp->ku[1]; c.kv[0] = jp->kv[0]; c.kv[1] = jp->kv[1];
           }
           c.sys = jp->sys; c.sus = jp->sus; c.svs = jp->svs; c.dys = jp->dys; c.dus = jp->dus; c.dvs = jp->dvs;
-          c.sy = jp->sy + x0; c.su = jp->su + (x0 >> 1); c.sv = jp->sv + (x0 >> 1);
+          const int nv12 = jp->nv12;
+          const int xc = nv12 ? x0 : (x0 >> 1);  // byte offset of the strip inside a chroma row
+          c.nv12 = nv12;
+          c.sy = jp->sy + x0; c.su = jp->su + xc; c.sv = nv12 ? nullptr : jp->sv + xc;
           c.dy = jp->dy ? jp->dy + x0 : nullptr;
-          c.du = jp->dy ? jp->du + (x0 >> 1) : nullptr;
-          c.dv = jp->dy ? jp->dv + (x0 >> 1) : nullptr;
+          c.du = jp->dy ? jp->du + xc : nullptr;
+          c.dv = (jp->dy && !nv12) ? jp->dv + xc : nullptr;
         }
         __syncwarp();
 #pragma unroll 1
@@ -676,14 +680,22 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
         uint8_t *const du = c.du, *const dv = c.dv;
         const int dus = c.dus, dvs = c.dvs;
         // depth chroma planes are constant 128: 16-byte stores, one
-        // warp-store covers 4 rows x 128 bytes of one plane
+        // warp-store covers 4 rows x 128 bytes of one plane (NV12: 2 rows x 256 bytes of the UV plane)
         if (dy && fullw) {
-          const int ngroups = (cB - cA + 3) >> 2;
-          for (int t = warp; t < 2 * ngroups; t += NW) {
-            const int row = cA + 4 * (t >> 1) + (lane >> 3);
-            if (row < cB && (lane & 7) * 16 < cw) {
-              uint8_t *o = (t & 1) ? dv + (uint32_t)(row * dvs) : du + (uint32_t)(row * dus);
-              *(uint4 *)(o + (lane & 7) * 16) = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+          if (!c.nv12) {
+            const int ngroups = (cB - cA + 3) >> 2;
+            for (int t = warp; t < 2 * ngroups; t += NW) {
+              const int row = cA + 4 * (t >> 1) + (lane >> 3);
+              if (row < cB && (lane & 7) * 16 < cw) {
+                uint8_t *o = (t & 1) ? dv + (uint32_t)(row * dvs) : du + (uint32_t)(row * dus);
+                *(uint4 *)(o + (lane & 7) * 16) = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+              }
+            }
+          } else {
+            for (int t = warp; 2 * t < cB - cA; t += NW) {
+              const int row = cA + 2 * t + (lane >> 4);
+              if (row < cB && (lane & 15) * 16 < 2 * cw)
+                *(uint4 *)(du + (uint32_t)(row * dus) + (lane & 15) * 16) = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
             }
           }
         }
@@ -732,7 +744,16 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
             }
             const uint32_t ub = __byte_perm(__byte_perm(us[0], us[1], 0x0040), __byte_perm(us[2], us[3], 0x0040), 0x5410);
             const uint32_t vb = __byte_perm(__byte_perm(vs[0], vs[1], 0x0040), __byte_perm(vs[2], vs[3], 0x0040), 0x5410);
-            if (fullw) {
+            if (c.nv12) {
+              // U0 V0 U1 V1 | U2 V2 U3 V3: chroma column cc sits at byte 2*cc of the UV row
+              const uint32_t w0 = __byte_perm(ub, vb, 0x5140), w1 = __byte_perm(ub, vb, 0x7362);
+              if (fullw) {
+                stg64(su_ + (uint32_t)(ci * sus + 2 * cc), w0, w1);
+              } else {
+                store8(su_ + ci * sus, 2 * cc, w0, w1, 2 * cw, vec_out);
+                if (dy) store8(du + ci * dus, 2 * cc, 0x80808080u, 0x80808080u, 2 * cw, vec_out);
+              }
+            } else if (fullw) {
               stg32(su_ + (uint32_t)(ci * sus + cc), ub);
               stg32(sv_ + (uint32_t)(ci * svs + cc), vb);
             } else {

@@ -121,7 +121,7 @@ struct alignas(64) DevJob {
   int32_t n_glyphs;
   int32_t tma_ok;     // 16-byte aligned rows, <= TMA_MAX_SOURCES sources: rows are staged by tensor-map TMA
   int32_t use_mask;   // tile_mask valid (tiles_x*tiles_y <= 32*MASK_WORDS)
-  int32_t pad1;
+  int32_t nv12;       // chroma goes to one interleaved plane (su / du; sv / dv unused)
   uint32_t tile_mask[MASK_WORDS];  // bit (band * strips_x + strip) set: a placed glyph intersects that cell
   int32_t tiles_x, tiles_y, tile_base;  // k_resize_tiles work (general jobs only; 0 tiles otherwise)
   // k_frame_strips work (same-size jobs only)

@@ -215,7 +215,7 @@ __device__ __forceinline__ void hpass_any(const DevFilter &f, int d0, int n_dst,
 // staged in shared memory, per destination row [pos - r0, coef[0..size)] as int32 / int16.
 template <int NP>
 __device__ __forceinline__ void vpass(int size, uint32_t vtab, int vrow_bytes, const uint32_t (&in)[NP], int stride, int d0y, int n_rows, int n_cols,
-                                      uint8_t *const (&dst)[NP], const int (&dst_stride)[NP], bool vec, int tid) {
+                                      uint8_t *const (&dst)[NP], const int (&dst_stride)[NP], bool vec, int tid, bool interleave = false) {
   const int ngrp = (n_cols + 3) >> 2;
   const int total = n_rows * ngrp;
   const int sh = (ngrp & (ngrp - 1)) == 0 ? __ffs(ngrp) - 1 : -1;
@@ -250,6 +250,20 @@ __device__ __forceinline__ void vpass(int size, uint32_t vtab, int vrow_bytes, c
       }
 #pragma unroll
       for (int p = 0; p < NP; p++) { v[p][0] >>= 19; v[p][1] >>= 19; v[p][2] >>= 19; v[p][3] >>= 19; }
+    }
+    if (NP == 2 && interleave) {  // NV12: the two planes go out as U0 V0 U1 V1 ... into dst[0]
+      uint8_t *q = dst[0] + (size_t)(d0y + ry) * dst_stride[0] + 8 * gx;
+      uint8_t b[8];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { b[2 * k] = (uint8_t)clip8(v[0][k]); b[2 * k + 1] = (uint8_t)clip8(v[NP - 1][k]); }
+      if (vec && 4 * gx + 4 <= n_cols) {
+        *(uint2 *)q = make_uint2(b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24), b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (4 * gx + (k >> 1) < n_cols) q[k] = b[k];
+      }
+      continue;
     }
 #pragma unroll
     for (int p = 0; p < NP; p++) {
@@ -426,9 +440,10 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
     const int ds_y[1] = {jb.sys};
     vpass<1>(jb.vl.size, sb + L.vtab, vl_row, in_y, t.dwp * 4, t.dy0, t.dh, t.dw, dst_y, ds_y, vec, tid);
     const uint32_t in_c[2] = {sb + L.hu, sb + L.hv};
-    uint8_t *const dst_c[2] = {jb.su + t.cx0, jb.sv + t.cx0};
+    const bool nv12 = jb.nv12 != 0;
+    uint8_t *const dst_c[2] = {jb.su + (nv12 ? 2 * t.cx0 : t.cx0), nv12 ? nullptr : jb.sv + t.cx0};
     const int ds_c[2] = {jb.sus, jb.svs};
-    vpass<2>(jb.vc.size, sb + L.vtab + t.dh * vl_row, vc_row, in_c, t.dcwp * 4, t.cy0, t.dch, t.dcw, dst_c, ds_c, vec, tid);
+    vpass<2>(jb.vc.size, sb + L.vtab + t.dh * vl_row, vc_row, in_c, t.dcwp * 4, t.cy0, t.dch, t.dcw, dst_c, ds_c, vec, tid, nv12);
   }
 
   // ---- depth: hScale8To15 (>>7) -> range compression -> vertical; U = V = 128 ----------------------
@@ -440,15 +455,20 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
     uint8_t *const dst_d[1] = {jb.dy + t.dx0};
     const int ds_d[1] = {jb.dys};
     vpass<1>(jb.vl.size, sb + L.vtab, vl_row, out_d, t.dwp * 4, t.dy0, t.dh, t.dw, dst_d, ds_d, vec, tid);
-    const int ngrp = (t.dcw + 3) >> 2;
+    // depth chroma is constant 128; NV12: one plane of 2*dcw bytes per row
+    const bool nv12 = jb.nv12 != 0;
+    const int rowb = nv12 ? 2 * t.dcw : t.dcw, xoff = nv12 ? 2 * t.cx0 : t.cx0;
+    const int ngrp = (rowb + 3) >> 2;
     for (int idx = tid; idx < t.dch * ngrp; idx += RS_THREADS) {
       const int ry = idx / ngrp, gx = idx - ry * ngrp;
-      uint8_t *pu = jb.du + (size_t)(t.cy0 + ry) * jb.dus + t.cx0 + 4 * gx, *pv = jb.dv + (size_t)(t.cy0 + ry) * jb.dvs + t.cx0 + 4 * gx;
-      if (vec && 4 * gx + 4 <= t.dcw) {
-        *(uint32_t *)pu = 0x80808080u; *(uint32_t *)pv = 0x80808080u;
+      uint8_t *pu = jb.du + (size_t)(t.cy0 + ry) * jb.dus + xoff + 4 * gx;
+      uint8_t *pv = nv12 ? nullptr : jb.dv + (size_t)(t.cy0 + ry) * jb.dvs + xoff + 4 * gx;
+      if (vec && 4 * gx + 4 <= rowb) {
+        *(uint32_t *)pu = 0x80808080u;
+        if (pv) *(uint32_t *)pv = 0x80808080u;
       } else {
         for (int k = 0; k < 4; k++)
-          if (4 * gx + k < t.dcw) { pu[k] = 128; pv[k] = 128; }
+          if (4 * gx + k < rowb) { pu[k] = 128; if (pv) pv[k] = 128; }
       }
     }
   }

@@ -247,12 +247,12 @@ struct PlaneLayout {  // where one YUV420P image sits inside a linear buffer
   size_t total;
 };
 
-PlaneLayout yuv_layout(const int32_t ls[3], int Hd, size_t base) {
+PlaneLayout yuv_layout(const int32_t ls[3], int Hd, size_t base, bool nv12) {
   PlaneLayout p;
   const int cH = (Hd + 1) >> 1;
   p.off[0] = base; p.bytes[0] = (size_t)ls[0] * Hd;
   p.off[1] = p.off[0] + p.bytes[0]; p.bytes[1] = (size_t)ls[1] * cH;
-  p.off[2] = p.off[1] + p.bytes[1]; p.bytes[2] = (size_t)ls[2] * cH;
+  p.off[2] = p.off[1] + p.bytes[1]; p.bytes[2] = nv12 ? 0 : (size_t)ls[2] * cH;
   p.total = p.bytes[0] + p.bytes[1] + p.bytes[2];
   return p;
 }
@@ -284,8 +284,10 @@ int validate(const nes_gpu_session *s, const nes_frame_in *in, const nes_frame_o
     return NES_ERR_TOO_LARGE;
   for (int k = 0; k < in->n_sources; k++)
     if ((int64_t)in->src[k].rgb_stride * H >= (int64_t)1 << 31 || (int64_t)in->src[k].depth_stride * H >= (int64_t)1 << 31) return NES_ERR_TOO_LARGE;
-  for (int p = 0; p < 3; p++) {
-    const int minls = p ? (Wd + 1) / 2 : Wd;
+  if (out->pix_fmt != NES_OUT_YUV420P && out->pix_fmt != NES_OUT_NV12) return NES_ERR_INVALID_ARG;
+  const bool nv12 = out->pix_fmt == NES_OUT_NV12;
+  for (int p = 0; p < (nv12 ? 2 : 3); p++) {
+    const int minls = p ? (nv12 ? 2 : 1) * ((Wd + 1) / 2) : Wd;
     if (!out->scene[p] || out->scene_linesize[p] < minls) return NES_ERR_INVALID_ARG;
     if (want_depth && (!out->depth[p] || out->depth_linesize[p] < minls)) return NES_ERR_INVALID_ARG;
   }
@@ -366,8 +368,8 @@ void job_alignment(DevJob *jb) {
     iv = iv && aligned16(jb->src[k].rgb, jb->src[k].rgb_stride);
     if (jb->src[k].depth) iv = iv && aligned16(jb->src[k].depth, jb->src[k].depth_stride);
   }
-  bool ov = aligned16(jb->sy, jb->sys) && aligned16(jb->su, jb->sus) && aligned16(jb->sv, jb->svs);
-  if (jb->dy) ov = ov && aligned16(jb->dy, jb->dys) && aligned16(jb->du, jb->dus) && aligned16(jb->dv, jb->dvs);
+  bool ov = aligned16(jb->sy, jb->sys) && aligned16(jb->su, jb->sus) && (jb->nv12 || aligned16(jb->sv, jb->svs));
+  if (jb->dy) ov = ov && aligned16(jb->dy, jb->dys) && aligned16(jb->du, jb->dus) && (jb->nv12 || aligned16(jb->dv, jb->dvs));
   jb->in_vec = iv;
   jb->out_vec = ov;
   // rows staged by tensor-map TMA: 16-byte aligned rows; composites only for 4-byte pixels
@@ -784,8 +786,8 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
     jb->sy = out->scene[0]; jb->su = out->scene[1]; jb->sv = out->scene[2];
     if (want_depth) { jb->dy = out->depth[0]; jb->du = out->depth[1]; jb->dv = out->depth[2]; }
   } else {
-    ps = yuv_layout(out->scene_linesize, Hd, 0);
-    pd = yuv_layout(out->depth_linesize, Hd, align_up(ps.total, 256));
+    ps = yuv_layout(out->scene_linesize, Hd, 0, out->pix_fmt == NES_OUT_NV12);
+    pd = yuv_layout(out->depth_linesize, Hd, align_up(ps.total, 256), out->pix_fmt == NES_OUT_NV12);
     const size_t need = pd.off[0] + (want_depth ? pd.total : 0);
     if ((st = ensure_dev(s, &sl.d_out, &sl.d_out_cap, need))) return st;
     jb->sy = sl.d_out + ps.off[0]; jb->su = sl.d_out + ps.off[1]; jb->sv = sl.d_out + ps.off[2];
@@ -793,6 +795,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   }
   jb->sys = out->scene_linesize[0]; jb->sus = out->scene_linesize[1]; jb->svs = out->scene_linesize[2];
   jb->dys = out->depth_linesize[0]; jb->dus = out->depth_linesize[1]; jb->dvs = out->depth_linesize[2];
+  jb->nv12 = out->pix_fmt == NES_OUT_NV12;
 
   jb->general = resize;
   if (resize && n_gl > 0) band_glyphs(jb, sl.h_glyphs, n_gl, &s->scratch_banded);
@@ -829,7 +832,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
     for (int im = 0; im < nimg; im++) {
       uint8_t *const *pl = im ? out->depth : out->scene;
       const PlaneLayout &L = im ? pd : ps;
-      const bool contiguous = pl[1] == pl[0] + L.bytes[0] && pl[2] == pl[1] + L.bytes[1];
+      const bool contiguous = pl[1] == pl[0] + L.bytes[0] && (jb->nv12 || pl[2] == pl[1] + L.bytes[1]);
       direct = direct && contiguous && is_pinned(pl[0]);
     }
     if (direct) {
@@ -841,7 +844,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
       for (int im = 0; im < nimg; im++) {
         uint8_t *const *pl = im ? out->depth : out->scene;
         const PlaneLayout &L = im ? pd : ps;
-        for (int p = 0; p < 3; p++) sl.staged.push_back(StagedCopy{pl[p], sl.h_out + L.off[p], L.bytes[p]});
+        for (int p = 0; p < (jb->nv12 ? 2 : 3); p++) sl.staged.push_back(StagedCopy{pl[p], sl.h_out + L.off[p], L.bytes[p]});
       }
     }
   }
@@ -938,6 +941,7 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
       jb->dy = out[f].depth[0]; jb->du = out[f].depth[1]; jb->dv = out[f].depth[2];
       jb->dys = out[f].depth_linesize[0]; jb->dus = out[f].depth_linesize[1]; jb->dvs = out[f].depth_linesize[2];
     }
+    jb->nv12 = out[f].pix_fmt == NES_OUT_NV12;
     jb->general = general;
     if (general && n_gl > 0) band_glyphs(jb, bt.h_glyphs + gl_used - n_gl, n_gl, &s->scratch_banded);
     if (general) {

@@ -524,3 +524,69 @@ def test_ingest_ring_zero_copy(N, O, port, glyphs, session):
             ring.commit(slot, 16)  # truncated message
     finally:
         ring.close()
+
+
+def _nv12(yuv) -> bytes:
+    """The oracle's planar result re-laid as NV12: same samples, chroma interleaved."""
+    y, u, v = yuv.planes()
+    uv = np.empty((u.shape[0], 2 * u.shape[1]), np.uint8)
+    uv[:, 0::2], uv[:, 1::2] = u, v
+    return y.tobytes() + uv.tobytes()
+
+
+@pytest.mark.parametrize("fmt,n,w,h,wd,hd", [("rgb24", 1, 1280, 720, 1280, 720), ("rgba", 2, 640, 360, 640, 360), ("rgb24", 1, 322, 94, 322, 94),
+                                             ("rgb24", 1, 384, 216, 256, 144), ("rgba", 3, 480, 270, 320, 180), ("bgra", 1, 200, 100, 300, 150)])
+def test_nv12_output(N, O, port, glyphs, session, fmt, n, w, h, wd, hd):
+    """NV12 destination (Y + interleaved UV): the same samples as YUV420P, from both kernels, with
+    composite, overlay and depth stream; full-width, ragged-width and unaligned strips."""
+    rng = np.random.default_rng(w + n)
+    if n == 1:
+        img = rng.integers(0, 256, (h, w, N.PIX_BPP[fmt]), dtype=np.uint8)
+        dep = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        srcs, comp, cdep = [(img, dep)], img, dep
+    else:
+        srcs, rgbs, deps = _rgba_sources(O, rng, n, w, h, fmt)
+        comp, cdep = port.composite(rgbs, deps, fmt)
+    runs = O.reference_strings(index=5)
+    surf = np.ascontiguousarray(comp.copy())
+    for pos, txt in runs:
+        (port.render_string if surf.shape[2] == 3 else (lambda a, p, t, g: port.render_string4(a, p, t, g, fmt)))(surf, pos, txt, glyphs)
+    want_s, want_d = _nv12(port.rgb_to_yuv420p(surf, fmt, wd, hd)), _nv12(port.gray_to_yuv420p(np.ascontiguousarray(cdep), wd, hd))
+    scene, depth = N.FrameManager(N.FrameContext(wd, hd, "nv12"), session=session), N.FrameManager(N.FrameContext(wd, hd, "nv12"))
+    sources = [(np.ascontiguousarray(a).reshape(-1), np.ascontiguousarray(d).reshape(-1), 0, 0) for a, d in srcs]
+    fin = N.Session.frame_in(fmt, w, h, sources)
+    session.convert(fin, runs, N.api._frame_out(scene, depth))
+    assert scene.cropped() == want_s, first_diff(scene.cropped(), want_s)
+    assert depth.cropped() == want_d, first_diff(depth.cropped(), want_d)
+
+
+def test_side_by_side_stereo_packing(N, O, port, session):
+    """Two eyes into one side-by-side frame (BASELINE config 3's layout) in a single launch: each eye
+    is a job whose destination planes start half a frame to the right and share the full line size."""
+    w, h = 1280, 720
+    ysz, csz = N.align32(2 * w) * h, N.align32(w) * (h // 2)
+    d_s, d_d = session.device_alloc(ysz + 2 * csz), session.device_alloc(ysz + 2 * csz)
+    fins, fouts, ptrs, eyes = [], [], [d_s, d_d], []
+    for eye in range(2):
+        rgb, dep = O.synth_rgb(w, h, 10 + eye), O.synth_depth(w, h, 10 + eye)
+        d_rgb, d_dep = session.device_alloc(w * h * 3), session.device_alloc(w * h)
+        session.h2d(d_rgb, rgb); session.h2d(d_dep, dep)
+        ptrs += [d_rgb, d_dep]; eyes.append((rgb, dep))
+        fins.append(N.Session.frame_in("rgb24", w, h, [((d_rgb, w * h * 3), (d_dep, w * h), 0, 0)], mem=N.NES_MEM_DEVICE))
+        fo = N.nes_frame_out(); fo.width, fo.height, fo.mem = w, h, N.NES_MEM_DEVICE
+        for p, (off, ls, xoff) in enumerate([(0, N.align32(2 * w), eye * w), (ysz, N.align32(w), eye * w // 2), (ysz + csz, N.align32(w), eye * w // 2)]):
+            fo.scene[p], fo.scene_linesize[p], fo.depth[p], fo.depth_linesize[p] = d_s + off + xoff, ls, d_d + off + xoff, ls
+        fouts.append(fo)
+    before = session.launches
+    session.convert_batch_device(fins, None, fouts, sync=True)
+    assert session.launches - before == 1
+    sbs_s, sbs_d = N.FrameManager(N.FrameContext(2 * w, h, "yuv420p")), N.FrameManager(N.FrameContext(2 * w, h, "yuv420p"))
+    session.d2h(sbs_s.buffer, d_s); session.d2h(sbs_d.buffer, d_d)
+    for eye, (rgb, dep) in enumerate(eyes):
+        ws, wd_ = port.rgb_to_yuv420p(rgb, "rgb24").planes(), port.gray_to_yuv420p(dep).planes()
+        for got, want in ((sbs_s, ws), (sbs_d, wd_)):
+            assert np.array_equal(got.planes[0][:, eye * w:(eye + 1) * w], want[0])
+            assert np.array_equal(got.planes[1][:, eye * w // 2:(eye + 1) * w // 2], want[1])
+            assert np.array_equal(got.planes[2][:, eye * w // 2:(eye + 1) * w // 2], want[2])
+    for p in ptrs:
+        session.device_free(p)
