@@ -107,6 +107,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// the same on a precomputed 32-bit shared address (the consumer loop keeps the barrier base in a register)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -472,12 +485,13 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
 
   // ============================= consumer warps ===========================================
   const uint32_t ring0 = smem_base + L::OFF_RING;
+  const uint32_t full0 = smem_base + L::OFF_BAR, empty0 = full0 + NS_MAX * 8;
   int q0 = 0, par0 = 0;  // sub-stage cursor of the chunk's first sub-stage: slot, parity of its use count
   for (int chunk_it = 0;; chunk_it++) {
     // the second sub-stage of this chunk (the ring may wrap between the two)
     int q1 = q0 + 1, par1 = par0;
     if (q1 == ns) { q1 = 0; par1 ^= 1; }
-    mbar_wait(&s_full[q0], (uint32_t)par0);
+    mbar_wait_a(full0 + q0 * 8, (uint32_t)par0);
     const ChunkCtx &c = *(const ChunkCtx *)(smem + L::OFF_CTX + (chunk_it & (NCTX - 1)) * L::CTX_BYTES);
     const int last = c.last;
     {
@@ -493,7 +507,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
 
       if (!c.tma || mode == MODE_MATERIALIZED || c.stamp) {
         // whole-chunk work on the staged rows: needs both sub-stages
-        mbar_wait(&s_full[q1], (uint32_t)par1);
+        mbar_wait_a(full0 + q1 * 8, (uint32_t)par1);
         uint8_t *const g[2] = {smem + L::OFF_STAGE + q0 * slot_bytes, smem + L::OFF_STAGE + q1 * slot_bytes};
         // ---- fill our rows ourselves when they were not staged by TMA ------------------------
         if (!c.tma) {
@@ -556,7 +570,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
         for (int i = 0; i < CHUNK_ROWS / SUB_ROWS; i++) {
           const int r = warp + i * SUB_ROWS;
           const int y = yc0 + r;
-          if (i == 1) mbar_wait(&s_full[q1], (uint32_t)par1);
+          if (i == 1) mbar_wait_a(full0 + q1 * 8, (uint32_t)par1);
           if (y >= ra && y < rb) {
             const uint32_t row = sb[i] + warp * ROWB;
             const uint32_t drow = sb[i] + dep_off + warp * DEP_ROWB;
@@ -662,7 +676,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
           }
           // this warp is done with its row of the sub-stage: release it to the producer
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[i ? q1 : q0]);
+          if (lane == 0) mbar_arrive_a(empty0 + (i ? q1 : q0) * 8);
         }
       }
       consumer_sync();
