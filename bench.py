@@ -171,6 +171,33 @@ def cpu_reference(wl_name: str, threads: int, budget_s: float, flags: int | None
                       + ("; composite = C port (no reference implementation exists)" if wl["n_src"] > 1 else "")}
 
 
+def bind_to_gpu_numa(local: int, world: int):
+    """One process per GPU: run (and first-touch its pinned buffers) on CPUs close to that GPU.
+    NVML gives the GPU's ideal CPU set; ranks that share a set split it.  Returns a short note."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        ideal = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            words = (max(allowed) // 64) + 1
+            masks = [pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(i), words) for i in range(world)]
+            sets = [sorted(c for c in allowed if (m[c // 64] >> (c % 64)) & 1) for m in masks]
+            if sets[local]:
+                peers = [i for i in range(world) if sets[i] == sets[local]]
+                k, n = peers.index(local), len(peers)
+                share = sets[local][k * len(sets[local]) // n:(k + 1) * len(sets[local]) // n]
+                ideal = share or sets[local]
+        except Exception:
+            ideal = None
+        if ideal is None:
+            ideal = allowed[local * len(allowed) // world:(local + 1) * len(allowed) // world] or allowed
+        os.sched_setaffinity(0, ideal)
+        return f"cpus {ideal[0]}-{ideal[-1]}"
+    except (AttributeError, OSError):
+        return "unbound"
+
+
 def reference_threads(sessions: int) -> int:
     """The reference runs one hot-path thread per eye per session (main.cpp:274-282)."""
     return max(1, min(os.cpu_count() or 1, 2 * sessions))
@@ -233,6 +260,7 @@ def main():
         emit({"error": "no CUDA device: the pixel pipeline has no CPU fallback"})
         return 2
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_numa(local, world) if world > 1 else "unbound (single process)"
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -241,7 +269,7 @@ def main():
         if world > 1:
             dist.barrier()
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local) if rank == 0 else None  # one nvidia-smi poller per box, not per rank
     s = n.Session(device=local, max_width=max(wl["w"], wl["wd"]), max_height=max(wl["h"], wl["hd"]), max_sources=wl["n_src"], ring_depth=3)
     metrics, bitmaps = n.synth.load_glyph_table()
     s.atlas_set(metrics, bitmaps)
@@ -324,7 +352,8 @@ def main():
     torch.cuda.synchronize()
     t1 = time.time()
     barrier()
-    sampler.window(t0, t1)
+    if sampler:
+        sampler.window(t0, t1)
     dev_ms = e0.elapsed_time(e1)
     launches = s.launches - l0
     if world > 1:
@@ -379,7 +408,8 @@ def main():
         dt = time.perf_counter() - p0
         t1 = time.time()
         barrier()
-        sampler.window(t0, t1)
+        if sampler:
+            sampler.window(t0, t1)
         if world > 1:
             tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -396,8 +426,10 @@ def main():
         e2e["last_frame_us"] = {k: round(v, 1) for k, v in tm.items() if k.endswith("_us")}
         e2e["pcie_share"] = round((tm["h2d_us"] + tm["d2h_us"]) / max(tm["total_us"], 1e-9), 3)
 
-    sampler.stop()
-    clocks = sampler.summary()
+    clocks = None
+    if sampler:
+        sampler.stop()
+        clocks = sampler.summary()
 
     # ---- roofline of the dominant kernel --------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -421,7 +453,7 @@ def main():
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "p50_frame_latency_ms": None if lat_p50 is None else round(lat_p50, 3),
             "single_frame_launch_fps": None if single is None else round(single, 1),
-            "host_issue_ms_per_step": round(host_issue_ms / args.steps, 4)}
+            "host_issue_ms_per_step": round(host_issue_ms / args.steps, 4), "host_binding": numa_note}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         s.close()
