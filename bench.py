@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--in-flight", type=int, default=3, help="frames in flight on the e2e path (= session ring depth)")
     ap.add_argument("--warmup-seconds", type=float, default=1.0, help="minimum wall time of untimed warm-up (clock ramp)")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -270,7 +271,7 @@ def main():
             dist.barrier()
 
     sampler = ClockSampler(local) if rank == 0 else None  # one nvidia-smi poller per box, not per rank
-    s = n.Session(device=local, max_width=max(wl["w"], wl["wd"]), max_height=max(wl["h"], wl["hd"]), max_sources=wl["n_src"], ring_depth=3)
+    s = n.Session(device=local, max_width=max(wl["w"], wl["wd"]), max_height=max(wl["h"], wl["hd"]), max_sources=wl["n_src"], ring_depth=args.in_flight)
     metrics, bitmaps = n.synth.load_glyph_table()
     s.atlas_set(metrics, bitmaps)
     bpp = n.PIX_BPP[wl["fmt"]]
@@ -315,7 +316,7 @@ def main():
         def step_dev():
             ts = []
             for f in range(B):
-                if len(ts) == 3:
+                if len(ts) == args.in_flight:
                     s.wait(ts.pop(0))
                 ts.append(s.submit_prepared(fins_dev[f], runs_made[f], fouts_dev[f]))
             for t in ts:
@@ -389,7 +390,7 @@ def main():
         def step_host():
             ts = []
             for f in range(B):
-                if len(ts) == 3:
+                if len(ts) == args.in_flight:
                     s.wait(ts.pop(0))
                 ts.append(s.submit_prepared(fins_host[f], runs_made[f], fouts_host[f][0]))
             for t in ts:
@@ -415,7 +416,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = {"value": world * B * e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": B * in_bytes, "d2h_bytes_per_step": B * out_bytes,
-               "steps": e_steps, "frames_in_flight": 3, "host_memory": "pinned (nes_gpu_host_alloc)"}
+               "steps": e_steps, "frames_in_flight": args.in_flight, "host_memory": "pinned (nes_gpu_host_alloc)"}
         lats = []
         for i in range(30):
             p = time.perf_counter()

@@ -590,3 +590,84 @@ def test_side_by_side_stereo_packing(N, O, port, session):
             assert np.array_equal(got.planes[2][:, eye * w // 2:(eye + 1) * w // 2], want[2])
     for p in ptrs:
         session.device_free(p)
+
+
+def test_stress_random_sequence(N, O, port, glyphs, session):
+    """300 back-to-back frames of random shape / format / source count / text / destination size
+    through submit+wait with frames in flight (exercises the self re-arming work counters, the
+    sub-stage ring across launches with different slot sizes, tensor-map caching and both kernels);
+    every 10th frame is checked against the oracle."""
+    rng = np.random.default_rng(2024)
+    shapes = [(64, 32), (130, 46), (256, 64), (322, 94), (512, 96), (640, 360), (768, 130), (1280, 720)]
+    pending = []
+    for it in range(300):
+        w, h = shapes[rng.integers(len(shapes))]
+        resize = rng.integers(4) == 0
+        wd, hd = ((w * 2 // 3) & ~1, (h * 2 // 3) & ~1) if resize else (w, h)
+        fmt = ["rgb24", "rgba", "bgra", "argb"][rng.integers(4)]
+        n = 1 if fmt == "rgb24" else int(rng.integers(1, 5))
+        if n == 1:
+            img = rng.integers(0, 256, (h, w, N.PIX_BPP[fmt]), dtype=np.uint8)
+            dep = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            srcs, comp, cdep = [(img, dep)], img, dep
+        else:
+            srcs, rgbs, deps = _rgba_sources(O, rng, n, w, h, fmt)
+            comp, cdep = (rgbs, deps), None
+        runs = O.reference_strings(index=it) if rng.integers(2) else None
+        scene, depth = N.FrameManager(N.FrameContext(wd, hd, "yuv420p"), session=session), N.FrameManager(N.FrameContext(wd, hd, "yuv420p"), session=session)
+        sources = [(np.ascontiguousarray(a).reshape(-1), np.ascontiguousarray(d).reshape(-1), 0, 0) for a, d in srcs]
+        fin = N.Session.frame_in(fmt, w, h, sources)
+        if len(pending) == 3:
+            _finish(N, O, port, glyphs, session, pending.pop(0))
+        ticket = session.submit(fin, runs, N.api._frame_out(scene, depth))
+        pending.append((ticket, it, fmt, n, comp, cdep, runs, wd, hd, scene, depth, sources, fin))
+    while pending:
+        _finish(N, O, port, glyphs, session, pending.pop(0))
+
+
+def _finish(N, O, port, glyphs, session, item):
+    ticket, it, fmt, n, comp, cdep, runs, wd, hd, scene, depth, sources, fin = item
+    session.wait(ticket)
+    if it % 10:
+        return
+    if n > 1:
+        comp, cdep = port.composite(comp[0], comp[1], fmt)
+    surf = np.ascontiguousarray(comp.copy())
+    for pos, txt in runs or []:
+        (port.render_string if surf.shape[2] == 3 else (lambda a, p, t, g: port.render_string4(a, p, t, g, fmt)))(surf, pos, txt, glyphs)
+    want_s, want_d = port.rgb_to_yuv420p(surf, fmt, wd, hd).cropped(), port.gray_to_yuv420p(np.ascontiguousarray(cdep), wd, hd).cropped()
+    assert scene.cropped() == want_s, (it, fmt, n, wd, hd, first_diff(scene.cropped(), want_s))
+    assert depth.cropped() == want_d, (it, fmt, n, wd, hd, first_diff(depth.cropped(), want_d))
+
+
+def test_two_sessions_two_threads(N, O, port, glyphs):
+    """The reference runs one process_frame_thread per eye (main.cpp:274-282): two host threads,
+    each with its own session on the same GPU, converting concurrently."""
+    import threading
+    w, h = 640, 360
+    errors = []
+
+    def eye(is_left):
+        try:
+            s = N.Session(device=0, max_width=w, max_height=h, max_sources=2)
+            s.atlas_set(glyphs.metrics, glyphs.bitmaps)
+            for f in range(40):
+                rgb, dep = O.synth_rgb(w, h, f + 100 * is_left), O.synth_depth(w, h, f + 100 * is_left)
+                runs = O.reference_strings(index=f, is_left=bool(is_left))
+                sc, dp = run_gpu(N, s, "rgb24", [(rgb, dep)], w, h, runs=runs, pinned=True)
+                if f % 8 == 0:
+                    surf = np.ascontiguousarray(rgb.copy())
+                    for pos, txt in runs:
+                        port.render_string(surf, pos, txt, glyphs)
+                    assert sc.cropped() == port.rgb_to_yuv420p(surf, "rgb24").cropped()
+                    assert dp.cropped() == port.gray_to_yuv420p(dep).cropped()
+            s.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ths = [threading.Thread(target=eye, args=(k,)) for k in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors
