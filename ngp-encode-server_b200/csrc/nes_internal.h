@@ -43,7 +43,7 @@ constexpr int GLYPH_BANDS = 256;          // placed glyphs of a resize job are b
 #endif
 // Shared-memory layout of one resize tile (byte offsets; every region 16-byte aligned).
 struct RsLayout {
-  int y14, u14, v14, hy, hu, hv, dep, mask, hits, vtab, total;
+  int y14, u14, v14, hy, hu, hv, dep, mask, hits, vtab, src, total;
 };
 // wh x ww: union source window (ww multiple of 4), cww: chroma plane row stride, nl / nc: luma /
 // chroma source rows fed to the vertical pass, dwp / dcwp: padded destination widths
@@ -62,6 +62,7 @@ NES_HD inline RsLayout rs_layout(int wh, int ww, int cww, int nl, int nc, int dw
   L.mask = take(wh * ((ww >> 5) + 1) * 4);
   L.hits = take(hit_cap * 4 + 16);
   L.vtab = take(dh * ((4 + 2 * vls + 3) & ~3) + dch * ((4 + 2 * vcs + 3) & ~3));
+  L.src = take(NES_MAX_SOURCES * 24);  // staged per-source pointers and strides
   L.total = o;
   return L;
 }

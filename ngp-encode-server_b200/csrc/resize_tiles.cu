@@ -124,6 +124,59 @@ __device__ __forceinline__ void load_group(const DevJob &jb, int x, int y, bool 
   }
 }
 
+// Per-source addressing staged in shared memory once per tile (the job descriptor lives in global
+// memory; stage A would otherwise re-read it for every group of pixels).
+struct SrcDesc {
+  const uint8_t *rgb, *depth;
+  int32_t rgb_stride, depth_stride;
+};
+
+// Aligned fast path of load_group for 4-byte pixels: the lane's column offset is fixed, sources come
+// from shared memory, the first source is taken wherever it is valid without a compare.
+__device__ __forceinline__ void load_group_fast4(const SrcDesc *sd, int n_src, uint32_t a_mask, int xb /* x * 4 */, int x, int y, uint32_t (&px)[4],
+                                                 uint32_t *d4) {
+  uint4 q[4];
+  uint32_t dw[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (k < n_src) {
+      q[k] = __ldg((const uint4 *)(sd[k].rgb + (uint32_t)(y * sd[k].rgb_stride + xb)));
+      dw[k] = __ldg((const uint32_t *)(sd[k].depth + (uint32_t)(y * sd[k].depth_stride + x)));
+    }
+  if (n_src == 1) {  // a single source is converted as it is (alpha only matters to the composite)
+    px[0] = q[0].x; px[1] = q[0].y; px[2] = q[0].z; px[3] = q[0].w;
+    *d4 = dw[0];
+    return;
+  }
+  uint32_t bd[4];
+  {
+    const uint32_t w[4] = {q[0].x, q[0].y, q[0].z, q[0].w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const bool valid = (w[i] & a_mask) != 0;
+      bd[i] = valid ? __byte_perm(dw[0], 0u, 0x4440 + i) : 256u;
+      px[i] = valid ? w[i] : 0u;
+    }
+  }
+  auto consider = [&](const uint4 &p, uint32_t d) {
+    const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t di = __byte_perm(d, 0u, 0x4440 + i);
+      const bool take = (w[i] & a_mask) != 0 && di < bd[i];
+      bd[i] = take ? di : bd[i];
+      px[i] = take ? w[i] : px[i];
+    }
+  };
+#pragma unroll
+  for (int k = 1; k < 4; k++)
+    if (k < n_src) consider(q[k], dw[k]);
+  for (int k = 4; k < n_src; k++)
+    consider(__ldg((const uint4 *)(sd[k].rgb + (uint32_t)(y * sd[k].rgb_stride + xb))), __ldg((const uint32_t *)(sd[k].depth + (uint32_t)(y * sd[k].depth_stride + x))));
+  const uint32_t lo = __byte_perm(min(bd[0], 255u), min(bd[1], 255u), 0x0040), hi = __byte_perm(min(bd[2], 255u), min(bd[3], 255u), 0x0040);
+  *d4 = __byte_perm(lo, hi, 0x5410);
+}
+
 struct Tile {
   int dx0, dw, dwp, dy0, dh;      // destination luma block (dwp: row stride of the H-pass output, multiple of 4)
   int cx0, dcw, dcwp, cy0, dch;   // destination chroma block
@@ -336,6 +389,13 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
   int *s_nhits = s_hits + HIT_CAP;
   if (L.total > smem_cap) { __trap(); }
 
+  if (tid < jb.n_src) {
+    SrcDesc *sdw = (SrcDesc *)(smem + L.src);
+    sdw[tid].rgb = jb.src[tid].rgb; sdw[tid].depth = jb.src[tid].depth;
+    sdw[tid].rgb_stride = jb.src[tid].rgb_stride; sdw[tid].depth_stride = jb.src[tid].depth_stride;
+  }
+  __syncthreads();
+
   // ---- overlay bit mask of the window (render_text.cc:94-106: coverage != 0 -> white) --------
   bool has_text = false;
   if (jb.n_glyphs > 0) {
@@ -377,13 +437,24 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
     const uint32_t ky0 = jb.ky[0], ky1 = jb.ky[1], ku0 = jb.ku[0], ku1 = jb.ku[1], kv0 = jb.kv[0], kv1 = jb.kv[1];
     const uint32_t white = BPP == 4 ? (0x00FFFFFFu << (8 * jb.rgb_base)) : 0x00FFFFFFu;
     const int ngrp = t.ww >> 2;
-    for (int r = warp; r < t.wh; r += NWARP) {
-      const int y = t.wy0 + r;
-      for (int g = lane; g < ngrp; g += 32) {
+    // the aligned fast path needs every source's depth plane (a lone source without a depth stream has none)
+    const bool fast = BPP == 4 && jb.in_vec && (jb.n_src > 1 || want_depth);
+    const int n_src = jb.n_src;
+    const uint32_t a_mask = jb.a_off >= 0 ? (0xFFu << (8 * jb.a_off)) : 0xFFFFFFFFu;
+    const SrcDesc *sd = (const SrcDesc *)(smem + L.src);
+    // a lane owns one column of 4-pixel groups (two when the window is wider than 128 pixels)
+    for (int g = lane; g < ngrp; g += 32) {
+      const int x = t.wx0 + 4 * g;
+      const bool inside = x + 4 <= W;
+      const uint32_t mshift = (4 * g) & 31;
+      const uint32_t *mrow = s_mask + (g >> 3);
+      for (int r = warp; r < t.wh; r += NWARP) {
+        const int y = t.wy0 + r;
         uint32_t px[4], d4;
-        load_group<BPP>(jb, t.wx0 + 4 * g, y, want_depth, px, &d4);
+        if (fast && inside) load_group_fast4(sd, n_src, a_mask, x * 4, x, y, px, &d4);
+        else load_group<BPP>(jb, x, y, want_depth, px, &d4);
         if (has_text) {
-          const uint32_t m = (s_mask[r * mw + (g >> 3)] >> ((4 * g) & 31)) & 15u;
+          const uint32_t m = (mrow[r * mw] >> mshift) & 15u;
 #pragma unroll
           for (int i = 0; i < 4; i++)
             if ((m >> i) & 1u) px[i] |= white;
