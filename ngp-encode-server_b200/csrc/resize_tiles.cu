@@ -18,7 +18,7 @@
 //     overlay from a per-tile bit mask, and writes 14-bit planes (int16) + depth bytes to shared
 //     memory: no packed-pixel tile, no scratch frame, the composite costs no extra pass;
 //   * stage H: lane = destination column (its taps live in registers), warp = source row;
-//   * stage V: lane = 4 adjacent destination columns (8-byte shared loads), 4-byte stores.
+//   * stage V: lane = 4 adjacent destination columns (int32 rows, 16-byte shared loads), 4-byte stores.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -43,13 +43,6 @@ __device__ __forceinline__ int dp2a_hi_s(uint32_t a, uint32_t b, int c) {
 __device__ __forceinline__ int dot_px(uint32_t k0, uint32_t k1, uint32_t px, int acc) { return dp2a_hi_s(k1, px, dp2a_lo_s(k0, px, acc)); }
 
 __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
-__device__ __forceinline__ int sext_lo(uint32_t w) {  // sign-extended low half (prmt: selector bit 3 replicates the sign of the byte)
-  int d;
-  asm("prmt.b32 %0, %1, %1, 0x9910;" : "=r"(d) : "r"(w));
-  return d;
-}
-__device__ __forceinline__ int sext_hi(uint32_t w) { return (int)w >> 16; }
-
 // 4 pixels at columns x..x+3 of row y as pixel words (3-byte pixels: r | g<<8 | b<<16 | junk<<24,
 // the junk byte has coefficient 0) + their 4 depth bytes, after the depth-select composite.
 template <int BPP>
