@@ -144,6 +144,7 @@ struct alignas(64) DevJob {
   int32_t glyph_band_shift, glyph_max_h;
   int32_t glyph_band[GLYPH_BANDS + 1];
   int32_t rs_tw, rs_th;     // destination tile of the resize kernel
+  RsLayout rs_lay;          // shared-memory carve-up for the largest tile of this size pair (same bases for every tile)
   const int32_t *rs_win_x;  // [tiles_x][4]: luma source columns [lc0, lc1), chroma source columns [cc0, cc1)
   const int32_t *rs_win_y;  // [tiles_y][4]: luma source rows [lr0, lr1), chroma source rows [cr0, cr1)
 };

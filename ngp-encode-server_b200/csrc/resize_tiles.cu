@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
   t.cww = half ? t.ww >> 1 : t.ww;
   const int nl = t.lr1 - t.lr0, nc = t.cr1 - t.cr0;
 
-  // shared memory carve-up (rs_layout is shared with the host's sizing code)
+  // shared memory carve-up (rs_layout is shared with the host's sizing code; the host sizes the
+  // allocation for the largest tile, jb.rs_lay)
   const RsLayout L = rs_layout(t.wh, t.ww, t.cww, nl, nc, t.dwp, t.dcwp, t.dh, t.dch, jb.vl.size, jb.vc.size, HIT_CAP);
   int16_t *s_y14 = (int16_t *)(smem + L.y14);  // [wh][ww]
   int16_t *s_u14 = (int16_t *)(smem + L.u14);  // [wh][cww]
@@ -413,12 +414,27 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
         const uint8_t *cov = jb.atlas + pg.atlas_off;
         const int q0 = max(0, t.wy0 - pg.y), q1 = min(pg.h, y1 - pg.y);
         const int p0 = max(0, t.wx0 - pg.x), p1 = min(pg.w, x1 - pg.x);
-        for (int q = q0; q < q1; q++)
-          for (int p = p0 + lane; p < p1; p += 32)
+        // lanes over the flattened clipped bitmap (a 10 x 14 glyph keeps all 32 lanes busy); the row of
+        // element i is floor(i / gw) by an exact reciprocal multiply (i < 4096, gw <= 256)
+        const int gw = p1 - p0, n = (q1 - q0) * gw;
+        if (n < 4096 && gw <= 256) {
+          const uint32_t rcp = ((1u << 20) + gw - 1) / gw;
+          for (int i = lane; i < n; i += 32) {
+            const int qq = (int)(((uint32_t)i * rcp) >> 20);
+            const int q = q0 + qq, p = p0 + i - qq * gw;
             if (cov[q * pg.pitch + p]) {
               const int xx = pg.x + p - t.wx0;
               atomicOr(&s_mask[(pg.y + q - t.wy0) * mw + (xx >> 5)], 1u << (xx & 31));
             }
+          }
+        } else {
+          for (int q = q0; q < q1; q++)
+            for (int p = p0 + lane; p < p1; p += 32)
+              if (cov[q * pg.pitch + p]) {
+                const int xx = pg.x + p - t.wx0;
+                atomicOr(&s_mask[(pg.y + q - t.wy0) * mw + (xx >> 5)], 1u << (xx & 31));
+              }
+        }
       }
       __syncthreads();
     }

@@ -43,6 +43,7 @@ struct FilterSet {  // device tables for one (W,H,Wd,Hd)
   int half = 0, csW = 0;
   int tw = 0, th = 0;      // destination tile of the resize kernel for this size pair
   int smem_need = 0;       // shared memory of its worst tile
+  RsLayout layout{};       // carve-up for the largest tile dimensions (one layout for all tiles)
   const int32_t *win_x = nullptr, *win_y = nullptr;  // device: per tile column / row source windows
 };
 
@@ -154,7 +155,7 @@ int fmt_info(int fmt, int *bpp, int *base, int *a_off, bool *bgr) {
 // Source windows of the resize tiles for one tile size: per tile column {lc0, lc1, cc0, cc1}, per tile
 // row {lr0, lr1, cr0, cr1} (filter positions are monotone except at fixed-up borders, so scan), and
 // the shared memory the worst tile needs (rs_layout, the same function the kernel carves with).
-int resize_windows(const FilterSet &fs, int Wd, int Hd, int tw, int th, std::vector<int32_t> *wx, std::vector<int32_t> *wy) {
+int resize_windows(const FilterSet &fs, int Wd, int Hd, int tw, int th, std::vector<int32_t> *wx, std::vector<int32_t> *wy, RsLayout *lay) {
   const int cdW = (Wd + 1) >> 1, cdH = (Hd + 1) >> 1;
   wx->clear(); wy->clear();
   for (int dx0 = 0; dx0 < Wd; dx0 += tw) {
@@ -173,7 +174,8 @@ int resize_windows(const FilterSet &fs, int Wd, int Hd, int tw, int th, std::vec
     for (int i = cy0; i < cy1; i++) { cr0 = std::min(cr0, fs.h_vc.pos[i]); cr1 = std::max(cr1, fs.h_vc.pos[i] + fs.vc.size); }
     wy->insert(wy->end(), {lr0, lr1, cr0, cr1});
   }
-  int worst = 0;
+  // one carve-up for every tile: each region sized for the largest value of its dimensions over all tiles
+  int m_wh = 0, m_ww = 0, m_cww = 0, m_nl = 0, m_nc = 0, m_dwp = 0, m_dcwp = 0, m_dh = 0, m_dch = 0;
   for (size_t ty = 0; ty * 4 < wy->size(); ty++)
     for (size_t tx = 0; tx * 4 < wx->size(); tx++) {
       const int32_t *X = &(*wx)[tx * 4], *Y = &(*wy)[ty * 4];
@@ -182,9 +184,13 @@ int resize_windows(const FilterSet &fs, int Wd, int Hd, int tw, int th, std::vec
       const int wx0 = std::min(X[0], pc0) & ~3, ww = ((std::max(X[1], pc1) - wx0) + 3) & ~3;
       const int wy0 = std::min(Y[0], Y[2]), wh = std::max(Y[1], Y[3]) - wy0;
       const int dy0 = (int)ty * th, dh = std::min(th, Hd - dy0), dch = std::min((dy0 + dh + 1) >> 1, cdH) - (dy0 >> 1);
-      const RsLayout L = rs_layout(wh, ww, fs.half ? ww >> 1 : ww, Y[1] - Y[0], Y[3] - Y[2], (dw + 3) & ~3, (dcw + 3) & ~3, dh, dch, fs.vl.size, fs.vc.size, HIT_CAP);
-      worst = std::max(worst, L.total);
+      m_wh = std::max(m_wh, wh); m_ww = std::max(m_ww, ww); m_cww = std::max(m_cww, fs.half ? ww >> 1 : ww);
+      m_nl = std::max(m_nl, Y[1] - Y[0]); m_nc = std::max(m_nc, Y[3] - Y[2]);
+      m_dwp = std::max(m_dwp, (dw + 3) & ~3); m_dcwp = std::max(m_dcwp, (dcw + 3) & ~3);
+      m_dh = std::max(m_dh, dh); m_dch = std::max(m_dch, dch);
     }
+  *lay = rs_layout(m_wh, m_ww, m_cww, m_nl, m_nc, m_dwp, m_dcwp, m_dh, m_dch, fs.vl.size, fs.vc.size, HIT_CAP);
+  const int worst = lay->total;
   return worst;
 }
 
@@ -224,7 +230,7 @@ int get_filters(nes_gpu_session *s, int W, int H, int Wd, int Hd, FilterSet **ou
   int pick = -1;
   for (int pass = 0; pass < 2 && pick < 0; pass++)
     for (int i = 0; i < (int)(sizeof(kTiles) / sizeof(kTiles[0])); i++) {
-      const int need = resize_windows(fs, Wd, Hd, kTiles[i][0], kTiles[i][1], &wx, &wy);
+      const int need = resize_windows(fs, Wd, Hd, kTiles[i][0], kTiles[i][1], &wx, &wy, &fs.layout);
       if (need <= (pass == 0 ? RS_SMEM_GOAL : RS_SMEM_MAX)) { pick = i; fs.smem_need = need; break; }
     }
   if (pick < 0) { cudaFree(fs.blob); return NES_ERR_TOO_LARGE; }  // scale ratio beyond what one tile can stage
@@ -804,7 +810,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
     if ((st = get_filters(s, W, H, Wd, Hd, &fs))) return st;
     jb->hl = fs->hl; jb->hc = fs->hc; jb->vl = fs->vl; jb->vc = fs->vc;
     jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need;
-    jb->rs_tw = fs->tw; jb->rs_th = fs->th; jb->rs_win_x = fs->win_x; jb->rs_win_y = fs->win_y;
+    jb->rs_tw = fs->tw; jb->rs_th = fs->th; jb->rs_win_x = fs->win_x; jb->rs_win_y = fs->win_y; jb->rs_lay = fs->layout;
   }
   job_tiles(jb, 0);
   job_alignment(jb);
@@ -949,7 +955,7 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
       if ((st = get_filters(s, W, H, out[f].width, out[f].height, &fs))) return st;
       jb->hl = fs->hl; jb->hc = fs->hc; jb->vl = fs->vl; jb->vc = fs->vc;
       jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need;
-      jb->rs_tw = fs->tw; jb->rs_th = fs->th; jb->rs_win_x = fs->win_x; jb->rs_win_y = fs->win_y;
+      jb->rs_tw = fs->tw; jb->rs_th = fs->th; jb->rs_win_x = fs->win_x; jb->rs_win_y = fs->win_y; jb->rs_lay = fs->layout;
     }
     job_tiles(jb, tile_base);
     tile_base += jb->tiles_x * jb->tiles_y;
