@@ -386,6 +386,7 @@ def main():
     # ---- e2e: host pinned buffers through submit/wait, 3 frames in flight ----------------
     e2e = None
     lat_p50 = None
+    lat_banded = None
     if not args.no_e2e:
         def step_host():
             ts = []
@@ -423,6 +424,17 @@ def main():
             s.wait(s.submit_prepared(fins_host[i % B], runs_made[i % B], fouts_host[i % B][0]))
             lats.append(1000.0 * (time.perf_counter() - p))
         lat_p50 = statistics.median(lats)
+        # the same with the low-latency mode (frame uploaded / converted / downloaded in 2 row bands)
+        lat_banded = None
+        if w == wd and h == hd:
+            s.set_latency_bands(env_int("NES_BENCH_BANDS", 2))
+            lats = []
+            for i in range(30):
+                p = time.perf_counter()
+                s.wait(s.submit_prepared(fins_host[i % B], runs_made[i % B], fouts_host[i % B][0]))
+                lats.append(1000.0 * (time.perf_counter() - p))
+            lat_banded = statistics.median(lats)
+            s.set_latency_bands(1)
         tm = s.last_timing()
         e2e["last_frame_us"] = {k: round(v, 1) for k, v in tm.items() if k.endswith("_us")}
         e2e["pcie_share"] = round((tm["h2d_us"] + tm["d2h_us"]) / max(tm["total_us"], 1e-9), 3)
@@ -453,6 +465,7 @@ def main():
             "config": dict(config, frames_per_step=B, l2="inputs larger than L2: ring of %d distinct frames, %.0f MB touched per step" % (B, B * (in_bytes + out_bytes) / 1e6)),
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "p50_frame_latency_ms": None if lat_p50 is None else round(lat_p50, 3),
+            "p50_frame_latency_ms_2_bands": None if (lat_p50 is None or lat_banded is None) else round(lat_banded, 3),
             "single_frame_launch_fps": None if single is None else round(single, 1),
             "host_issue_ms_per_step": round(host_issue_ms / args.steps, 4), "host_binding": numa_note}
 

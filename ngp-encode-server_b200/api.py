@@ -89,7 +89,7 @@ class nes_unpacked_frame(C.Structure):
 # every symbol include/nes_gpu.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "nes_gpu_abi_version", "nes_gpu_strerror", "nes_gpu_session_error", "nes_gpu_device_count",
-    "nes_gpu_session_create", "nes_gpu_session_destroy", "nes_gpu_session_stream", "nes_gpu_session_launches",
+    "nes_gpu_session_create", "nes_gpu_session_destroy", "nes_gpu_session_stream", "nes_gpu_session_launches", "nes_gpu_session_set_latency_bands",
     "nes_gpu_host_alloc", "nes_gpu_host_free", "nes_gpu_device_alloc", "nes_gpu_device_free",
     "nes_gpu_memcpy_h2d", "nes_gpu_memcpy_d2h", "nes_gpu_atlas_set", "nes_gpu_atlas_load_font",
     "nes_font_rasterise", "nes_gpu_submit", "nes_gpu_wait", "nes_gpu_convert", "nes_gpu_convert_batch_device", "nes_gpu_last_timing",
@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.nes_gpu_session_stream.argtypes = [vp]
     L.nes_gpu_session_stream.restype = vp
     L.nes_gpu_session_launches.argtypes = [vp]
+    L.nes_gpu_session_set_latency_bands.argtypes = [vp, i32]
     L.nes_gpu_session_launches.restype = u64
     L.nes_gpu_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.nes_gpu_host_free.argtypes = [vp]
@@ -315,6 +316,11 @@ class Session:
     @property
     def launches(self) -> int:
         return self.L.nes_gpu_session_launches(self.h)
+
+    def set_latency_bands(self, bands: int):
+        """Low-latency mode: pinned-to-pinned same-size frames go through in `bands` row bands
+        (download of a band overlaps the upload of the next)."""
+        self._check(self.L.nes_gpu_session_set_latency_bands(self.h, bands), "nes_gpu_session_set_latency_bands")
 
     # -- memory ------------------------------------------------------------------
     def host_array(self, nbytes: int) -> np.ndarray:

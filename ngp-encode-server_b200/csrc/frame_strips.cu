@@ -340,7 +340,7 @@ __device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *sub0, uin
 
 template <int BPP>
 __global__ void __launch_bounds__(CTA_THREADS, 3)
-k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters, int ns, int slot_bytes) {
+k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int total_units, uint32_t *__restrict__ counters, int ns, int slot_bytes) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using L = StripSmem<BPP>;
   constexpr int ROWB = L::ROWB;
@@ -365,8 +365,9 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
     // =========================== producer warp ===========================================
     // the first unit is static (grid <= total_units: every CTA has work), the rest come from a
     // global counter
-    int cur_u = blockIdx.x, next_u = 0;
-    if (lane == 0) next_u = (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
+    // (a launch may cover only the unit range [unit_begin, total_units): banded low-latency submits)
+    int cur_u = unit_begin + (int)blockIdx.x, next_u = 0;
+    if (lane == 0) next_u = unit_begin + (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
     next_u = __shfl_sync(0xffffffffu, next_u, 0);
     int q = 0, par = 0, round0 = 1;  // sub-stage cursor: slot, parity of its use count, first trip round the ring
     int chunk_it = 0, rbase = 0;
@@ -472,7 +473,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uin
         if (rbase >= RING_ROWS) rbase -= RING_ROWS;
       }
       cur_u = next_u;
-      if (lane == 0 && cur_u < total_units) next_u = (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
+      if (lane == 0 && cur_u < total_units) next_u = unit_begin + (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
       next_u = __shfl_sync(0xffffffffu, next_u, 0);
     }
     // the last CTA to run out of work re-arms the counters for the next launch on this stream
@@ -882,7 +883,7 @@ void plan_frame_strips(DevJob *jobs, int n_jobs) {
   }
 }
 
-int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream) {
+int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream, int unit_begin, int unit_end) {
   int total[2] = {0, 0}, staged[2];
   launch_staged(jobs_host, n_jobs, staged);
   for (int j = 0; j < n_jobs; j++) {
@@ -892,11 +893,14 @@ int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_j
   int launches = 0;
   for (int cls = 0; cls < 2; cls++) {
     if (total[cls] == 0) continue;
+    // a unit range only makes sense for a single job (its units are numbered from 0)
+    const int u0 = (n_jobs == 1 && unit_end > 0) ? unit_begin : 0, u1 = (n_jobs == 1 && unit_end > 0) ? std::min(unit_end, total[cls]) : total[cls];
+    if (u1 <= u0) continue;
     const StripsConfig c = strips_config(cls, staged[cls]);
     if (c.ns < 2) return -1;
-    const int grid = std::min(total[cls], g_num_sms * c.ctas);
-    if (cls == 0) k_frame_strips<3><<<grid, CTA_THREADS, c.smem, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[0], counters, c.ns, c.slot);
-    else k_frame_strips<4><<<grid, CTA_THREADS, c.smem, (cudaStream_t)stream>>>(jobs_dev, n_jobs, total[1], counters + 2, c.ns, c.slot);
+    const int grid = std::min(u1 - u0, g_num_sms * c.ctas);
+    if (cls == 0) k_frame_strips<3><<<grid, CTA_THREADS, c.smem, (cudaStream_t)stream>>>(jobs_dev, n_jobs, u0, u1, counters, c.ns, c.slot);
+    else k_frame_strips<4><<<grid, CTA_THREADS, c.smem, (cudaStream_t)stream>>>(jobs_dev, n_jobs, u0, u1, counters + 2, c.ns, c.slot);
     launches++;
   }
   return launches;

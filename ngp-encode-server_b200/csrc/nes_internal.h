@@ -150,7 +150,8 @@ struct alignas(64) DevJob {
 };
 
 // Launchers (frame_strips.cu, resize_tiles.cu).  jobs: device pointer to n_jobs descriptors.
-int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream);
+// unit_end > 0 (single-job launches only): process only the units [unit_begin, unit_end) of the job
+int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream, int unit_begin = 0, int unit_end = 0);
 // Assigns seg_rows / unit_base of the same-size jobs of a launch (host).
 void plan_frame_strips(DevJob *jobs_host, int n_jobs);
 int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);

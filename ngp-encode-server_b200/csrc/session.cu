@@ -32,6 +32,7 @@ namespace {
 
 constexpr int kMaxBatch = 256;
 constexpr int kBatchRing = 8;
+constexpr int kMaxBands = 8;
 constexpr int kBatchGlyphFactor = 8;  // placed glyphs per batched launch = this x cfg.max_glyphs
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -61,6 +62,7 @@ struct Slot {
   DevJob *h_job = nullptr, *d_job = nullptr;
   DevPlaced *h_glyphs = nullptr, *d_glyphs = nullptr;
   cudaEvent_t e_start = nullptr, e_in = nullptr, e_k0 = nullptr, e_k1 = nullptr, e_out = nullptr;
+  cudaEvent_t e_band_in[kMaxBands] = {}, e_band_k[kMaxBands] = {};  // banded submits: rows uploaded / converted per band
   uint64_t ticket = 0;
   bool busy = false;
   int n_launches = 0;
@@ -97,6 +99,7 @@ struct nes_gpu_session {
   int sticky = 0;
   std::vector<nes_placed_glyph> scratch_placed;
   std::vector<DevPlaced> scratch_banded;
+  int latency_bands = 1;  // > 1: upload / convert / download a frame in that many row bands (nes_gpu_session_set_latency_bands)
 };
 
 namespace {
@@ -542,6 +545,10 @@ int nes_gpu_session_create(const nes_gpu_cfg *cfg, nes_gpu_session **out) {
     cudaEvent_t *ev[5] = {&sl.e_start, &sl.e_in, &sl.e_k0, &sl.e_k1, &sl.e_out};
     for (cudaEvent_t *e : ev)
       if (cudaEventCreate(e) != cudaSuccess) return fail(NES_ERR_CUDA);
+    for (int b = 0; b < kMaxBands; b++)
+      if (cudaEventCreateWithFlags(&sl.e_band_in[b], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&sl.e_band_k[b], cudaEventDisableTiming) != cudaSuccess)
+        return fail(NES_ERR_CUDA);
     if (cudaHostAlloc((void **)&sl.h_job, sizeof(DevJob), cudaHostAllocDefault) != cudaSuccess) return fail(NES_ERR_CUDA);
     if (cudaMalloc((void **)&sl.d_job, sizeof(DevJob)) != cudaSuccess) return fail(NES_ERR_CUDA);
     if (cudaHostAlloc((void **)&sl.h_glyphs, gl_bytes, cudaHostAllocDefault) != cudaSuccess) return fail(NES_ERR_CUDA);
@@ -565,6 +572,10 @@ void nes_gpu_session_destroy(nes_gpu_session *s) {
     cudaEvent_t ev[5] = {sl.e_start, sl.e_in, sl.e_k0, sl.e_k1, sl.e_out};
     for (cudaEvent_t e : ev)
       if (e) cudaEventDestroy(e);
+    for (int b = 0; b < kMaxBands; b++) {
+      if (sl.e_band_in[b]) cudaEventDestroy(sl.e_band_in[b]);
+      if (sl.e_band_k[b]) cudaEventDestroy(sl.e_band_k[b]);
+    }
   }
   for (BatchTables &b : s->batch) {
     cudaFreeHost(b.h_jobs); cudaFree(b.d_jobs); cudaFreeHost(b.h_glyphs); cudaFree(b.d_glyphs);
@@ -582,6 +593,13 @@ void nes_gpu_session_destroy(nes_gpu_session *s) {
 }
 
 void *nes_gpu_session_stream(nes_gpu_session *s) { return s ? (void *)s->st_k : nullptr; }
+
+int nes_gpu_session_set_latency_bands(nes_gpu_session *s, int bands) {
+  if (!s || bands < 1 || bands > kMaxBands) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->latency_bands = bands;
+  return NES_OK;
+}
 uint64_t nes_gpu_session_launches(nes_gpu_session *s) { return s ? s->launches : 0; }
 
 int nes_gpu_host_alloc(size_t bytes, void **out) {
@@ -737,6 +755,8 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
 
   sl.staged.clear();
   CU_TRY(s, cudaEventRecord(sl.e_start, s->st_in));
+  bool banded = false, pinned_upload = false;
+  struct PinnedUpload { const uint8_t *rgb, *depth; uint8_t *d_rgb, *d_depth; size_t rs, ds; } up[NES_MAX_SOURCES] = {};
 
   // ---- inputs ----
   if (in->mem == NES_MEM_DEVICE) {
@@ -757,6 +777,9 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
       if (need_depth_in) all_pinned = all_pinned && is_pinned(in->src[k].depth);
     }
     if (!all_pinned && (st = ensure_host(s, &sl.h_in, &sl.h_in_cap, need))) return st;
+    // banded low-latency submit: pinned host buffers both ways, same-size path; the uploads are issued band by
+    // band further down, interleaved with the launches
+    banded = s->latency_bands > 1 && all_pinned && !resize && out->mem == NES_MEM_HOST;
     for (int k = 0; k < in->n_sources; k++) {
       const nes_source &sr = in->src[k];
       const size_t o_rgb = (rgb_sz + dep_sz) * k, o_dep = o_rgb + rgb_sz;
@@ -767,12 +790,9 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
       jb->src[k].depth = need_depth_in ? sl.d_in + o_dep : nullptr;
       jb->src[k].depth_stride = (int)ds_dev;
       if (all_pinned) {
-        if (rs == rs_dev) CU_TRY(s, cudaMemcpyAsync(sl.d_in + o_rgb, sr.rgb, rs * (H - 1) + (size_t)W * bpp, cudaMemcpyHostToDevice, s->st_in));
-        else CU_TRY(s, cudaMemcpy2DAsync(sl.d_in + o_rgb, rs_dev, sr.rgb, rs, (size_t)W * bpp, H, cudaMemcpyHostToDevice, s->st_in));
-        if (need_depth_in) {
-          if (ds == ds_dev) CU_TRY(s, cudaMemcpyAsync(sl.d_in + o_dep, sr.depth, ds * (H - 1) + W, cudaMemcpyHostToDevice, s->st_in));
-          else CU_TRY(s, cudaMemcpy2DAsync(sl.d_in + o_dep, ds_dev, sr.depth, ds, W, H, cudaMemcpyHostToDevice, s->st_in));
-        }
+        // issued below (whole frame, or band by band): remember where the rows are
+        up[k] = PinnedUpload{sr.rgb, need_depth_in ? sr.depth : nullptr, sl.d_in + o_rgb, sl.d_in + o_dep, rs, ds};
+        pinned_upload = true;
       } else {
         // the one host memcpy of the payload: caller memory -> pinned staging
         if (rs == rs_dev) std::memcpy(sl.h_in + o_rgb, sr.rgb, rs * (H - 1) + (size_t)W * bpp);
@@ -820,37 +840,96 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
 
   if (n_gl > 0) CU_TRY(s, cudaMemcpyAsync(sl.d_glyphs, sl.h_glyphs, (size_t)n_gl * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaMemcpyAsync(sl.d_job, sl.h_job, sizeof(DevJob), cudaMemcpyHostToDevice, s->st_in));
-  CU_TRY(s, cudaEventRecord(sl.e_in, s->st_in));
 
-  // ---- kernels ----
-  CU_TRY(s, cudaStreamWaitEvent(s->st_k, sl.e_in, 0));
-  CU_TRY(s, cudaEventRecord(sl.e_k0, s->st_k));
-  sl.n_launches = run_kernels(s, sl.d_job, sl.h_job, 1, s->st_k);
-  CU_TRY(s, cudaGetLastError());
-  CU_TRY(s, cudaEventRecord(sl.e_k1, s->st_k));
-
-  // ---- download ----
-  CU_TRY(s, cudaStreamWaitEvent(s->st_out, sl.e_k1, 0));
-  if (out->mem == NES_MEM_HOST) {
-    const size_t total = pd.off[0] + (want_depth ? pd.total : 0);
-    const int nimg = want_depth ? 2 : 1;
-    bool direct = true;
-    for (int im = 0; im < nimg; im++) {
-      uint8_t *const *pl = im ? out->depth : out->scene;
-      const PlaneLayout &L = im ? pd : ps;
-      const bool contiguous = pl[1] == pl[0] + L.bytes[0] && (jb->nv12 || pl[2] == pl[1] + L.bytes[1]);
-      direct = direct && contiguous && is_pinned(pl[0]);
+  // rows [y0, y1) of every (pinned) source -> the device copy
+  const size_t rs_dev_ = align_up((size_t)W * bpp, 16), ds_dev_ = align_up((size_t)W, 16);
+  auto upload_rows = [&](int y0, int y1) -> int {
+    if (y1 <= y0) return NES_OK;
+    for (int k = 0; k < in->n_sources; k++) {
+      const PinnedUpload &u = up[k];
+      const size_t rows = (size_t)(y1 - y0);
+      if (u.rs == rs_dev_) CU_TRY(s, cudaMemcpyAsync(u.d_rgb + y0 * rs_dev_, u.rgb + y0 * u.rs, y1 == H ? (rows - 1) * u.rs + (size_t)W * bpp : rows * u.rs, cudaMemcpyHostToDevice, s->st_in));
+      else CU_TRY(s, cudaMemcpy2DAsync(u.d_rgb + y0 * rs_dev_, rs_dev_, u.rgb + y0 * u.rs, u.rs, (size_t)W * bpp, rows, cudaMemcpyHostToDevice, s->st_in));
+      if (u.depth) {
+        if (u.ds == ds_dev_) CU_TRY(s, cudaMemcpyAsync(u.d_depth + y0 * ds_dev_, u.depth + y0 * u.ds, y1 == H ? (rows - 1) * u.ds + (size_t)W : rows * u.ds, cudaMemcpyHostToDevice, s->st_in));
+        else CU_TRY(s, cudaMemcpy2DAsync(u.d_depth + y0 * ds_dev_, ds_dev_, u.depth + y0 * u.ds, u.ds, (size_t)W, rows, cudaMemcpyHostToDevice, s->st_in));
+      }
     }
-    if (direct) {
-      CU_TRY(s, cudaMemcpyAsync(out->scene[0], sl.d_out + ps.off[0], ps.total, cudaMemcpyDeviceToHost, s->st_out));
-      if (want_depth) CU_TRY(s, cudaMemcpyAsync(out->depth[0], sl.d_out + pd.off[0], pd.total, cudaMemcpyDeviceToHost, s->st_out));
-    } else {
-      if ((st = ensure_host(s, &sl.h_out, &sl.h_out_cap, total))) return st;
-      CU_TRY(s, cudaMemcpyAsync(sl.h_out, sl.d_out, total, cudaMemcpyDeviceToHost, s->st_out));
+    return NES_OK;
+  };
+
+  // destination planes: straight into the caller's memory when it is pinned and laid out like av_image_alloc
+  const int nimg = want_depth ? 2 : 1, nplanes = jb->nv12 ? 2 : 3;
+  bool direct = out->mem == NES_MEM_HOST;
+  for (int im = 0; direct && im < nimg; im++) {
+    uint8_t *const *pl = im ? out->depth : out->scene;
+    const PlaneLayout &L = im ? pd : ps;
+    const bool contiguous = pl[1] == pl[0] + L.bytes[0] && (jb->nv12 || pl[2] == pl[1] + L.bytes[1]);
+    direct = contiguous && is_pinned(pl[0]);
+  }
+  banded = banded && direct && jb->segs_y >= 2;
+
+  if (banded) {
+    // ---- low-latency path: upload, convert and download the frame in row bands, so that the download of
+    // band b overlaps the upload of band b+1 and only the last band's kernel + download follow the last
+    // uploaded byte.  Bands are whole segments; a band's kernel needs HALO source rows below its last row.
+    const int nb = std::min(s->latency_bands, (int)jb->segs_y), S = jb->seg_rows;
+    int uploaded = 0;
+    sl.n_launches = 0;
+    for (int b = 0; b < nb; b++) {
+      const int seg_lo = b * jb->segs_y / nb, seg_hi = (b + 1) * jb->segs_y / nb;
+      const int r0 = seg_lo * S, r1 = std::min(seg_hi * S, H);
+      const int up_end = (b == nb - 1) ? H : std::min(r1 + HALO, H);
+      if ((st = upload_rows(uploaded, up_end))) return st;
+      uploaded = up_end;
+      CU_TRY(s, cudaEventRecord(sl.e_band_in[b], s->st_in));
+      CU_TRY(s, cudaStreamWaitEvent(s->st_k, sl.e_band_in[b], 0));
+      if (b == 0) CU_TRY(s, cudaEventRecord(sl.e_k0, s->st_k));
+      const int l = launch_frame_strips(sl.d_job, sl.h_job, 1, s->d_counters, s->st_k, seg_lo * jb->strips_x, seg_hi * jb->strips_x);
+      if (l < 0) { s->err = "launch_frame_strips failed"; return NES_ERR_CUDA; }
+      sl.n_launches += l;
+      s->launches += (uint64_t)l;
+      CU_TRY(s, cudaGetLastError());
+      CU_TRY(s, cudaEventRecord(sl.e_band_k[b], s->st_k));
+      CU_TRY(s, cudaStreamWaitEvent(s->st_out, sl.e_band_k[b], 0));
       for (int im = 0; im < nimg; im++) {
         uint8_t *const *pl = im ? out->depth : out->scene;
+        const int32_t *ls = im ? out->depth_linesize : out->scene_linesize;
         const PlaneLayout &L = im ? pd : ps;
-        for (int p = 0; p < (jb->nv12 ? 2 : 3); p++) sl.staged.push_back(StagedCopy{pl[p], sl.h_out + L.off[p], L.bytes[p]});
+        for (int p = 0; p < nplanes; p++) {
+          const size_t y0 = p ? r0 / 2 : r0, y1 = p ? r1 / 2 : r1;
+          CU_TRY(s, cudaMemcpyAsync(pl[p] + y0 * ls[p], sl.d_out + L.off[p] + y0 * ls[p], (y1 - y0) * ls[p], cudaMemcpyDeviceToHost, s->st_out));
+        }
+      }
+    }
+    CU_TRY(s, cudaEventRecord(sl.e_in, s->st_in));
+    CU_TRY(s, cudaEventRecord(sl.e_k1, s->st_k));
+  } else {
+    if (pinned_upload && (st = upload_rows(0, H))) return st;
+    CU_TRY(s, cudaEventRecord(sl.e_in, s->st_in));
+
+    // ---- kernels ----
+    CU_TRY(s, cudaStreamWaitEvent(s->st_k, sl.e_in, 0));
+    CU_TRY(s, cudaEventRecord(sl.e_k0, s->st_k));
+    sl.n_launches = run_kernels(s, sl.d_job, sl.h_job, 1, s->st_k);
+    CU_TRY(s, cudaGetLastError());
+    CU_TRY(s, cudaEventRecord(sl.e_k1, s->st_k));
+
+    // ---- download ----
+    CU_TRY(s, cudaStreamWaitEvent(s->st_out, sl.e_k1, 0));
+    if (out->mem == NES_MEM_HOST) {
+      const size_t total = pd.off[0] + (want_depth ? pd.total : 0);
+      if (direct) {
+        CU_TRY(s, cudaMemcpyAsync(out->scene[0], sl.d_out + ps.off[0], ps.total, cudaMemcpyDeviceToHost, s->st_out));
+        if (want_depth) CU_TRY(s, cudaMemcpyAsync(out->depth[0], sl.d_out + pd.off[0], pd.total, cudaMemcpyDeviceToHost, s->st_out));
+      } else {
+        if ((st = ensure_host(s, &sl.h_out, &sl.h_out_cap, total))) return st;
+        CU_TRY(s, cudaMemcpyAsync(sl.h_out, sl.d_out, total, cudaMemcpyDeviceToHost, s->st_out));
+        for (int im = 0; im < nimg; im++) {
+          uint8_t *const *pl = im ? out->depth : out->scene;
+          const PlaneLayout &L = im ? pd : ps;
+          for (int p = 0; p < nplanes; p++) sl.staged.push_back(StagedCopy{pl[p], sl.h_out + L.off[p], L.bytes[p]});
+        }
       }
     }
   }

@@ -671,3 +671,44 @@ def test_two_sessions_two_threads(N, O, port, glyphs):
     for t in ths:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("bands", [2, 4, 8])
+def test_latency_bands(N, O, port, glyphs, bands):
+    """Low-latency mode: the frame goes up, through the kernel and down in row bands; same bytes out,
+    `bands` launches per frame; composites, text crossing band borders, NV12, and a frame too small to split."""
+    s = N.Session(device=0, max_width=1920, max_height=1080, max_sources=2)
+    try:
+        s.atlas_set(glyphs.metrics, glyphs.bitmaps)
+        s.set_latency_bands(bands)
+        rng = np.random.default_rng(bands)
+        for fmt, n, w, h, out_fmt in [("rgb24", 1, 1280, 720, "yuv420p"), ("rgba", 2, 1920, 1080, "yuv420p"), ("rgb24", 1, 640, 360, "nv12"), ("rgb24", 1, 64, 32, "yuv420p")]:
+            if n == 1:
+                img = rng.integers(0, 256, (h, w, N.PIX_BPP[fmt]), dtype=np.uint8)
+                dep = rng.integers(0, 256, (h, w), dtype=np.uint8)
+                srcs, comp, cdep = [(img, dep)], img, dep
+            else:
+                srcs, rgbs, deps = _rgba_sources(O, rng, n, w, h, fmt)
+                comp, cdep = port.composite(rgbs, deps, fmt)
+            text = b"\n".join(bytes((40 + (i * 5 + j) % 80) for i in range(w // 24)) for j in range(h // 22))
+            runs = [(O.POS_LEFT_TOP, text)]
+            surf = np.ascontiguousarray(comp.copy())
+            (port.render_string if surf.shape[2] == 3 else (lambda a, p, t, g: port.render_string4(a, p, t, g, fmt)))(surf, O.POS_LEFT_TOP, text, glyphs)
+            ws, wd_ = port.rgb_to_yuv420p(surf, fmt), port.gray_to_yuv420p(np.ascontiguousarray(cdep))
+            want_s, want_d = (_nv12(ws), _nv12(wd_)) if out_fmt == "nv12" else (ws.cropped(), wd_.cropped())
+            scene, depth = N.FrameManager(N.FrameContext(w, h, out_fmt), session=s), N.FrameManager(N.FrameContext(w, h, out_fmt), session=s)
+            sources = []
+            for a, d in srcs:
+                ha, hd_ = s.host_array(a.nbytes), s.host_array(d.nbytes)
+                ha[:] = np.ascontiguousarray(a).reshape(-1); hd_[:] = np.ascontiguousarray(d).reshape(-1)
+                sources.append((ha, hd_, 0, 0))
+            fin = N.Session.frame_in(fmt, w, h, sources)
+            before = s.launches
+            s.convert(fin, runs, N.api._frame_out(scene, depth))
+            assert scene.cropped() == want_s, (fmt, n, w, h, first_diff(scene.cropped(), want_s))
+            assert depth.cropped() == want_d, (fmt, n, w, h, first_diff(depth.cropped(), want_d))
+            assert 1 <= s.launches - before <= bands
+            if h >= 360:
+                assert s.launches - before == bands
+    finally:
+        s.close()
