@@ -712,3 +712,51 @@ def test_latency_bands(N, O, port, glyphs, bands):
                 assert s.launches - before == bands
     finally:
         s.close()
+
+
+@pytest.mark.parametrize("fmt,n,w,h", [("rgb24", 1, 272, 36), ("rgb24", 1, 528, 14), ("rgba", 2, 272, 50), ("rgba", 1, 1936, 62), ("rgb24", 1, 4112, 34),
+                                       ("bgra", 3, 784, 12), ("rgb24", 1, 16, 16), ("rgba", 4, 48, 132)])
+def test_tma_path_ragged_strips_and_short_frames(N, O, port, session, fmt, n, w, h):
+    """Widths that are multiples of 16 (rows staged by TMA) but leave a last strip of 16..240 pixels
+    (generic store path, zero-filled box columns), frames of 12..16 rows (a single chunk with rows
+    above and below the frame), and frames taller than wide."""
+    rng = np.random.default_rng(w * 3 + h)
+    if n == 1:
+        img = rng.integers(0, 256, (h, w, N.PIX_BPP[fmt]), dtype=np.uint8)
+        dep = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        srcs, comp, cdep = [(img, dep)], img, dep
+    else:
+        srcs, rgbs, deps = _rgba_sources(O, rng, n, w, h, fmt)
+        comp, cdep = port.composite(rgbs, deps, fmt)
+    sc, dp = run_gpu(N, session, fmt, srcs, w, h, pinned=True)
+    want_s, want_d = port.rgb_to_yuv420p(np.ascontiguousarray(comp), fmt).cropped(), port.gray_to_yuv420p(np.ascontiguousarray(cdep)).cropped()
+    assert sc.cropped() == want_s, first_diff(sc.cropped(), want_s)
+    assert dp.cropped() == want_d, first_diff(dp.cropped(), want_d)
+
+
+def test_strided_device_sources(N, O, port, session):
+    """Device-resident sources whose row stride is wider than the row (a renderer writing into a padded
+    surface): the tensor maps carry the stride; also an odd byte offset (falls back to the non-TMA path)."""
+    w, h = 640, 96
+    rng = np.random.default_rng(9)
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    dep = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    want_s, want_d = port.rgb_to_yuv420p(rgb, "rgb24").cropped(), port.gray_to_yuv420p(dep).cropped()
+    for rs, ds, off in [(w * 3 + 64, w + 32, 0), (w * 3 + 16, w + 16, 0), (w * 3 + 64, w + 32, 1)]:
+        big = np.zeros((h, rs), np.uint8); big[:, : w * 3] = rgb.reshape(h, -1)
+        bigd = np.zeros((h, ds), np.uint8); bigd[:, :w] = dep
+        d_rgb, d_dep = session.device_alloc(big.nbytes + 16), session.device_alloc(bigd.nbytes + 16)
+        session.h2d(d_rgb + off, big); session.h2d(d_dep + off, bigd)
+        ysz, csz = N.align32(w) * h, N.align32(w // 2) * (h // 2)
+        d_s, d_d = session.device_alloc(ysz + 2 * csz), session.device_alloc(ysz + 2 * csz)
+        fin = N.Session.frame_in("rgb24", w, h, [((d_rgb + off, big.nbytes), (d_dep + off, bigd.nbytes), rs, ds)], mem=N.NES_MEM_DEVICE)
+        fo = N.nes_frame_out(); fo.width, fo.height, fo.mem = w, h, N.NES_MEM_DEVICE
+        for p, (o, ls) in enumerate([(0, N.align32(w)), (ysz, N.align32(w // 2)), (ysz + csz, N.align32(w // 2))]):
+            fo.scene[p], fo.scene_linesize[p], fo.depth[p], fo.depth_linesize[p] = d_s + o, ls, d_d + o, ls
+        session.convert_batch_device([fin], None, [fo], sync=True)
+        sc, dp = N.FrameManager(N.FrameContext(w, h, "yuv420p")), N.FrameManager(N.FrameContext(w, h, "yuv420p"))
+        session.d2h(sc.buffer, d_s); session.d2h(dp.buffer, d_d)
+        assert sc.cropped() == want_s, (rs, ds, off, first_diff(sc.cropped(), want_s))
+        assert dp.cropped() == want_d, (rs, ds, off)
+        for p in (d_rgb, d_dep, d_s, d_d):
+            session.device_free(p)
