@@ -11,7 +11,7 @@
 // Shape of the kernel (HBM-bound u8/int32 streaming work, no tensor cores):
 //   * work unit = one SEGMENT (seg_rows output rows) of one 256-pixel column STRIP of one
 //     frame; persistent CTAs fetch units from a global counter;
-//   * a CTA walks its segment top to bottom in CHUNKS of 16 source rows;
+//   * a CTA walks its segment top to bottom in CHUNKS of 16 source rows (32 for 3-byte pixels);
 //   * source rows travel through a ring of 8-row SUB-STAGES in shared memory.  Warp 8 is the
 //     PRODUCER: per sub-stage it issues one 2D tensor-map TMA copy per staged plane
 //     (cp.async.bulk.tensor -> SASS UTMALDG: the packed pixels of every source and their GRAY8
@@ -49,6 +49,18 @@ namespace {
 enum { MODE_ROWS = 0, MODE_SELECT = 1, MODE_MATERIALIZED = 2 };
 
 constexpr int DEP_ROWB = STRIP_W;  // bytes of a staged depth row
+// Source rows per compute chunk, per pixel-size class.  32 rows halve the per-chunk bookkeeping but the
+// chroma ring (RING_ROWS = 40) then needs a second consumer barrier per chunk (phase A of the next chunk
+// would overwrite rows phase B still reads).
+#ifndef NES_CHUNK_ROWS_BPP3
+#define NES_CHUNK_ROWS_BPP3 32  // measured: 4K 0.60 -> 0.64 of HBM peak against 16
+#endif
+template <int BPP>
+struct Geo {
+  static constexpr int CH = BPP == 3 ? NES_CHUNK_ROWS_BPP3 : CHUNK_ROWS;
+  static constexpr int NSUB = CH / SUB_ROWS;
+  static constexpr bool SECOND_BARRIER = 2 * CH + 6 > RING_ROWS;
+};
 // The chroma ring has RING_ROWS logical slots; slots [0, RING_MIRROR) are written twice (also
 // RING_ROWS rows further) so that the 8 consecutive rows a vertical tap window reads never wrap.
 constexpr int RING_MIRROR = 8;
@@ -301,9 +313,9 @@ __device__ __forceinline__ void select_staged(uint32_t px, uint32_t dep, int n_s
 // Glyph stamp into the staged rows of source 0 (consumer warps only).  Reference semantics
 // (render_text.cc:94-106): every bitmap pixel with coverage != 0 inside the frame becomes
 // (255,255,255).  All stamps write the same value: overlapping glyphs are order-free.
-// Chunk-local row r lives in sub-stage r / 8 (generic pointers sub0 / sub1), row r % 8.
+// Chunk-local row r lives in the (r / 8)-th sub-stage of the chunk, row r % 8.
 template <int BPP>
-__device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *sub0, uint8_t *sub1, int x0, int x1, int yc0, int ra, int rb,
+__device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *stage0, int qc, int ns, int slot_bytes, int x0, int x1, int yc0, int ra, int rb,
                                             int rgb_base, int *s_hits, int *s_nhits) {
   constexpr int ROWB = STRIP_W * BPP;
   constexpr int NT = 32 * CONSUMER_WARPS;
@@ -324,7 +336,9 @@ __device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *sub0, uin
       const int p0 = max(0, x0 - pg.x), p1 = min(pg.w, x1 - pg.x);
       for (int q = q0; q < q1; q++) {
         const int r = pg.y + q - yc0;
-        uint8_t *row = (r < SUB_ROWS ? sub0 : sub1) + (r & (SUB_ROWS - 1)) * ROWB;
+        int qq = qc + (r >> 3);  // chunk-local row r lives in sub-stage r / 8 after the chunk's first one (the ring may wrap)
+        if (qq >= ns) qq -= ns;
+        uint8_t *row = stage0 + qq * slot_bytes + (r & (SUB_ROWS - 1)) * ROWB;
         for (int p = p0 + lane; p < p1; p += 32)
           if (cov[q * pg.pitch + p]) {
             uint8_t *px = row + (pg.x + p - x0) * BPP + (BPP == 4 ? rgb_base : 0);
@@ -347,6 +361,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
   constexpr int RING_ROWB = L::RING_ROWB;
   constexpr int CLS = BPP - 3;
   constexpr int NW = CONSUMER_WARPS;
+  using G = Geo<BPP>;
   uint64_t *s_full = (uint64_t *)(smem + L::OFF_BAR);  // [NS_MAX]
   uint64_t *s_empty = s_full + NS_MAX;                  // [NS_MAX]
   int *s_hits = (int *)(smem + L::OFF_HITS);
@@ -381,7 +396,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
       const int x0 = strip * STRIP_W, tw = min(STRIP_W, W - x0);
       const int Y0 = seg * S, Y1 = min(Y0 + S, H);
       const int L0 = Y0 - HALO, need_end = min(Y1 + HALO, H);
-      const int nchunks = (need_end - L0 + CHUNK_ROWS - 1) / CHUNK_ROWS;
+      const int nchunks = (need_end - L0 + G::CH - 1) / G::CH;
       const int tma = jp->tma_ok;
       const int n_staged = tma ? n_src : 1;
       const int dep_staged = (jp->dy != nullptr) || n_src > 1;
@@ -401,8 +416,8 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
         }
       }
       for (int k = 0; k < nchunks; k++, chunk_it++) {
-        const int yc0 = L0 + k * CHUNK_ROWS;
-        const int ra = max(yc0, 0), rb = min(yc0 + CHUNK_ROWS, need_end);
+        const int yc0 = L0 + k * G::CH;
+        const int ra = max(yc0, 0), rb = min(yc0 + G::CH, need_end);
         const bool last_k = (k == nchunks - 1);
         if (lane == 0) {
           // the context slot was last used NCTX chunks ago; the consumers are at most
@@ -426,8 +441,8 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
           c.n_src = n_src; c.job = j; c.n_staged = n_staged;
           c.x0 = x0; c.tw = tw; c.yc0 = yc0; c.ra = ra; c.rb = rb;
           c.ya = max(ra, Y0); c.yb = min(rb, Y1);
-          const int cA = (k == 0) ? (Y0 >> 1) : (Y0 >> 1) + ((k * CHUNK_ROWS) >> 1) - 3;
-          const int cB = last_k ? (Y1 >> 1) : (Y0 >> 1) + (((k + 1) * CHUNK_ROWS) >> 1) - 3;
+          const int cA = (k == 0) ? (Y0 >> 1) : (Y0 >> 1) + ((k * G::CH) >> 1) - 3;
+          const int cB = last_k ? (Y1 >> 1) : (Y0 >> 1) + (((k + 1) * G::CH) >> 1) - 3;
           c.cA = cA; c.cB = cB; c.H = H;
           c.edge = (2 * cA - 3 < 0) || (2 * (cB - 1) + 4 > H - 1);
           c.rbase = rbase;
@@ -456,7 +471,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
         }
         __syncwarp();
 #pragma unroll 1
-        for (int sub = 0; sub < CHUNK_ROWS / SUB_ROWS; sub++) {
+        for (int sub = 0; sub < G::NSUB; sub++) {
           if (!round0) mbar_wait(&s_empty[q], (uint32_t)(par ^ 1));
           const int ys = yc0 + sub * SUB_ROWS;
           const bool wanted = tma && ys < rb && ys + SUB_ROWS > ra;  // else nothing of this sub-stage is read
@@ -469,7 +484,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
           }
           if (++q == ns) { q = 0; par ^= 1; round0 = 0; }
         }
-        rbase += CHUNK_ROWS;
+        rbase += G::CH;
         if (rbase >= RING_ROWS) rbase -= RING_ROWS;
       }
       cur_u = next_u;
@@ -487,16 +502,23 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
   // ============================= consumer warps ===========================================
   const uint32_t ring0 = smem_base + L::OFF_RING;
   const uint32_t full0 = smem_base + L::OFF_BAR, empty0 = full0 + NS_MAX * 8;
-  int q0 = 0, par0 = 0;  // sub-stage cursor of the chunk's first sub-stage: slot, parity of its use count
+  int qc = 0, parc = 0;  // sub-stage cursor of the chunk's first sub-stage: slot, parity of its use count
   for (int chunk_it = 0;; chunk_it++) {
-    // the second sub-stage of this chunk (the ring may wrap between the two)
-    int q1 = q0 + 1, par1 = par0;
-    if (q1 == ns) { q1 = 0; par1 ^= 1; }
-    mbar_wait_a(full0 + q0 * 8, (uint32_t)par0);
+    // the chunk's sub-stages (the ring may wrap between them)
+    int q[G::NSUB], par[G::NSUB];
+    q[0] = qc; par[0] = parc;
+#pragma unroll
+    for (int i = 1; i < G::NSUB; i++) {
+      q[i] = q[i - 1] + 1; par[i] = par[i - 1];
+      if (q[i] == ns) { q[i] = 0; par[i] ^= 1; }
+    }
+    mbar_wait_a(full0 + q[0] * 8, (uint32_t)par[0]);
     const ChunkCtx &c = *(const ChunkCtx *)(smem + L::OFF_CTX + (chunk_it & (NCTX - 1)) * L::CTX_BYTES);
     const int last = c.last;
     {
-      const uint32_t sb[2] = {smem_base + L::OFF_STAGE + (uint32_t)(q0 * slot_bytes), smem_base + L::OFF_STAGE + (uint32_t)(q1 * slot_bytes)};
+      uint32_t sb[G::NSUB];
+#pragma unroll
+      for (int i = 0; i < G::NSUB; i++) sb[i] = smem_base + L::OFF_STAGE + (uint32_t)(q[i] * slot_bytes);
       const uint32_t dep_off = (uint32_t)(c.n_staged * SUB_ROWS) * ROWB;
       const int x0 = c.x0, tw = c.tw, yc0 = c.yc0, ra = c.ra, rb = c.rb, ya = c.ya, yb = c.yb;
       const int n_src = c.n_src;
@@ -507,17 +529,17 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
       const int dys = c.dys;
 
       if (!c.tma || mode == MODE_MATERIALIZED || c.stamp) {
-        // whole-chunk work on the staged rows: needs both sub-stages
-        mbar_wait_a(full0 + q1 * 8, (uint32_t)par1);
-        uint8_t *const g[2] = {smem + L::OFF_STAGE + q0 * slot_bytes, smem + L::OFF_STAGE + q1 * slot_bytes};
+        // whole-chunk work on the staged rows: needs all of its sub-stages
+#pragma unroll
+        for (int i = 1; i < G::NSUB; i++) mbar_wait_a(full0 + q[i] * 8, (uint32_t)par[i]);
         // ---- fill our rows ourselves when they were not staged by TMA ------------------------
         if (!c.tma) {
           const DevJob &jb = jobs[c.job];
-#pragma unroll 1
-          for (int i = 0; i < CHUNK_ROWS / SUB_ROWS; i++) {
+#pragma unroll
+          for (int i = 0; i < G::NSUB; i++) {
             const int y = yc0 + warp + i * SUB_ROWS;
             if (y < ra || y >= rb) continue;
-            uint8_t *const gi = i ? g[1] : g[0];
+            uint8_t *const gi = smem + L::OFF_STAGE + q[i] * slot_bytes;
             uint8_t *sp = gi + warp * ROWB;
             uint8_t *sd = gi + SUB_ROWS * ROWB + warp * DEP_ROWB;
             if (n_src == 1) {
@@ -539,11 +561,11 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
         }
         // ---- staged composite under text: materialise the select into source 0's rows ----------
         if (BPP == 4 && mode == MODE_MATERIALIZED) {
-#pragma unroll 1
-          for (int i = 0; i < CHUNK_ROWS / SUB_ROWS; i++) {
+#pragma unroll
+          for (int i = 0; i < G::NSUB; i++) {
             const int y = yc0 + warp + i * SUB_ROWS;
             if (y < ra || y >= rb) continue;
-            const uint32_t sbi = i ? sb[1] : sb[0];
+            const uint32_t sbi = sb[i];
             const uint32_t px = sbi + warp * ROWB;
             const uint32_t dp = sbi + dep_off + warp * DEP_ROWB;
             uint32_t p[8], d4[2];
@@ -558,7 +580,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
         }
         __syncwarp();
         // ---- text overlay, stamped into the staged rows of source 0 ----------------------------
-        if (c.stamp) stamp_chunk<BPP>(jobs[c.job], g[0], g[1], x0, x0 + tw, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
+        if (c.stamp) stamp_chunk<BPP>(jobs[c.job], smem + L::OFF_STAGE, qc, ns, slot_bytes, x0, x0 + tw, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
         fence_proxy_async();  // our generic-proxy writes to the stage come before the TMA refill
       }
 
@@ -568,10 +590,10 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
         const int sys = c.sys;
         const int rbase = c.rbase;
 #pragma unroll
-        for (int i = 0; i < CHUNK_ROWS / SUB_ROWS; i++) {
+        for (int i = 0; i < G::NSUB; i++) {
           const int r = warp + i * SUB_ROWS;
           const int y = yc0 + r;
-          if (i == 1) mbar_wait_a(full0 + q1 * 8, (uint32_t)par1);
+          if (i >= 1) mbar_wait_a(full0 + q[i] * 8, (uint32_t)par[i]);
           if (y >= ra && y < rb) {
             const uint32_t row = sb[i] + warp * ROWB;
             const uint32_t drow = sb[i] + dep_off + warp * DEP_ROWB;
@@ -677,7 +699,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
           }
           // this warp is done with its row of the sub-stage: release it to the producer
           __syncwarp();
-          if (lane == 0) mbar_arrive_a(empty0 + (i ? q1 : q0) * 8);
+          if (lane == 0) mbar_arrive_a(empty0 + q[i] * 8);
         }
       }
       consumer_sync();
@@ -723,8 +745,9 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
           for (int ci = cA + warp; ci < cB; ci += NW) {
             uint32_t t[8][4];
             if (!edge) {
-              int s0 = rbase + (2 * ci - 3 - yc0);  // in [rbase - 6, rbase + 8]: rows s0..s0+7 <= 47 never wrap (mirror)
+              int s0 = rbase + (2 * ci - 3 - yc0);  // >= rbase - 6; after the wrap s0 is in [0, RING_ROWS]: rows s0..s0+7 <= 47 (mirror)
               if (s0 < 0) s0 += RING_ROWS;
+              if (s0 > RING_ROWS) s0 -= RING_ROWS;
               const uint32_t base = col + (uint32_t)(s0 * RING_ROWB);
 #pragma unroll
               for (int j = 0; j < 8; j++) {
@@ -784,8 +807,9 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
       }
     }
     if (last) break;
-    q0 = q1 + 1; par0 = par1;
-    if (q0 == ns) { q0 = 0; par0 ^= 1; }
+    if (G::SECOND_BARRIER) consumer_sync();  // phase A of the next chunk reuses ring rows phase B was reading
+    qc = q[G::NSUB - 1] + 1; parc = par[G::NSUB - 1];
+    if (qc == ns) { qc = 0; parc ^= 1; }
   }
 }
 
@@ -830,7 +854,7 @@ static StripsConfig strips_config(int cls, int staged) {
     if (g_force_ctas && ctas > g_force_ctas) continue;
     const int budget = smem_sm / ctas - g_smem_reserved - off;
     const int ns = std::min(NS_MAX, budget / slot);
-    if (ns >= 2) { c.ns = ns; c.ctas = ctas; c.smem = off + ns * slot; break; }
+    if (ns >= std::max(2, cls == 0 ? Geo<3>::NSUB : Geo<4>::NSUB)) { c.ns = ns; c.ctas = ctas; c.smem = off + ns * slot; break; }
   }
   return c;
 }
@@ -852,9 +876,10 @@ void plan_frame_strips(DevJob *jobs, int n_jobs) {
   launch_staged(jobs, n_jobs, staged);
   for (int cls = 0; cls < 2; cls++) {
     const int grid = sms * std::max(1, strips_config(cls, staged[cls]).ctas);
-    int best_s = CHUNK_ROWS * 2 - 2 * HALO;
+    const int ch = cls == 0 ? Geo<3>::CH : Geo<4>::CH;
+    int best_s = std::max(ch, 32) - 2 * HALO;
     double best_cost = 1e30;
-    for (int S = CHUNK_ROWS * 2 - 2 * HALO; S <= 256; S += CHUNK_ROWS) {
+    for (int S = std::max(ch, 32) - 2 * HALO; S <= 256; S += ch) {
       double work = 0;
       long units = 0;
       for (int j = 0; j < n_jobs; j++) {
