@@ -338,11 +338,13 @@ __device__ __forceinline__ void stage_vtab(const DevFilter &f, int d0y, int n_ro
 }  // namespace
 
 template <int BPP>
-__global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__restrict__ jobs, int n_jobs, int smem_cap) {
+__global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__restrict__ jobs, int n_jobs, const RsLayout L) {
   extern __shared__ __align__(16) uint8_t smem[];
   int tile;
   const DevJob *jp = find_job(jobs, n_jobs, blockIdx.x, &tile);
-  if (!jp->general || jp->bpp != BPP) return;
+  // a launch serves the jobs of one pixel class that share one shared-memory carve-up (kernel parameter:
+  // constant-bank operands; derived per tile in registers it cost 6 % of the kernel's instructions)
+  if (!jp->general || jp->bpp != BPP || jp->rs_lay.total != L.total || jp->rs_lay.vtab != L.vtab || jp->rs_lay.hy != L.hy || jp->rs_lay.dep != L.dep) return;
   const DevJob &jb = *jp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARP = RS_THREADS / 32;
@@ -370,9 +372,6 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
   t.cww = half ? t.ww >> 1 : t.ww;
   const int nl = t.lr1 - t.lr0, nc = t.cr1 - t.cr0;
 
-  // shared memory carve-up (rs_layout is shared with the host's sizing code; the host sizes the
-  // allocation for the largest tile, jb.rs_lay)
-  const RsLayout L = rs_layout(t.wh, t.ww, t.cww, nl, nc, t.dwp, t.dcwp, t.dh, t.dch, jb.vl.size, jb.vc.size, HIT_CAP);
   int16_t *s_y14 = (int16_t *)(smem + L.y14);  // [wh][ww]
   int16_t *s_u14 = (int16_t *)(smem + L.u14);  // [wh][cww]
   int16_t *s_v14 = (int16_t *)(smem + L.v14);
@@ -381,7 +380,6 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
   uint32_t *s_mask = (uint32_t *)(smem + L.mask);  // [wh][mw] overlay bits
   int *s_hits = (int *)(smem + L.hits);
   int *s_nhits = s_hits + HIT_CAP;
-  if (L.total > smem_cap) { __trap(); }
 
   if (tid < jb.n_src) {
     SrcDesc *sdw = (SrcDesc *)(smem + L.src);
@@ -571,21 +569,26 @@ int kernels_init() {
 }
 
 int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream) {
-  int total = 0, smem[2] = {0, 0};
-  bool any[2] = {false, false};
+  int total = 0;
+  for (int j = 0; j < n_jobs; j++) total = jobs_host[j].tile_base + jobs_host[j].tiles_x * jobs_host[j].tiles_y;
+  if (total == 0) return 0;
+  // one launch per (pixel class, carve-up): CTAs of other jobs return at once.  A batch normally holds one
+  // size pair, i.e. one launch.
+  int launches = 0;
   for (int j = 0; j < n_jobs; j++) {
     const DevJob &jb = jobs_host[j];
-    total = jb.tile_base + jb.tiles_x * jb.tiles_y;
-    if (jb.general) { any[jb.bpp - 3] = true; smem[jb.bpp - 3] = jb.rs_smem > smem[jb.bpp - 3] ? jb.rs_smem : smem[jb.bpp - 3]; }
-  }
-  if (total == 0) return 0;
-  int launches = 0;
-  for (int cls = 0; cls < 2; cls++) {
-    if (!any[cls]) continue;
-    const int sm = (smem[cls] + 1023) & ~1023;
+    if (!jb.general) continue;
+    bool seen = false;
+    for (int i = 0; i < j && !seen; i++) {
+      const DevJob &o = jobs_host[i];
+      seen = o.general && o.bpp == jb.bpp && o.rs_lay.total == jb.rs_lay.total && o.rs_lay.vtab == jb.rs_lay.vtab && o.rs_lay.hy == jb.rs_lay.hy &&
+             o.rs_lay.dep == jb.rs_lay.dep;
+    }
+    if (seen) continue;
+    const int sm = (jb.rs_lay.total + 1023) & ~1023;
     if (sm > g_resize_smem_cap) return -1;
-    if (cls == 0) k_resize_tiles<3><<<total, RS_THREADS, sm, (cudaStream_t)stream>>>(jobs_dev, n_jobs, sm);
-    else k_resize_tiles<4><<<total, RS_THREADS, sm, (cudaStream_t)stream>>>(jobs_dev, n_jobs, sm);
+    if (jb.bpp == 3) k_resize_tiles<3><<<total, RS_THREADS, sm, (cudaStream_t)stream>>>(jobs_dev, n_jobs, jb.rs_lay);
+    else k_resize_tiles<4><<<total, RS_THREADS, sm, (cudaStream_t)stream>>>(jobs_dev, n_jobs, jb.rs_lay);
     launches++;
   }
   return launches;
