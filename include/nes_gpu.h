@@ -53,7 +53,7 @@ extern "C" {
 #define NES_API
 #endif
 
-#define NES_ABI_VERSION 1
+#define NES_ABI_VERSION 2
 #define NES_MAX_SOURCES 8
 
 typedef enum nes_status {
@@ -121,11 +121,17 @@ typedef struct nes_glyph {
   const uint8_t *coverage; /* rows * pitch bytes, 8-bit coverage                      */
 } nes_glyph;
 
-/* One render_string_to_frame(frame, position, content) call (render_text.h:27-29) */
+/* One render_string_to_frame(frame, position, content) call (render_text.h:27-29).
+ * view_*: the sub-rectangle of the source frame that plays the role of the reference's
+ * `frame` for this call -- pen placement uses view_w x view_h, the stamp is clipped to the
+ * view (render_text.cc:98 clips to the frame it was given).  view_w == 0 (the default of a
+ * zero-initialised struct) means the whole frame.  A side-by-side stereo frame
+ * (BASELINE config 3) gives each eye its own set of runs: views (0,0,W/2,H) and (W/2,0,W/2,H). */
 typedef struct nes_text_run {
   int32_t position; /* nes_text_pos                                                   */
   int32_t len;      /* bytes in text                                                  */
   const char *text; /* not NUL-terminated necessarily; '\n' starts a new line (+20 px) */
+  int32_t view_x, view_y, view_w, view_h;
 } nes_text_run;
 
 /* One renderer's output for this frame (nes.proto:18-25 fields frame, depth). */
@@ -249,6 +255,17 @@ NES_API int nes_gpu_convert(nes_gpu_session *s, const nes_frame_in *in, const ne
 NES_API int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_frame_in *in,
                                          const nes_text_run *const *runs, const int *n_runs,
                                          const nes_frame_out *out, int sync);
+/* The same split in two: nes_gpu_batch_prepare validates the frames, lays out the text and leaves the descriptor
+ * table resident on the device; nes_gpu_batch_run is then only the kernel launches (a stable set of device-resident
+ * frames -- a ring of session buffers -- is converted again and again without per-frame host work, and consecutive
+ * runs overlap on the device: the next launch fills the SMs the previous one drains).  The frames' pointers, sizes
+ * and text are those given at prepare time.  Free with nes_gpu_batch_free before destroying the session. */
+typedef struct nes_gpu_batch nes_gpu_batch;
+NES_API int nes_gpu_batch_prepare(nes_gpu_session *s, int n_frames, const nes_frame_in *in,
+                                  const nes_text_run *const *runs, const int *n_runs,
+                                  const nes_frame_out *out, nes_gpu_batch **batch);
+NES_API int nes_gpu_batch_run(nes_gpu_session *s, nes_gpu_batch *batch, int sync);
+NES_API void nes_gpu_batch_free(nes_gpu_session *s, nes_gpu_batch *batch);
 NES_API int nes_gpu_last_timing(nes_gpu_session *s, nes_timing *t);
 
 /* ---- host-side pieces, exported so they can be checked without a GPU ------ */
@@ -266,6 +283,7 @@ typedef struct nes_placed_glyph {
   int32_t x, y;   /* frame position of bitmap pixel (0,0)                             */
   int32_t code;   /* index into the atlas                                             */
   int32_t reserved;
+  int32_t clip_x, clip_y, clip_w, clip_h; /* part of the bitmap inside the run's view (bitmap coordinates) */
 } nes_placed_glyph;
 NES_API int nes_gpu_text_layout(nes_gpu_session *s, int frame_w, int frame_h, const nes_text_run *run,
                                 nes_placed_glyph *out, int cap);

@@ -23,7 +23,7 @@ import sysconfig
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnes_gpu.so")
+LIB_PATH = os.environ.get("NES_GPU_LIB") or os.path.join(HERE, "libnes_gpu.so")  # NES_GPU_LIB: diagnostic builds of the same library
 
 NES_MAX_SOURCES = 8
 NES_MEM_HOST, NES_MEM_DEVICE = 0, 1
@@ -55,7 +55,8 @@ class nes_glyph(C.Structure):
 
 
 class nes_text_run(C.Structure):
-    _fields_ = [("position", C.c_int32), ("len", C.c_int32), ("text", C.c_char_p)]
+    _fields_ = [("position", C.c_int32), ("len", C.c_int32), ("text", C.c_char_p),
+                ("view_x", C.c_int32), ("view_y", C.c_int32), ("view_w", C.c_int32), ("view_h", C.c_int32)]
 
 
 class nes_source(C.Structure):
@@ -77,7 +78,8 @@ class nes_timing(C.Structure):
 
 
 class nes_placed_glyph(C.Structure):
-    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("code", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("code", C.c_int32), ("reserved", C.c_int32),
+                ("clip_x", C.c_int32), ("clip_y", C.c_int32), ("clip_w", C.c_int32), ("clip_h", C.c_int32)]
 
 
 class nes_unpacked_frame(C.Structure):
@@ -93,6 +95,7 @@ ABI_SYMBOLS = [
     "nes_gpu_host_alloc", "nes_gpu_host_free", "nes_gpu_device_alloc", "nes_gpu_device_free",
     "nes_gpu_memcpy_h2d", "nes_gpu_memcpy_d2h", "nes_gpu_atlas_set", "nes_gpu_atlas_load_font",
     "nes_font_rasterise", "nes_gpu_submit", "nes_gpu_wait", "nes_gpu_convert", "nes_gpu_convert_batch_device", "nes_gpu_last_timing",
+    "nes_gpu_batch_prepare", "nes_gpu_batch_run", "nes_gpu_batch_free",
     "nes_gpu_filter_table", "nes_gpu_text_layout", "nes_unpack_rendered_frame",
     "nes_ingest_ring_create", "nes_ingest_ring_destroy", "nes_ingest_acquire", "nes_ingest_commit", "nes_ingest_release",
 ]
@@ -138,6 +141,10 @@ def lib() -> C.CDLL:
     L.nes_gpu_convert.argtypes = [vp, C.POINTER(nes_frame_in), C.POINTER(nes_text_run), i32, C.POINTER(nes_frame_out)]
     L.nes_gpu_convert_batch_device.argtypes = [vp, i32, C.POINTER(nes_frame_in), C.POINTER(C.POINTER(nes_text_run)), C.POINTER(i32), C.POINTER(nes_frame_out), i32]
     L.nes_gpu_last_timing.argtypes = [vp, C.POINTER(nes_timing)]
+    L.nes_gpu_batch_prepare.argtypes = [vp, i32, C.POINTER(nes_frame_in), C.POINTER(C.POINTER(nes_text_run)), C.POINTER(i32), C.POINTER(nes_frame_out), C.POINTER(vp)]
+    L.nes_gpu_batch_run.argtypes = [vp, vp, i32]
+    L.nes_gpu_batch_free.argtypes = [vp, vp]
+    L.nes_gpu_batch_free.restype = None
     L.nes_gpu_filter_table.argtypes = [i32, i32, i32, C.POINTER(C.c_int16), i32, C.POINTER(C.c_int32), i32]
     L.nes_gpu_text_layout.argtypes = [vp, i32, i32, C.POINTER(nes_text_run), C.POINTER(nes_placed_glyph), i32]
     L.nes_unpack_rendered_frame.argtypes = [vp, u64, i32, C.POINTER(nes_unpacked_frame)]
@@ -295,9 +302,14 @@ class Session:
         self._keep = {}
 
     def close(self):
+        """Destroys the session and frees the pinned buffers host_array() handed out (arrays obtained from
+        host_array must not be touched afterwards)."""
         if self.h:
             self.L.nes_gpu_session_destroy(self.h)
             self.h = C.c_void_p()
+            for p in self._keep.values():
+                self.L.nes_gpu_host_free(p)
+            self._keep.clear()
 
     def __del__(self):
         try:
@@ -365,8 +377,8 @@ class Session:
         ft = freetype_so or find_freetype()
         self._check(self.L.nes_gpu_atlas_load_font(self.h, ft.encode() if ft else None, font_path.encode()), "nes_gpu_atlas_load_font")
 
-    def text_layout(self, w: int, h: int, position: int, text: bytes):
-        run = nes_text_run(position, len(text), text)
+    def text_layout(self, w: int, h: int, position: int, text: bytes, view=(0, 0, 0, 0)):
+        run = nes_text_run(position, len(text), text, *view)
         cap = max(len(text), 1)
         out = (nes_placed_glyph * cap)()
         n = self.L.nes_gpu_text_layout(self.h, w, h, C.byref(run), out, cap)
@@ -377,11 +389,11 @@ class Session:
     # -- descriptors -------------------------------------------------------------
     @staticmethod
     def make_runs(runs):
-        """runs: [(position, bytes)] -> (ctypes array, n)"""
+        """runs: [(position, bytes)] or [(position, bytes, (view_x, view_y, view_w, view_h))] -> (ctypes array, n)"""
         n = len(runs or [])
         arr = (nes_text_run * max(n, 1))()
-        for i, (pos, txt) in enumerate(runs or []):
-            arr[i] = nes_text_run(pos, len(txt), txt)
+        for i, r in enumerate(runs or []):
+            arr[i] = nes_text_run(r[0], len(r[1]), r[1], *(r[2] if len(r) > 2 else (0, 0, 0, 0)))
         return arr, n
 
     @staticmethod
@@ -449,6 +461,21 @@ class Session:
         if r:
             self._check(r, "nes_gpu_convert_batch_device")
 
+    def batch_prepare(self, fins, runs_list, fouts):
+        """nes_gpu_batch_prepare: descriptor table of device-resident frames built + uploaded once -> handle."""
+        n, a_in, a_runs, a_n, a_out = self.prepare_batch(fins, runs_list, fouts)[:5]
+        h = C.c_void_p()
+        self._check(self.L.nes_gpu_batch_prepare(self.h, n, a_in, a_runs, a_n, a_out, C.byref(h)), "nes_gpu_batch_prepare")
+        return h
+
+    def batch_run(self, handle, sync: bool = False):
+        r = self.L.nes_gpu_batch_run(self.h, handle, 1 if sync else 0)
+        if r:
+            self._check(r, "nes_gpu_batch_run")
+
+    def batch_free(self, handle):
+        self.L.nes_gpu_batch_free(self.h, handle)
+
     def submit_prepared(self, fin, runs_made, fout) -> int:
         t = C.c_uint64()
         r = self.L.nes_gpu_submit(self.h, C.byref(fin), runs_made[0], runs_made[1], C.byref(fout), C.byref(t))
@@ -480,6 +507,7 @@ class FrameManager:
 
     def __init__(self, context: FrameContext, buffer: np.ndarray | None = None, session: Session | None = None):
         self.context = context
+        self._owner = session  # pinned planes live as long as the session that allocated them
         w, h = context.width, context.height
         self.text_runs = []  # overlays queued by RenderTextContext, applied on the device copy
         if context.pix_fmt == "yuv420p":

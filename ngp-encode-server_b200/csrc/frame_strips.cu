@@ -87,6 +87,9 @@ struct ChunkCtx {
   int32_t fullw;     // 16-byte aligned planes, strip width a multiple of 32: vector stores, lanes past the strip idle
   int32_t vec_out, rgb_base, dep_staged;
   int32_t nv12;      // chroma interleaved into one plane (su / du)
+#ifdef NES_TRACE
+  int32_t unit, k;   // work unit and chunk index inside it
+#endif
   uint32_t a_mask;   // alpha byte mask of a pixel word (composite validity)
   uint32_t ky[4], ku[3], kv[3];
   int32_t sys, sus, svs, dys, dus, dvs;
@@ -103,7 +106,7 @@ struct StripSmem {
   static constexpr int CTX_BYTES = ((int)sizeof(ChunkCtx) + 15) & ~15;
   static constexpr int OFF_BAR = OFF_CTX + NCTX * CTX_BYTES;
   static constexpr int OFF_HITS = OFF_BAR + 2 * NS_MAX * 8;
-  static constexpr int OFF_STAGE = (OFF_HITS + HIT_CAP * 4 + 16 + 1023) & ~1023;
+  static constexpr int OFF_STAGE = (OFF_HITS + STRIP_HITS * (int)sizeof(DevPlaced) + 16 + 1023) & ~1023;
   // bytes of one sub-stage holding n sources: 8 pixel rows + 8 depth rows per source
   static constexpr int slot_bytes(int n) { return n * SUB_ROWS * (ROWB + DEP_ROWB); }
 };
@@ -248,14 +251,13 @@ __device__ __forceinline__ void store8(uint8_t *row, int x, uint32_t w0, uint32_
 __device__ __forceinline__ void stg32(uint8_t *p, uint32_t w) { *(uint32_t *)p = w; }
 __device__ __forceinline__ void stg64(uint8_t *p, uint32_t w0, uint32_t w1) { *(uint2 *)p = make_uint2(w0, w1); }
 
-// Which job of this kernel's bpp class does work unit `u` belong to (unit_base is a prefix
-// sum over the batch in which the jobs of the other class take no units): the last job
-// whose base is <= u.
-__device__ __forceinline__ int job_of_unit(const DevJob *jobs, int n_jobs, int cls, int u) {
+// Which job of this kernel's bpp class does work unit `u` of numbering phase `ph` belong to (unit_base is a
+// prefix sum over the batch in which the jobs of the other class take no units): the last job whose base is <= u.
+__device__ __forceinline__ int job_of_unit(const DevJob *jobs, int n_jobs, int cls, int ph, int u) {
   int lo = 0, hi = n_jobs - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].unit_base[cls] <= u) lo = mid; else hi = mid - 1;
+    if (jobs[mid].unit_base[cls][ph] <= u) lo = mid; else hi = mid - 1;
   }
   return lo;
 }
@@ -314,36 +316,55 @@ __device__ __forceinline__ void select_staged(uint32_t px, uint32_t dep, int n_s
 // (render_text.cc:94-106): every bitmap pixel with coverage != 0 inside the frame becomes
 // (255,255,255).  All stamps write the same value: overlapping glyphs are order-free.
 // Chunk-local row r lives in the (r / 8)-th sub-stage of the chunk, row r % 8.
+// The glyph list is bucketed by row band on the host, so only the glyphs near the chunk's rows are tested
+// (one thread each); the descriptors that hit are staged in shared memory; then a warp takes a glyph and a
+// lane one of its rows: ONE load of the row's bit mask (1 bit per pixel, DevPlaced) and a loop over its set bits.
 template <int BPP>
 __device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *stage0, int qc, int ns, int slot_bytes, int x0, int x1, int yc0, int ra, int rb,
-                                            int rgb_base, int *s_hits, int *s_nhits) {
+                                            int rgb_base, DevPlaced *s_hits, int *s_nhits) {
   constexpr int ROWB = STRIP_W * BPP;
-  constexpr int NT = 32 * CONSUMER_WARPS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int base = 0; base < jb.n_glyphs; base += HIT_CAP) {
+  int g_begin = 0, g_end = jb.n_glyphs;
+  if (jb.glyph_band_shift >= 0) {
+    const int b0 = max(ra - jb.glyph_max_h, 0) >> jb.glyph_band_shift, b1 = (rb - 1) >> jb.glyph_band_shift;
+    g_begin = jb.glyph_band[b0]; g_end = jb.glyph_band[b1 + 1];
+  }
+  const DevPlaced *__restrict__ glyphs = jb.glyphs;
+  const uint32_t *__restrict__ atlas = jb.atlas;
+  for (int base = g_begin; base < g_end; base += STRIP_HITS) {
     if (tid == 0) *s_nhits = 0;
     consumer_sync();
-    for (int g = base + tid; g < min(base + HIT_CAP, jb.n_glyphs); g += NT) {
-      const DevPlaced pg = jb.glyphs[g];
-      if (pg.x < x1 && pg.x + pg.w > x0 && pg.y < rb && pg.y + pg.h > ra) s_hits[atomicAdd(s_nhits, 1)] = g;
+    if (tid < STRIP_HITS && base + tid < g_end) {
+      const DevPlaced pg = glyphs[base + tid];
+      if (pg.x < x1 && pg.x + pg.w > x0 && pg.y < rb && pg.y + pg.h > ra) s_hits[atomicAdd(s_nhits, 1)] = pg;
     }
     consumer_sync();
     const int nh = *s_nhits;
     for (int h = warp; h < nh; h += CONSUMER_WARPS) {
-      const DevPlaced pg = jb.glyphs[s_hits[h]];
-      const uint8_t *cov = jb.atlas + pg.atlas_off;
-      const int q0 = max(0, ra - pg.y), q1 = min(pg.h, rb - pg.y);
-      const int p0 = max(0, x0 - pg.x), p1 = min(pg.w, x1 - pg.x);
-      for (int q = q0; q < q1; q++) {
+      const DevPlaced pg = s_hits[h];
+      const int q0 = max(0, ra - pg.y), q1 = min(pg.h, rb - pg.y);   // visible rows inside the chunk
+      const int p0 = max(0, x0 - pg.x), p1 = min(pg.w, x1 - pg.x);   // visible columns inside the strip
+      const int bit_lo = pg.bit0 + p0, bit_hi = pg.bit0 + p1;        // bit range of a row's mask
+      const int w_lo = bit_lo >> 5, w_hi = (bit_hi - 1) >> 5;
+      const int nw = w_hi - w_lo + 1;
+      for (int i = lane; i < (q1 - q0) * nw; i += 32) {
+        const int qq = i / nw, wi = w_lo + (i - qq * nw), q = q0 + qq;
+        uint32_t m = __ldg(atlas + pg.mask_off + (uint32_t)(q * pg.wpr + wi));
+        // keep bits [bit_lo, bit_hi) of this word
+        const int lo = max(bit_lo - 32 * wi, 0), hi = min(bit_hi - 32 * wi, 32);
+        m &= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (32 - hi));
+        if (m == 0) continue;
         const int r = pg.y + q - yc0;
-        int qq = qc + (r >> 3);  // chunk-local row r lives in sub-stage r / 8 after the chunk's first one (the ring may wrap)
-        if (qq >= ns) qq -= ns;
-        uint8_t *row = stage0 + qq * slot_bytes + (r & (SUB_ROWS - 1)) * ROWB;
-        for (int p = p0 + lane; p < p1; p += 32)
-          if (cov[q * pg.pitch + p]) {
-            uint8_t *px = row + (pg.x + p - x0) * BPP + (BPP == 4 ? rgb_base : 0);
-            px[0] = 255; px[1] = 255; px[2] = 255;
-          }
+        int slot = qc + (r >> 3);  // chunk-local row r lives in sub-stage r / 8 after the chunk's first one (the ring may wrap)
+        if (slot >= ns) slot -= ns;
+        uint8_t *row = stage0 + slot * slot_bytes + (r & (SUB_ROWS - 1)) * ROWB + (BPP == 4 ? rgb_base : 0);
+        const int xbase = pg.x - pg.bit0 + 32 * wi - x0;  // strip-local column of bit 0 of this word
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          uint8_t *px = row + (xbase + b) * BPP;
+          px[0] = 255; px[1] = 255; px[2] = 255;
+        }
       }
     }
     consumer_sync();
@@ -352,9 +373,28 @@ __device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *stage0, i
 
 }  // namespace
 
+#ifdef NES_TRACE
+// diagnostic build only (make EXTRA=-DNES_TRACE OUT=...): per CTA {start, first stage full, end (ns, globaltimer), smid | chunks << 32}
+__device__ unsigned long long g_trace[4 * 1024];
+__device__ unsigned long long g_trace_units[2 * 16384];  // per unit {time its first chunk was taken up, cta | stamp chunks << 32}
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+#endif
+
 template <int BPP>
 __global__ void __launch_bounds__(CTA_THREADS, 3)
-k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int total_units, uint32_t *__restrict__ counters, int ns, int slot_bytes) {
+k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int total_units, int text_units, uint32_t *__restrict__ counters, int ns, int slot_bytes) {
+  // programmatic dependent launch: the next launch on this stream (other frames: nothing of ours is its input)
+  // may fill the SMs as our CTAs drain instead of waiting for the whole grid
+  asm volatile("griddepcontrol.launch_dependents;");
   extern __shared__ __align__(1024) uint8_t smem[];
   using L = StripSmem<BPP>;
   constexpr int ROWB = L::ROWB;
@@ -364,12 +404,15 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
   using G = Geo<BPP>;
   uint64_t *s_full = (uint64_t *)(smem + L::OFF_BAR);  // [NS_MAX]
   uint64_t *s_empty = s_full + NS_MAX;                  // [NS_MAX]
-  int *s_hits = (int *)(smem + L::OFF_HITS);
-  int *s_nhits = s_hits + HIT_CAP;
+  DevPlaced *s_hits = (DevPlaced *)(smem + L::OFF_HITS);
+  int *s_nhits = (int *)(s_hits + STRIP_HITS);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t smem_base = smem_u32(smem);
 
+#ifdef NES_TRACE
+  if (tid == 0 && blockIdx.x < 1024) g_trace[4 * blockIdx.x] = gtime();
+#endif
   if (tid == 0) {
     for (int i = 0; i < NS_MAX; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -388,10 +431,14 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
     int chunk_it = 0, rbase = 0;
     while (cur_u < total_units) {
       // ---- unit geometry (all lanes compute it: cheap, keeps the copy code uniform) ---------
-      const int j = job_of_unit(jobs, n_jobs, CLS, cur_u);
+      // units [0, text_units) are the segments with text of every job (phase 0), the rest follow (phase 1)
+      const int ph = cur_u < text_units ? 0 : 1;
+      const int pu = ph ? cur_u - text_units : cur_u;
+      const int j = job_of_unit(jobs, n_jobs, CLS, ph, pu);
       const DevJob *jp = jobs + j;
-      const int local = cur_u - jp->unit_base[CLS];
-      const int strip = local % jp->strips_x, seg = local / jp->strips_x;
+      const int local = pu - jp->unit_base[CLS][ph];
+      const int strip = local % jp->strips_x;
+      const int seg = jp->seg_order[(ph ? jp->n_text_segs : 0) + local / jp->strips_x];
       const int W = jp->W, H = jp->H, S = jp->seg_rows, n_src = jp->n_src;
       const int x0 = strip * STRIP_W, tw = min(STRIP_W, W - x0);
       const int Y0 = seg * S, Y1 = min(Y0 + S, H);
@@ -434,6 +481,9 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
               }
             }
           }
+#ifdef NES_TRACE
+          c.unit = cur_u; c.k = k;
+#endif
           c.last = last_k && next_u >= total_units;
           c.tma = tma;
           c.stamp = stamp;
@@ -513,7 +563,16 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
       if (q[i] == ns) { q[i] = 0; par[i] ^= 1; }
     }
     mbar_wait_a(full0 + q[0] * 8, (uint32_t)par[0]);
+#ifdef NES_TRACE
+    if (tid == 0 && chunk_it == 0 && blockIdx.x < 1024) g_trace[4 * blockIdx.x + 1] = gtime();
+#endif
     const ChunkCtx &c = *(const ChunkCtx *)(smem + L::OFF_CTX + (chunk_it & (NCTX - 1)) * L::CTX_BYTES);
+#ifdef NES_TRACE
+    if (tid == 0 && c.unit < 16384) {
+      if (c.k == 0) { g_trace_units[2 * c.unit] = gtime(); g_trace_units[2 * c.unit + 1] = blockIdx.x; }
+      if (c.stamp) g_trace_units[2 * c.unit + 1] += 1ull << 32;
+    }
+#endif
     const int last = c.last;
     {
       uint32_t sb[G::NSUB];
@@ -806,12 +865,32 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
         }
       }
     }
+#ifdef NES_TRACE
+    if (last && tid == 0 && blockIdx.x < 1024) {
+      g_trace[4 * blockIdx.x + 2] = gtime();
+      g_trace[4 * blockIdx.x + 3] = (unsigned long long)smid() | ((unsigned long long)(chunk_it + 1) << 32);
+    }
+#endif
     if (last) break;
     if (G::SECOND_BARRIER) consumer_sync();  // phase A of the next chunk reuses ring rows phase B was reading
     qc = q[G::NSUB - 1] + 1; parc = par[G::NSUB - 1];
     if (qc == ns) { qc = 0; parc ^= 1; }
   }
 }
+
+#ifdef NES_TRACE
+extern "C" __attribute__((visibility("default"))) int nes_debug_read_trace(unsigned long long *out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * (size_t)n);
+}
+extern "C" __attribute__((visibility("default"))) int nes_debug_read_trace_units(unsigned long long *out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace_units, sizeof(unsigned long long) * (size_t)n);
+}
+extern "C" __attribute__((visibility("default"))) int nes_debug_clear_trace_units() {
+  void *p = nullptr;
+  cudaGetSymbolAddress(&p, g_trace_units);
+  return (int)cudaMemset(p, 0, sizeof(g_trace_units));
+}
+#endif
 
 static int g_num_sms = 0;
 static int g_smem_per_sm = 0, g_smem_reserved = 1024;
@@ -869,17 +948,22 @@ static void launch_staged(const DevJob *jobs, int n_jobs, int staged[2]) {
 // Host-side planning of a launch: one segment height per bpp class (trade: 6 halo rows per
 // segment against the one-unit tail of the persistent grid; seg_rows + 6 is a multiple of the
 // chunk height so that no staged row is wasted), unit numbering.  Jobs of the other class
-// (and general jobs) take no units.
-void plan_frame_strips(DevJob *jobs, int n_jobs) {
+// (and general jobs) take no units.  Segments that carry text (the job's tile_mask) are numbered first, over
+// the whole launch: a chunk with text costs several plain ones, and a unit that is started last is the tail.
+void plan_frame_strips(DevJob *jobs, int n_jobs, bool text_first) {
   const int sms = g_num_sms > 0 ? g_num_sms : 148;
   int staged[2];
   launch_staged(jobs, n_jobs, staged);
   for (int cls = 0; cls < 2; cls++) {
     const int grid = sms * std::max(1, strips_config(cls, staged[cls]).ctas);
     const int ch = cls == 0 ? Geo<3>::CH : Geo<4>::CH;
-    int best_s = std::max(ch, 32) - 2 * HALO;
+    int s_min = std::max(ch, 32) - 2 * HALO;
+    for (int j = 0; j < n_jobs; j++)
+      if (!jobs[j].general && jobs[j].bpp == 3 + cls)
+        while ((jobs[j].H + s_min - 1) / s_min > MAX_SEGS) s_min += ch;
+    int best_s = s_min;
     double best_cost = 1e30;
-    for (int S = std::max(ch, 32) - 2 * HALO; S <= 256; S += ch) {
+    for (int S = s_min; S <= std::max(256, s_min); S += ch) {
       double work = 0;
       long units = 0;
       for (int j = 0; j < n_jobs; j++) {
@@ -894,38 +978,79 @@ void plan_frame_strips(DevJob *jobs, int n_jobs) {
       const double cost = units <= grid ? unit_cost : work / grid + 0.7 * unit_cost;
       if (cost < best_cost - 1e-9) { best_cost = cost; best_s = S; }
     }
-    int base = 0;
+    int base[2] = {0, 0};
     for (int j = 0; j < n_jobs; j++) {
       DevJob &jb = jobs[j];
-      jb.unit_base[cls] = base;
+      jb.unit_base[cls][0] = base[0];
+      jb.unit_base[cls][1] = base[1];
       if (jb.general || jb.bpp != 3 + cls) continue;
-      jb.seg_rows = best_s;
+      const int S = best_s;
+      jb.seg_rows = S;
       jb.strips_x = (jb.W + STRIP_W - 1) / STRIP_W;
-      jb.segs_y = (jb.H + best_s - 1) / best_s;
+      jb.segs_y = (jb.H + S - 1) / S;
       jb.n_units = jb.strips_x * jb.segs_y;
-      base += jb.n_units;
+      // segments with text first
+      int n_text = 0, n_plain = 0;
+      uint8_t plain[MAX_SEGS];
+      const int nbands = (jb.H + (1 << MASK_BAND_SHIFT) - 1) >> MASK_BAND_SHIFT;
+      for (int sg = 0; sg < jb.segs_y; sg++) {
+        bool text = false;
+        if (text_first && jb.n_glyphs > 0 && jb.use_mask) {
+          const int r0 = std::max(sg * S - HALO, 0), r1 = std::min((sg + 1) * S + HALO, jb.H);
+          for (int band = r0 >> MASK_BAND_SHIFT; band <= (r1 - 1) >> MASK_BAND_SHIFT && band < nbands && band < 256 && !text; band++)
+            text = (jb.band_text[band >> 5] >> (band & 31)) & 1u;
+        }
+        if (text) jb.seg_order[n_text++] = (uint8_t)sg; else plain[n_plain++] = (uint8_t)sg;
+      }
+      for (int i = 0; i < n_plain; i++) jb.seg_order[n_text + i] = plain[i];
+      jb.n_text_segs = n_text;
+      base[0] += n_text * jb.strips_x;
+      base[1] += n_plain * jb.strips_x;
     }
   }
 }
 
-int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream, int unit_begin, int unit_end) {
-  int total[2] = {0, 0}, staged[2];
+static bool g_pdl = true;  // NES_NO_PDL=1: plain stream-ordered launches (A/B experiments)
+
+template <int BPP>
+static cudaError_t launch_one(int grid, int smem, cudaStream_t st, const DevJob *jobs, int n_jobs, int u0, int u1, int text_units, uint32_t *counters, int ns,
+                              int slot) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(CTA_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_frame_strips<BPP>, jobs, n_jobs, u0, u1, text_units, counters, ns, slot);
+}
+
+int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream, int unit_begin, int unit_end) {
+  int total[2] = {0, 0}, text[2] = {0, 0}, staged[2];
   launch_staged(jobs_host, n_jobs, staged);
   for (int j = 0; j < n_jobs; j++) {
     const DevJob &jb = jobs_host[j];
-    if (!jb.general) total[jb.bpp - 3] += jb.n_units;
+    if (!jb.general) { total[jb.bpp - 3] += jb.n_units; text[jb.bpp - 3] += jb.n_text_segs * jb.strips_x; }
   }
+  static const bool once = [] { if (const char *v = getenv("NES_NO_PDL")) g_pdl = atoi(v) == 0; return true; }();
+  (void)once;
   int launches = 0;
   for (int cls = 0; cls < 2; cls++) {
     if (total[cls] == 0) continue;
-    // a unit range only makes sense for a single job (its units are numbered from 0)
+    // a unit range only makes sense for a single job (its units are numbered from 0, in frame order)
     const int u0 = (n_jobs == 1 && unit_end > 0) ? unit_begin : 0, u1 = (n_jobs == 1 && unit_end > 0) ? std::min(unit_end, total[cls]) : total[cls];
     if (u1 <= u0) continue;
     const StripsConfig c = strips_config(cls, staged[cls]);
     if (c.ns < 2) return -1;
     const int grid = std::min(u1 - u0, g_num_sms * c.ctas);
-    if (cls == 0) k_frame_strips<3><<<grid, CTA_THREADS, c.smem, (cudaStream_t)stream>>>(jobs_dev, n_jobs, u0, u1, counters, c.ns, c.slot);
-    else k_frame_strips<4><<<grid, CTA_THREADS, c.smem, (cudaStream_t)stream>>>(jobs_dev, n_jobs, u0, u1, counters + 2, c.ns, c.slot);
+    // every launch gets its own self re-arming counter pair: consecutive launches overlap (see the kernel's first line)
+    uint32_t *ctr = counters + 2 * ((*seq)++ % COUNTER_SLOTS);
+    const cudaError_t e = cls == 0 ? launch_one<3>(grid, c.smem, (cudaStream_t)stream, jobs_dev, n_jobs, u0, u1, text[cls], ctr, c.ns, c.slot)
+                                   : launch_one<4>(grid, c.smem, (cudaStream_t)stream, jobs_dev, n_jobs, u0, u1, text[cls], ctr, c.ns, c.slot);
+    if (e != cudaSuccess) return -1;
     launches++;
   }
   return launches;

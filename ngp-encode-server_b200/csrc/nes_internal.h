@@ -25,7 +25,9 @@ constexpr int NCTX = 8;            // chunk contexts in flight
 constexpr int TMA_MAX_SOURCES = 4; // composites of more sources are filled by the consumer warps
 constexpr int CONSUMER_WARPS = 8;
 constexpr int CTA_THREADS = 32 * (CONSUMER_WARPS + 1);  // + one producer warp (TMA, chunk contexts)
-constexpr int HIT_CAP = 256;  // glyph rect tests per overlay chunk
+constexpr int HIT_CAP = 256;  // glyph rect tests per pass (resize tiles)
+constexpr int STRIP_HITS = 256;  // glyph rect tests per pass of an overlay chunk (k_frame_strips; the hits are staged as whole descriptors)
+constexpr int MAX_SEGS = 192;   // segments of one frame (k_frame_strips work numbering)
 constexpr int MASK_WORDS = 128;  // per-job bitmap: (32-row band, strip) cells touched by text
 constexpr int MASK_BAND_SHIFT = 5;
 
@@ -77,12 +79,16 @@ struct DevSource {
   int32_t depth_stride;
 };
 
-// One glyph of a text run placed in the frame (top-left of its bitmap).
+// One glyph of a text run placed in the frame, already clipped to the run's view.  The atlas on the device
+// holds one BIT per bitmap pixel (coverage != 0, the only thing render_text.cc:100 looks at): glyph row q is
+// `wpr` 32-bit words; visible column p of visible row q is bit (bit0 + p) of the row that starts at word
+// mask_off + q * wpr.
 struct DevPlaced {
-  int32_t x, y;
-  int32_t w, h;
-  int32_t pitch;
-  uint32_t atlas_off;
+  int32_t x, y;       // frame position of the first visible bitmap pixel
+  int32_t w, h;       // visible size
+  uint32_t mask_off;  // word index of the first visible row's mask inside the atlas
+  uint16_t wpr;       // mask words per bitmap row
+  uint16_t bit0;      // bit index of the first visible column inside a row's mask
 };
 
 struct DevFilter {
@@ -118,18 +124,23 @@ struct alignas(64) DevJob {
   int32_t dys, dus, dvs;
   int32_t in_vec;         // 1: all source pointers/strides 16-byte aligned
   const DevPlaced *glyphs;
-  const uint8_t *atlas;
+  const uint32_t *atlas;  // 1 bit per glyph pixel (see DevPlaced)
   int32_t n_glyphs;
   int32_t tma_ok;     // 16-byte aligned rows, <= TMA_MAX_SOURCES sources: rows are staged by tensor-map TMA
   int32_t use_mask;   // tile_mask valid (tiles_x*tiles_y <= 32*MASK_WORDS)
   int32_t nv12;       // chroma goes to one interleaved plane (su / du; sv / dv unused)
   uint32_t tile_mask[MASK_WORDS];  // bit (band * strips_x + strip) set: a placed glyph intersects that cell
+  uint32_t band_text[8];           // bit band set: some cell of that 32-row band is (host: segment ordering)
   int32_t tiles_x, tiles_y, tile_base;  // k_resize_tiles work (general jobs only; 0 tiles otherwise)
-  // k_frame_strips work (same-size jobs only)
+  // k_frame_strips work (same-size jobs only).  The units of a launch are numbered in two phases: first the
+  // segments that carry text, of every job (they take up to 3x longer: started first they never form the
+  // tail of the launch), then all the others.  seg_order lists this job's segments in that order.
   int32_t strips_x, segs_y;
   int32_t seg_rows;    // output rows per segment (even)
-  int32_t unit_base[2];  // [bpp-3]: units of that bpp class ahead of this job in the batch
+  int32_t unit_base[2][2];  // [bpp-3][phase]: units of that class and phase ahead of this job in the launch
   int32_t n_units;
+  int32_t n_text_segs;      // the first n_text_segs entries of seg_order are phase 0
+  uint8_t seg_order[MAX_SEGS];
   // dp2a operands for packed 3-byte pixels read as raw words (frame_strips.cu phase A)
   uint32_t ky3[4], ku3[3], kv3[3];
   uint32_t ky2[2];     // luma coefficients x2, unsigned (4-byte pixels): Y lands in byte 2 of the sum
@@ -141,7 +152,7 @@ struct alignas(64) DevJob {
   int32_t general;  // 1: k_resize_tiles (any size change, or H < 12 where libswscale's chroma filter is truncated)
   // placed glyphs sorted by band = clamp(y, 0, H-1) >> glyph_band_shift: band b holds glyphs
   // [glyph_band[b], glyph_band[b+1]); a tile only tests the bands its source window can touch
-  int32_t glyph_band_shift, glyph_max_h;
+  int32_t glyph_band_shift, glyph_max_h;  // shift < 0: the list is short and unsorted, scan it whole
   int32_t glyph_band[GLYPH_BANDS + 1];
   int32_t rs_tw, rs_th;     // destination tile of the resize kernel
   RsLayout rs_lay;          // shared-memory carve-up for the largest tile of this size pair (same bases for every tile)
@@ -151,9 +162,12 @@ struct alignas(64) DevJob {
 
 // Launchers (frame_strips.cu, resize_tiles.cu).  jobs: device pointer to n_jobs descriptors.
 // unit_end > 0 (single-job launches only): process only the units [unit_begin, unit_end) of the job
-int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, void *stream, int unit_begin = 0, int unit_end = 0);
-// Assigns seg_rows / unit_base of the same-size jobs of a launch (host).
-void plan_frame_strips(DevJob *jobs_host, int n_jobs);
+// counters: COUNTER_SLOTS pairs; *seq: the session's launch sequence number (picks the pair)
+int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream, int unit_begin = 0, int unit_end = 0);
+// Assigns seg_rows / seg_order / unit_base of the same-size jobs of a launch (host).  text_first = false keeps the
+// segments in frame order (banded submits launch unit ranges that must be row bands).
+void plan_frame_strips(DevJob *jobs_host, int n_jobs, bool text_first = true);
+constexpr int COUNTER_SLOTS = 64;  // work counters of k_frame_strips: one self re-arming {next unit, CTAs done} pair per launch in flight
 int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
 int kernels_init();  // opt-in shared memory sizes; returns cudaError_t
 int frame_strips_init();

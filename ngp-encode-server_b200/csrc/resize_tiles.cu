@@ -201,6 +201,12 @@ __device__ __forceinline__ int4 lds_v4(uint32_t a) {
   return v;
 }
 
+// two carve-ups are the same launch only if every region offset agrees
+__host__ __device__ inline bool same_layout(const RsLayout &a, const RsLayout &b) {
+  return a.y14 == b.y14 && a.u14 == b.u14 && a.v14 == b.v14 && a.hy == b.hy && a.hu == b.hu && a.hv == b.hv && a.dep == b.dep && a.mask == b.mask &&
+         a.hits == b.hits && a.vtab == b.vtab && a.src == b.src && a.total == b.total;
+}
+
 enum { H_SCENE = 0, H_DEPTH = 1 };
 
 // Horizontal polyphase of NP planes that share one filter (NP = 2: U and V):
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
   const DevJob *jp = find_job(jobs, n_jobs, blockIdx.x, &tile);
   // a launch serves the jobs of one pixel class that share one shared-memory carve-up (kernel parameter:
   // constant-bank operands; derived per tile in registers it cost 6 % of the kernel's instructions)
-  if (!jp->general || jp->bpp != BPP || jp->rs_lay.total != L.total || jp->rs_lay.vtab != L.vtab || jp->rs_lay.hy != L.hy || jp->rs_lay.dep != L.dep) return;
+  if (!jp->general || jp->bpp != BPP || !same_layout(jp->rs_lay, L)) return;
   const DevJob &jb = *jp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARP = RS_THREADS / 32;
@@ -409,29 +415,27 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
       any |= nh;
       for (int h = warp; h < nh; h += NWARP) {
         const DevPlaced pg = jb.glyphs[s_hits[h]];
-        const uint8_t *cov = jb.atlas + pg.atlas_off;
         const int q0 = max(0, t.wy0 - pg.y), q1 = min(pg.h, y1 - pg.y);
         const int p0 = max(0, t.wx0 - pg.x), p1 = min(pg.w, x1 - pg.x);
-        // lanes over the flattened clipped bitmap (a 10 x 14 glyph keeps all 32 lanes busy); the row of
-        // element i is floor(i / gw) by an exact reciprocal multiply (i < 4096, gw <= 256)
-        const int gw = p1 - p0, n = (q1 - q0) * gw;
-        if (n < 4096 && gw <= 256) {
-          const uint32_t rcp = ((1u << 20) + gw - 1) / gw;
-          for (int i = lane; i < n; i += 32) {
-            const int qq = (int)(((uint32_t)i * rcp) >> 20);
-            const int q = q0 + qq, p = p0 + i - qq * gw;
-            if (cov[q * pg.pitch + p]) {
-              const int xx = pg.x + p - t.wx0;
-              atomicOr(&s_mask[(pg.y + q - t.wy0) * mw + (xx >> 5)], 1u << (xx & 31));
-            }
+        // the atlas holds one bit per glyph pixel (DevPlaced): a lane takes one word of one visible row and ORs
+        // it, shifted to the window's column grid, into the tile's overlay mask
+        const int bit_lo = pg.bit0 + p0, bit_hi = pg.bit0 + p1;
+        const int w_lo = bit_lo >> 5, w_hi = (bit_hi - 1) >> 5, nw = w_hi - w_lo + 1;
+        for (int i = lane; i < (q1 - q0) * nw; i += 32) {
+          const int qq = i / nw, wi = w_lo + (i - qq * nw), q = q0 + qq;
+          uint32_t m = __ldg(jb.atlas + pg.mask_off + (uint32_t)(q * pg.wpr + wi));
+          const int lo = max(bit_lo - 32 * wi, 0), hi = min(bit_hi - 32 * wi, 32);
+          m &= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (32 - hi));
+          if (m == 0) continue;
+          const int xb = pg.x - pg.bit0 + 32 * wi - t.wx0;  // window column of bit 0 of this word (negative only for masked-off bits)
+          const int wd = xb >> 5, sh = xb & 31;
+          uint32_t *mrow = s_mask + (pg.y + q - t.wy0) * mw;
+          const uint32_t lo_part = m << sh;
+          if (lo_part && wd >= 0) atomicOr(&mrow[wd], lo_part);
+          if (sh) {
+            const uint32_t hi_part = m >> (32 - sh);
+            if (hi_part) atomicOr(&mrow[wd + 1], hi_part);
           }
-        } else {
-          for (int q = q0; q < q1; q++)
-            for (int p = p0 + lane; p < p1; p += 32)
-              if (cov[q * pg.pitch + p]) {
-                const int xx = pg.x + p - t.wx0;
-                atomicOr(&s_mask[(pg.y + q - t.wy0) * mw + (xx >> 5)], 1u << (xx & 31));
-              }
         }
       }
       __syncthreads();
@@ -581,8 +585,7 @@ int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_j
     bool seen = false;
     for (int i = 0; i < j && !seen; i++) {
       const DevJob &o = jobs_host[i];
-      seen = o.general && o.bpp == jb.bpp && o.rs_lay.total == jb.rs_lay.total && o.rs_lay.vtab == jb.rs_lay.vtab && o.rs_lay.hy == jb.rs_lay.hy &&
-             o.rs_lay.dep == jb.rs_lay.dep;
+      seen = o.general && o.bpp == jb.bpp && same_layout(o.rs_lay, jb.rs_lay);
     }
     if (seen) continue;
     const int sm = (jb.rs_lay.total + 1023) & ~1023;

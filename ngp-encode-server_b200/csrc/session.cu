@@ -69,11 +69,19 @@ struct Slot {
   std::vector<StagedCopy> staged;
 };
 
+struct RunCacheEntry {  // one laid-out text run (place_text)
+  uint64_t atlas_gen = ~0ull;
+  int W = 0, H = 0, position = 0, view[4] = {0, 0, 0, 0};
+  std::string text;
+  std::vector<DevPlaced> placed;
+};
+
 struct BatchTables {
   DevJob *h_jobs = nullptr, *d_jobs = nullptr;
   DevPlaced *h_glyphs = nullptr, *d_glyphs = nullptr;
   cudaEvent_t done = nullptr, up = nullptr;
   bool used = false;
+  int n = 0;  // frames described
 };
 
 }  // namespace
@@ -87,17 +95,21 @@ struct nes_gpu_session {
   uint64_t batch_seq = 0;
   uint64_t next_ticket = 1;
   uint64_t launches = 0;
+  uint64_t strips_seq = 0;  // k_frame_strips launches issued (selects the work-counter pair)
   HostAtlas atlas;
-  uint8_t *d_atlas = nullptr;
-  uint32_t *d_counters = nullptr;  // k_frame_strips work counters (self re-arming), [2] per bpp class
+  uint32_t *d_atlas = nullptr;     // glyph bit masks (HostAtlas::mask)
+  uint32_t *d_counters = nullptr;  // k_frame_strips work counters: COUNTER_SLOTS self re-arming pairs, handed out round-robin per launch
   std::map<std::tuple<int, int, int, int>, FilterSet> filters;
-  // tensor maps of staged planes, keyed by (pointer, stride, width in bytes, rows): a streaming
+  // tensor maps of staged planes, keyed by (pointer, stride, width in bytes, rows, box bytes): a streaming
   // session cycles through a handful of ring buffers, so encoding happens once per buffer
-  std::map<std::tuple<const void *, int, int, int>, TMap> tmaps;
+  std::map<std::tuple<const void *, int, int, int, int>, TMap> tmaps;
   nes_timing last{};
   std::string err;
   int sticky = 0;
   std::vector<nes_placed_glyph> scratch_placed;
+  std::vector<RunCacheEntry> run_cache = std::vector<RunCacheEntry>(16);
+  size_t run_cache_next = 0;
+  uint64_t atlas_gen = 0;  // bumped by every atlas upload (invalidates run_cache)
   std::vector<DevPlaced> scratch_banded;
   int latency_bands = 1;  // > 1: upload / convert / download a frame in that many row bands (nes_gpu_session_set_latency_bands)
 };
@@ -120,7 +132,16 @@ int ensure_dev(nes_gpu_session *s, uint8_t **p, size_t *cap, size_t need) {
   *p = nullptr;
   *cap = 0;
   need = align_up(need, 1 << 20);
-  CU_TRY(s, cudaMalloc((void **)p, need));
+  {
+    const cudaError_t e = cudaMalloc((void **)p, need);
+    if (e == cudaErrorMemoryAllocation) {  // a transient condition of the device, not a broken session
+      cudaGetLastError();
+      *p = nullptr;
+      s->err = "cudaMalloc: out of device memory (" + std::to_string(need) + " bytes)";
+      return NES_ERR_NO_MEMORY;
+    }
+    CU_TRY(s, e);
+  }
   CU_TRY(s, cudaMemset(*p, 0, need));
   *cap = need;
   return NES_OK;
@@ -132,7 +153,16 @@ int ensure_host(nes_gpu_session *s, uint8_t **p, size_t *cap, size_t need) {
   *p = nullptr;
   *cap = 0;
   need = align_up(need, 1 << 20);
-  CU_TRY(s, cudaHostAlloc((void **)p, need, cudaHostAllocDefault));
+  {
+    const cudaError_t e = cudaHostAlloc((void **)p, need, cudaHostAllocDefault);
+    if (e == cudaErrorMemoryAllocation) {
+      cudaGetLastError();
+      *p = nullptr;
+      s->err = "cudaHostAlloc: out of pinned host memory (" + std::to_string(need) + " bytes)";
+      return NES_ERR_NO_MEMORY;
+    }
+    CU_TRY(s, e);
+  }
   *cap = need;
   return NES_OK;
 }
@@ -295,10 +325,15 @@ int validate(const nes_gpu_session *s, const nes_frame_in *in, const nes_frame_o
     if ((int64_t)in->src[k].rgb_stride * H >= (int64_t)1 << 31 || (int64_t)in->src[k].depth_stride * H >= (int64_t)1 << 31) return NES_ERR_TOO_LARGE;
   if (out->pix_fmt != NES_OUT_YUV420P && out->pix_fmt != NES_OUT_NV12) return NES_ERR_INVALID_ARG;
   const bool nv12 = out->pix_fmt == NES_OUT_NV12;
+  // line sizes: at least a row, at most a generous multiple of the session's widest row (side-by-side packing
+  // passes the packed frame's line size for each eye); an absurd value would otherwise surface as an allocation failure
+  const int64_t maxls = 16 * (int64_t)std::max(s->cfg.max_width, 64);
   for (int p = 0; p < (nv12 ? 2 : 3); p++) {
     const int minls = p ? (nv12 ? 2 : 1) * ((Wd + 1) / 2) : Wd;
     if (!out->scene[p] || out->scene_linesize[p] < minls) return NES_ERR_INVALID_ARG;
+    if (out->scene_linesize[p] > maxls) return NES_ERR_TOO_LARGE;
     if (want_depth && (!out->depth[p] || out->depth_linesize[p] < minls)) return NES_ERR_INVALID_ARG;
+    if (want_depth && out->depth_linesize[p] > maxls) return NES_ERR_TOO_LARGE;
   }
   return NES_OK;
 }
@@ -343,6 +378,7 @@ void job_common(DevJob *jb, const nes_frame_in *in, const nes_frame_out *out, in
 // that every other chunk skips the overlay stage without looking at the glyph list.
 void job_tile_mask(DevJob *jb, const DevPlaced *placed) {
   jb->use_mask = 0;
+  std::memset(jb->band_text, 0, sizeof(jb->band_text));
   if (jb->general || jb->n_glyphs <= 0) return;
   const int strips = (jb->W + STRIP_W - 1) / STRIP_W;
   const int nbands = (jb->H + (1 << MASK_BAND_SHIFT) - 1) >> MASK_BAND_SHIFT;
@@ -356,6 +392,7 @@ void job_tile_mask(DevJob *jb, const DevPlaced *placed) {
       for (int st = x0 / STRIP_W; st <= (x1 - 1) / STRIP_W; st++) {
         const int t = band * strips + st;
         jb->tile_mask[t >> 5] |= 1u << (t & 31);
+        jb->band_text[band >> 5] |= 1u << (band & 31);
       }
   }
   jb->use_mask = 1;
@@ -406,7 +443,7 @@ EncodeTiledFn encode_tiled_fn() {
 // SUB_ROWS rows x one strip (box_bytes).  Rows / columns outside the plane read as zero.
 int plane_tmap(nes_gpu_session *s, const uint8_t *base, int stride, int width_bytes, int rows, int box_bytes, TMap *out) {
   static_assert(sizeof(TMap) == sizeof(CUtensorMap) && alignof(TMap) >= alignof(CUtensorMap), "TMap mirrors CUtensorMap");
-  const auto key = std::make_tuple((const void *)base, stride, width_bytes, rows);
+  const auto key = std::make_tuple((const void *)base, stride, width_bytes, rows, box_bytes);
   auto it = s->tmaps.find(key);
   if (it != s->tmaps.end()) { *out = it->second; return NES_OK; }
   EncodeTiledFn enc = encode_tiled_fn();
@@ -440,28 +477,51 @@ int job_tmaps(nes_gpu_session *s, DevJob *jb) {
 }
 
 // Text runs -> placed glyph descriptors at dst[0..].  Returns count or negative status.
+// A streaming session repeats most of its strings from frame to frame (the camera matrix, "direction=..."): the
+// placed form of the last few distinct runs is kept and copied instead of laid out again.
 int place_text(nes_gpu_session *s, int W, int H, const nes_text_run *runs, int n_runs, DevPlaced *dst, int cap) {
   if (n_runs <= 0) return 0;
   if (!runs) return NES_ERR_INVALID_ARG;
   if (!s->atlas.valid) return NES_ERR_NO_ATLAS;
-  s->scratch_placed.clear();
+  int n = 0;
   for (int r = 0; r < n_runs; r++) {
-    if (runs[r].len > 0 && !runs[r].text) return NES_ERR_INVALID_ARG;
-    layout_run(s->atlas, W, H, runs[r], &s->scratch_placed);
-  }
-  const int n = (int)s->scratch_placed.size();
-  if (n > cap) return NES_ERR_TOO_LARGE;
-  for (int i = 0; i < n; i++) {
-    const nes_placed_glyph &pg = s->scratch_placed[i];
-    const HostGlyph &g = s->atlas.glyph[pg.code];
-    dst[i] = DevPlaced{pg.x, pg.y, g.width, g.rows, g.pitch, g.offset};
+    const nes_text_run &run = runs[r];
+    if (run.len > 0 && !run.text) return NES_ERR_INVALID_ARG;
+    if (run.len <= 0) continue;
+    RunCacheEntry *hit = nullptr;
+    for (RunCacheEntry &e : s->run_cache)
+      if (e.atlas_gen == s->atlas_gen && e.W == W && e.H == H && e.position == run.position && e.view[0] == run.view_x && e.view[1] == run.view_y &&
+          e.view[2] == run.view_w && e.view[3] == run.view_h && (int)e.text.size() == run.len && std::memcmp(e.text.data(), run.text, (size_t)run.len) == 0) {
+        hit = &e;
+        break;
+      }
+    if (!hit) {
+      s->scratch_placed.clear();
+      layout_run(s->atlas, W, H, run, &s->scratch_placed);
+      hit = &s->run_cache[s->run_cache_next++ % s->run_cache.size()];
+      hit->atlas_gen = s->atlas_gen; hit->W = W; hit->H = H; hit->position = run.position;
+      hit->view[0] = run.view_x; hit->view[1] = run.view_y; hit->view[2] = run.view_w; hit->view[3] = run.view_h;
+      hit->text.assign(run.text, (size_t)run.len);
+      hit->placed.clear();
+      for (const nes_placed_glyph &pg : s->scratch_placed) {
+        const HostGlyph &g = s->atlas.glyph[pg.code];
+        // pre-clipped to the run's view (hence to the frame): the device only clips to its own tile / chunk
+        hit->placed.push_back(DevPlaced{pg.x + pg.clip_x, pg.y + pg.clip_y, pg.clip_w, pg.clip_h, g.mask_off + (uint32_t)(pg.clip_y * g.wpr), (uint16_t)g.wpr, (uint16_t)pg.clip_x});
+      }
+    }
+    const int m = (int)hit->placed.size();
+    if (n + m > cap) return NES_ERR_TOO_LARGE;
+    if (m) std::memcpy(dst + n, hit->placed.data(), (size_t)m * sizeof(DevPlaced));
+    n += m;
   }
   return n;
 }
 
-// Resize jobs: bucket the placed glyphs by row band (stable counting sort; stamps are order-free)
-// so that a tile tests only the glyphs near its source window instead of the whole list.
+// Bucket the placed glyphs by row band (stable counting sort; stamps are order-free) so that a tile / chunk
+// tests only the glyphs near its source rows instead of the whole list.
 void band_glyphs(DevJob *jb, DevPlaced *gl, int n, std::vector<DevPlaced> *tmp) {
+  // a short list is scanned whole by an overlay chunk of the fused kernel (one pass of STRIP_HITS tests): no sort
+  if (!jb->general && n <= STRIP_HITS) { jb->glyph_band_shift = -1; return; }
   int shift = 5;
   while (((jb->H - 1) >> shift) >= GLYPH_BANDS) shift++;
   jb->glyph_band_shift = shift;
@@ -477,7 +537,7 @@ void band_glyphs(DevJob *jb, DevPlaced *gl, int n, std::vector<DevPlaced> *tmp) 
 
 int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, int n, cudaStream_t st) {
   int l = 0;
-  const int r0 = launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, st);
+  const int r0 = launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, &s->strips_seq, st);
   if (r0 > 0) l += r0;
   const int r = launch_resize_tiles(d_jobs, h_jobs, n, st);
   if (r > 0) l += r;
@@ -537,8 +597,8 @@ int nes_gpu_session_create(const nes_gpu_cfg *cfg, nes_gpu_session **out) {
   if (cudaStreamCreateWithFlags(&s->st_in, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&s->st_k, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&s->st_out, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
-  if (cudaMalloc((void **)&s->d_counters, 4 * sizeof(uint32_t)) != cudaSuccess) return fail(NES_ERR_CUDA);
-  if (cudaMemset(s->d_counters, 0, 4 * sizeof(uint32_t)) != cudaSuccess) return fail(NES_ERR_CUDA);
+  if (cudaMalloc((void **)&s->d_counters, 2 * COUNTER_SLOTS * sizeof(uint32_t)) != cudaSuccess) return fail(NES_ERR_CUDA);
+  if (cudaMemset(s->d_counters, 0, 2 * COUNTER_SLOTS * sizeof(uint32_t)) != cudaSuccess) return fail(NES_ERR_CUDA);
   s->slots.resize((size_t)s->cfg.ring_depth);
   const size_t gl_bytes = (size_t)s->cfg.max_glyphs * sizeof(DevPlaced);
   for (Slot &sl : s->slots) {
@@ -646,10 +706,13 @@ static int upload_atlas(nes_gpu_session *s) {
   CU_TRY(s, cudaSetDevice(s->cfg.device));
   CU_TRY(s, cudaStreamSynchronize(s->st_k));
   if (s->d_atlas) { CU_TRY(s, cudaFree(s->d_atlas)); s->d_atlas = nullptr; }
-  const size_t n = std::max<size_t>(s->atlas.coverage.size(), 16);
-  CU_TRY(s, cudaMalloc((void **)&s->d_atlas, n));
-  if (!s->atlas.coverage.empty())
-    CU_TRY(s, cudaMemcpy(s->d_atlas, s->atlas.coverage.data(), s->atlas.coverage.size(), cudaMemcpyHostToDevice));
+  build_masks(&s->atlas);
+  s->atlas_gen++;
+  const size_t n = std::max<size_t>(s->atlas.mask.size(), 4) * sizeof(uint32_t);
+  CU_TRY(s, cudaMalloc((void **)&s->d_atlas, n + 64));  // + slack: a row's last word may be read as part of a wider load
+  CU_TRY(s, cudaMemset(s->d_atlas, 0, n + 64));
+  if (!s->atlas.mask.empty())
+    CU_TRY(s, cudaMemcpy(s->d_atlas, s->atlas.mask.data(), s->atlas.mask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   s->atlas.valid = true;
   return NES_OK;
 }
@@ -824,7 +887,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   jb->nv12 = out->pix_fmt == NES_OUT_NV12;
 
   jb->general = resize;
-  if (resize && n_gl > 0) band_glyphs(jb, sl.h_glyphs, n_gl, &s->scratch_banded);
+  if (n_gl > 0) band_glyphs(jb, sl.h_glyphs, n_gl, &s->scratch_banded);
   if (resize) {
     FilterSet *fs;
     if ((st = get_filters(s, W, H, Wd, Hd, &fs))) return st;
@@ -836,7 +899,8 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   job_alignment(jb);
   if ((st = job_tmaps(s, jb))) return st;
   job_tile_mask(jb, sl.h_glyphs);
-  plan_frame_strips(jb, 1);
+  // (banded submits launch unit ranges that must be whole row bands: segments stay in frame order)
+  plan_frame_strips(jb, 1, /*text_first=*/!banded);
 
   if (n_gl > 0) CU_TRY(s, cudaMemcpyAsync(sl.d_glyphs, sl.h_glyphs, (size_t)n_gl * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaMemcpyAsync(sl.d_job, sl.h_job, sizeof(DevJob), cudaMemcpyHostToDevice, s->st_in));
@@ -885,7 +949,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
       CU_TRY(s, cudaEventRecord(sl.e_band_in[b], s->st_in));
       CU_TRY(s, cudaStreamWaitEvent(s->st_k, sl.e_band_in[b], 0));
       if (b == 0) CU_TRY(s, cudaEventRecord(sl.e_k0, s->st_k));
-      const int l = launch_frame_strips(sl.d_job, sl.h_job, 1, s->d_counters, s->st_k, seg_lo * jb->strips_x, seg_hi * jb->strips_x);
+      const int l = launch_frame_strips(sl.d_job, sl.h_job, 1, s->d_counters, &s->strips_seq, s->st_k, seg_lo * jb->strips_x, seg_hi * jb->strips_x);
       if (l < 0) { s->err = "launch_frame_strips failed"; return NES_ERR_CUDA; }
       sl.n_launches += l;
       s->launches += (uint64_t)l;
@@ -978,13 +1042,10 @@ int nes_gpu_last_timing(nes_gpu_session *s, nes_timing *t) {
   return NES_OK;
 }
 
-int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_frame_in *in, const nes_text_run *const *runs,
-                                 const int *n_runs, const nes_frame_out *out, int sync) {
-  if (!s || !in || !out || n_frames < 1 || n_frames > kMaxBatch) return NES_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lk(s->mu);
-  if (s->sticky) return s->sticky;
-  CU_TRY(s, cudaSetDevice(s->cfg.device));
-  BatchTables &bt = s->batch[s->batch_seq++ % kBatchRing];
+// Descriptor table of a batch of device-resident frames -> bt (pinned + device copies, uploaded on the copy
+// stream; bt.up is recorded behind the upload).
+static int build_batch(nes_gpu_session *s, BatchTables &bt, int n_frames, const nes_frame_in *in, const nes_text_run *const *runs, const int *n_runs,
+                       const nes_frame_out *out) {
   const int gl_cap = s->cfg.max_glyphs * kBatchGlyphFactor;
   const size_t gl_bytes = (size_t)gl_cap * sizeof(DevPlaced);
   if (!bt.h_jobs) {
@@ -995,7 +1056,7 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
     CU_TRY(s, cudaEventCreateWithFlags(&bt.done, cudaEventDisableTiming));
     CU_TRY(s, cudaEventCreateWithFlags(&bt.up, cudaEventDisableTiming));
   }
-  if (bt.used) CU_TRY(s, cudaEventSynchronize(bt.done));  // tables still referenced by an older batch
+  if (bt.used) CU_TRY(s, cudaEventSynchronize(bt.done));  // tables still referenced by an older launch
   int tile_base = 0, gl_used = 0;
   for (int f = 0; f < n_frames; f++) {
     int bpp, base, a_off; bool bgr;
@@ -1028,7 +1089,7 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
     }
     jb->nv12 = out[f].pix_fmt == NES_OUT_NV12;
     jb->general = general;
-    if (general && n_gl > 0) band_glyphs(jb, bt.h_glyphs + gl_used - n_gl, n_gl, &s->scratch_banded);
+    if (n_gl > 0) band_glyphs(jb, bt.h_glyphs + gl_used - n_gl, n_gl, &s->scratch_banded);
     if (general) {
       FilterSet *fs;
       if ((st = get_filters(s, W, H, out[f].width, out[f].height, &fs))) return st;
@@ -1047,6 +1108,19 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
   if (gl_used > 0) CU_TRY(s, cudaMemcpyAsync(bt.d_glyphs, bt.h_glyphs, (size_t)gl_used * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaMemcpyAsync(bt.d_jobs, bt.h_jobs, sizeof(DevJob) * n_frames, cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaEventRecord(bt.up, s->st_in));
+  bt.n = n_frames;
+  return NES_OK;
+}
+
+int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_frame_in *in, const nes_text_run *const *runs,
+                                 const int *n_runs, const nes_frame_out *out, int sync) {
+  if (!s || !in || !out || n_frames < 1 || n_frames > kMaxBatch) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (s->sticky) return s->sticky;
+  CU_TRY(s, cudaSetDevice(s->cfg.device));
+  BatchTables &bt = s->batch[s->batch_seq++ % kBatchRing];
+  const int st = build_batch(s, bt, n_frames, in, runs, n_runs, out);
+  if (st) return st;
   CU_TRY(s, cudaStreamWaitEvent(s->st_k, bt.up, 0));
   run_kernels(s, bt.d_jobs, bt.h_jobs, n_frames, s->st_k);
   CU_TRY(s, cudaGetLastError());
@@ -1054,6 +1128,61 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
   bt.used = true;
   if (sync) CU_TRY(s, cudaStreamSynchronize(s->st_k));
   return NES_OK;
+}
+
+// ---- prepared batches: descriptors built and uploaded once, launched many times -------------------------
+struct nes_gpu_batch {
+  BatchTables bt;
+};
+
+int nes_gpu_batch_prepare(nes_gpu_session *s, int n_frames, const nes_frame_in *in, const nes_text_run *const *runs, const int *n_runs,
+                          const nes_frame_out *out, nes_gpu_batch **batch) {
+  if (!s || !in || !out || !batch || n_frames < 1 || n_frames > kMaxBatch) return NES_ERR_INVALID_ARG;
+  *batch = nullptr;
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (s->sticky) return s->sticky;
+  CU_TRY(s, cudaSetDevice(s->cfg.device));
+  nes_gpu_batch *b = new (std::nothrow) nes_gpu_batch();
+  if (!b) return NES_ERR_NO_MEMORY;
+  const int st = build_batch(s, b->bt, n_frames, in, runs, n_runs, out);
+  // the table is resident before the call returns: nes_gpu_batch_run is then nothing but the launches, back to
+  // back on the compute stream (no event in between: consecutive launches overlap, frame_strips.cu)
+  cudaError_t e = st == NES_OK ? cudaStreamSynchronize(s->st_in) : cudaSuccess;
+  if (st != NES_OK || e != cudaSuccess) {
+    BatchTables &t = b->bt;
+    cudaFreeHost(t.h_jobs); cudaFree(t.d_jobs); cudaFreeHost(t.h_glyphs); cudaFree(t.d_glyphs);
+    if (t.done) cudaEventDestroy(t.done);
+    if (t.up) cudaEventDestroy(t.up);
+    delete b;
+    if (st != NES_OK) return st;
+    CU_TRY(s, e);
+  }
+  *batch = b;
+  return NES_OK;
+}
+
+int nes_gpu_batch_run(nes_gpu_session *s, nes_gpu_batch *b, int sync) {
+  if (!s || !b) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (s->sticky) return s->sticky;
+  CU_TRY(s, cudaSetDevice(s->cfg.device));
+  run_kernels(s, b->bt.d_jobs, b->bt.h_jobs, b->bt.n, s->st_k);
+  CU_TRY(s, cudaGetLastError());
+  if (sync) CU_TRY(s, cudaStreamSynchronize(s->st_k));
+  return NES_OK;
+}
+
+void nes_gpu_batch_free(nes_gpu_session *s, nes_gpu_batch *b) {
+  if (!s || !b) return;
+  std::lock_guard<std::mutex> lk(s->mu);
+  cudaSetDevice(s->cfg.device);
+  cudaStreamSynchronize(s->st_k);
+  BatchTables &t = b->bt;
+  cudaFreeHost(t.h_jobs); cudaFree(t.d_jobs); cudaFreeHost(t.h_glyphs); cudaFree(t.d_glyphs);
+  if (t.done) cudaEventDestroy(t.done);
+  if (t.up) cudaEventDestroy(t.up);
+  cudaGetLastError();
+  delete b;
 }
 
 }  // extern "C"

@@ -33,8 +33,17 @@ static void pen_start(int pos, int W, int H, int *px, int *py) {
 }
 
 int layout_run(const HostAtlas &atlas, int W, int H, const nes_text_run &run, std::vector<nes_placed_glyph> *out) {
+  // the run's view is what the reference calls `frame` (an eye of a side-by-side frame, or the whole frame)
+  int vx = 0, vy = 0, vw = W, vh = H;
+  if (run.view_w > 0 && run.view_h > 0) {
+    vx = run.view_x; vy = run.view_y; vw = run.view_w; vh = run.view_h;
+    // a view sticking out of the frame is cut to it (nothing outside the frame exists to be stamped)
+    if (vx < 0 || vy < 0 || vx >= W || vy >= H) return 0;
+  }
+  // visible part of the view inside the frame, in view coordinates
+  const int cx1 = (vx + vw > W) ? W - vx : vw, cy1 = (vy + vh > H) ? H - vy : vh;
   int pen_x, pen_y;
-  pen_start(run.position, W, H, &pen_x, &pen_y);
+  pen_start(run.position, vw, vh, &pen_x, &pen_y);
   const int line_x = pen_x;
   int placed = 0;
   for (int n = 0; n < run.len; n++) {
@@ -46,16 +55,31 @@ int layout_run(const HostAtlas &atlas, int W, int H, const nes_text_run &run, st
     }
     const HostGlyph &g = atlas.glyph[ch];
     if (g.width > 0 && g.rows > 0) {
-      const int gx = pen_x + g.left, gy = pen_y - g.top;
-      // keep only glyphs that can touch the frame (the reference bounds-checks per pixel, :98)
-      if (gx < W && gy < H && gx + g.width > 0 && gy + g.rows > 0) {
-        out->push_back(nes_placed_glyph{gx, gy, (int32_t)ch, 0});
+      const int gx = pen_x + g.left, gy = pen_y - g.top;  // view coordinates
+      // keep only the part of the bitmap inside the view (the reference bounds-checks per pixel, :98)
+      const int p0 = gx < 0 ? -gx : 0, q0 = gy < 0 ? -gy : 0;
+      const int p1 = gx + g.width > cx1 ? cx1 - gx : g.width, q1 = gy + g.rows > cy1 ? cy1 - gy : g.rows;
+      if (p0 < p1 && q0 < q1) {
+        out->push_back(nes_placed_glyph{vx + gx, vy + gy, (int32_t)ch, 0, p0, q0, p1 - p0, q1 - q0});
         placed++;
       }
     }
     pen_x += g.advance;  // render_text.cc:109
   }
   return placed;
+}
+
+void build_masks(HostAtlas *atlas) {
+  atlas->mask.clear();
+  for (HostGlyph &g : atlas->glyph) {
+    g.wpr = (g.width + 31) / 32;
+    g.mask_off = (uint32_t)atlas->mask.size();
+    if (g.width <= 0 || g.rows <= 0) { g.wpr = 0; continue; }
+    atlas->mask.resize(atlas->mask.size() + (size_t)g.wpr * g.rows, 0u);
+    for (int q = 0; q < g.rows; q++)
+      for (int p = 0; p < g.width; p++)
+        if (atlas->coverage[g.offset + (size_t)q * g.pitch + p]) atlas->mask[g.mask_off + (size_t)q * g.wpr + (p >> 5)] |= 1u << (p & 31);
+  }
 }
 
 // ---- FreeType through dlopen (public API, LP64 layouts of freetype.h / ftimage.h) ----
@@ -150,7 +174,10 @@ int rasterise_font(const char *freetype_so, const char *font_path, HostAtlas *at
     // the reference passes a (signed) char: bytes >= 0x80 become huge code points -> .notdef
     const int rc = load_char(face, (unsigned long)(char)c, kFtLoadRender);
     const FtGlyphSlot *slot = face->glyph;
-    if (rc != 0 && slot->bitmap.buffer == nullptr) continue;
+    // a failed load leaves the slot holding the previous code's bitmap (the reference would re-stamp whatever
+    // the previous character of the string left there, render_text.cc:88-93: not reproducible from a static
+    // atlas): store an empty glyph with no advance -- a documented deviation
+    if (rc != 0) continue;
     g.width = (int)slot->bitmap.width;
     g.rows = (int)slot->bitmap.rows;
     g.left = slot->bitmap_left;

@@ -101,11 +101,16 @@ def algorithmic_bytes(wl: dict) -> int:
 
 
 def text_runs(wl: dict, f: int):
+    """(position, text[, view]) runs of frame f.  A view (x, y, w, h) makes that sub-rectangle the frame the
+    reference's render_string_to_frame sees (nes_text_run.view_*): config 3 stamps one 4-string set per eye."""
     from .api import RENDER_POSITION_LEFT_TOP
     if wl["text"] == "reference":
         return reference_strings(index=f)
-    if wl["text"] == "reference_sbs":  # one set per eye; the right eye's set lands in the right half via a wide left margin
-        return reference_strings(index=f)  # placement arithmetic is per frame; the SBS frame carries one set (documented)
+    if wl["text"] == "reference_sbs":  # SURVEY.md §8 d config 3: two 4-string sets, one per half
+        half = wl["w"] // 2
+        left = [(p, t, (0, 0, half, wl["h"])) for p, t in reference_strings(index=f, is_left=True)]
+        right = [(p, t, (half, 0, half, wl["h"])) for p, t in reference_strings(index=f, is_left=False)]
+        return left + right
     if wl["text"] == "dense":
         return [(RENDER_POSITION_LEFT_TOP, dense_text())]
     return []

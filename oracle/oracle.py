@@ -493,3 +493,39 @@ def reference_strings(index: int = 0, timestamp: str = "12:34:56.789", is_left: 
         (POS_LEFT_TOP, timestamp.encode()),
         (POS_RIGHT_TOP, b"direction=left" if is_left else b"direction=right"),
     ]
+
+
+# --------------------------------------------------------------------------
+# one whole frame of the path, the way the reference would run it
+# --------------------------------------------------------------------------
+def stamp_runs(surface: np.ndarray, runs, fmt: str, port: "Port", glyphs: "GlyphTable | None" = None, ref: "Ref | None" = None, tctx=None) -> None:
+    """render_string_to_frame (render_text.cc:35-111) for every run, in call order, in place.
+    A run is (position, text) or (position, text, (x, y, w, h)): with a view the reference's loop runs on
+    that sub-frame (copied out contiguous -- the loop assumes stride == width*bpp, render_text.cc:101 --
+    stamped, copied back), i.e. once per eye of a side-by-side frame.  With ``ref``/``tctx`` the glyphs come
+    from the real FreeType per character, else from the golden glyph table through the C port."""
+    bpp = surface.shape[2]
+    for r in runs or []:
+        pos, txt = r[0], r[1]
+        view = r[2] if len(r) > 2 and r[2][2] > 0 else None
+        tgt = surface if view is None else np.ascontiguousarray(surface[view[1]:view[1] + view[3], view[0]:view[0] + view[2]])
+        if ref is not None:
+            ref.text_render(tctx, tgt, pos, txt) if bpp == 3 else ref.text_render4(tctx, tgt, pos, txt, fmt)
+        else:
+            port.render_string(tgt, pos, txt, glyphs) if bpp == 3 else port.render_string4(tgt, pos, txt, glyphs, fmt)
+        if view is not None:
+            surface[view[1]:view[1] + view[3], view[0]:view[0] + view[2]] = tgt
+
+
+def expected_frame(srcs, fmt: str, runs, wd: int, hd: int, port: "Port", glyphs: "GlyphTable | None" = None, ref: "Ref | None" = None, tctx=None, flags: int = PARITY_FLAGS):
+    """[depth composite (C port: the reference has none)] -> overlays -> scene and depth
+    conversion (type_managers.cc:143-155).  srcs: [(pixels [h,w,bpp], depth [h,w])].  With ``ref`` the text
+    and the conversion run in the real FreeType / libswscale, else in the port.  -> (Yuv scene, Yuv depth)"""
+    if len(srcs) > 1:
+        comp, cdep = port.composite([s[0] for s in srcs], [s[1] for s in srcs], fmt)
+    else:
+        comp, cdep = np.ascontiguousarray(srcs[0][0]).copy(), np.ascontiguousarray(srcs[0][1])
+    stamp_runs(comp, runs, fmt, port, glyphs, ref, tctx)
+    if ref is not None:
+        return ref.sws_convert(comp, fmt, wd, hd, flags=flags), ref.sws_convert(cdep, "gray", wd, hd, flags=flags)
+    return port.rgb_to_yuv420p(comp, fmt, wd, hd), port.gray_to_yuv420p(cdep, wd, hd)

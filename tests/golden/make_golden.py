@@ -64,6 +64,18 @@ def main():
         s = R.sws_convert(surf, "rgb24")
         out["overlay"].append({"size": [w, h], "stamped": int((surf != O.synth_rgb(w, h)).any(axis=2).sum()), "stamp_calls": int(stamped),
                                "rgb": sha16(surf.tobytes()), "yuv": sha16(s.cropped())})
+    # BASELINE configs at their stated sizes, frame 0 of the benchmark's synthetic workloads
+    # (composite through the C port -- the reference has none --, text through the real FreeType,
+    # conversion through the real libswscale)
+    import ngp_encode_server_b200 as n
+    P = O.Port()
+    out["configs"] = {}
+    for name, wl in n.synth.WORKLOADS.items():
+        srcs = n.synth.make_sources(wl, 0)
+        runs = n.synth.text_runs(wl, 0)
+        sc, dp = O.expected_frame(srcs, wl["fmt"], runs, wl["wd"], wl["hd"], P, ref=R, tctx=t)
+        out["configs"][name] = {"frame": 0, "src": [wl["w"], wl["h"]], "dst": [wl["wd"], wl["hd"]], "fmt": wl["fmt"], "n_src": wl["n_src"],
+                                "n_runs": len(runs), "scene": sha16(sc.cropped()), "depth": sha16(dp.cropped())}
     R.text_free(t)
     # constant frame
     c = R.sws_convert(np.full((16, 16, 3), 200, np.uint8), "rgb24")

@@ -293,6 +293,51 @@ def test_async_ring_and_batch(N, O, port, session):
             session.device_free(p)
 
 
+def test_prepared_batch(N, O, port, glyphs, session):
+    """nes_gpu_batch_prepare / run / free: a descriptor table built once and launched several times back to back
+    (consecutive launches overlap on the device); mixed text / no text frames, every output checked after each round
+    of runs with fresh output buffers (zeroed in between)."""
+    w, h = 768, 200
+    n = 6
+    frames = [(O.synth_rgb(w, h, f), O.synth_depth(w, h, f)) for f in range(n)]
+    runs = [O.reference_strings(index=f) if f % 2 == 0 else None for f in range(n)]
+    want = []
+    for f in range(n):
+        sc, dp = O.expected_frame([frames[f]], "rgb24", runs[f], w, h, port, glyphs)
+        want.append((sc.cropped(), dp.cropped()))
+    ysz, csz = N.align32(w) * h, N.align32(w // 2) * (h // 2)
+    fins, fouts, devs = [], [], []
+    for f in range(n):
+        d_rgb, d_dep, d_s, d_d = (session.device_alloc(k) for k in (w * h * 3, w * h, ysz + 2 * csz, ysz + 2 * csz))
+        session.h2d(d_rgb, frames[f][0]); session.h2d(d_dep, frames[f][1])
+        fins.append(N.Session.frame_in("rgb24", w, h, [((d_rgb, w * h * 3), (d_dep, w * h), 0, 0)], mem=N.NES_MEM_DEVICE))
+        fo = N.nes_frame_out(); fo.width, fo.height, fo.mem = w, h, N.NES_MEM_DEVICE
+        for p, (off, ls) in enumerate([(0, N.align32(w)), (ysz, N.align32(w // 2)), (ysz + csz, N.align32(w // 2))]):
+            fo.scene[p], fo.scene_linesize[p], fo.depth[p], fo.depth_linesize[p] = d_s + off, ls, d_d + off, ls
+        fouts.append(fo); devs.append((d_rgb, d_dep, d_s, d_d))
+    b = session.batch_prepare(fins, [r or [] for r in runs], fouts)
+    zero = np.zeros(ysz + 2 * csz, np.uint8)
+    try:
+        for rounds in (1, 5):
+            for f in range(n):
+                session.h2d(devs[f][2], zero); session.h2d(devs[f][3], zero)
+            before = session.launches
+            for _ in range(rounds):
+                session.batch_run(b)
+            session.batch_run(b, sync=True)
+            assert session.launches - before == rounds + 1
+            for f in range(n):
+                sc, dp = N.FrameManager(N.FrameContext(w, h, "yuv420p")), N.FrameManager(N.FrameContext(w, h, "yuv420p"))
+                session.d2h(sc.buffer, devs[f][2]); session.d2h(dp.buffer, devs[f][3])
+                assert sc.cropped() == want[f][0], (f, first_diff(sc.cropped(), want[f][0]))
+                assert dp.cropped() == want[f][1], f
+    finally:
+        session.batch_free(b)
+        for d in devs:
+            for p in d:
+                session.device_free(p)
+
+
 def test_reference_call_sequence(N, O, port, glyphs, session):
     """The reference's own flow (server.cpp:172-194 -> encode.cpp:55-98) through the mirrored
     classes: wire bytes -> RenderedFrame -> 4x render_string_to_frame -> convert_frame."""
@@ -324,6 +369,50 @@ def test_reference_call_sequence(N, O, port, glyphs, session):
         assert dst.cropped() == port.gray_to_yuv420p(dep).cropped()
     finally:
         s.close()
+
+
+# ------------------------------------------------------------------ BASELINE configs at their stated sizes
+@pytest.mark.parametrize("name", ["c2_1080p_2src_composite", "c3_7680x2160_sbs", "c4_1080p_sessions", "c5_4k_4src_to_1440p", "4k_rgb24"])
+def test_config_size_golden(N, O, port, glyphs, session, golden, name):
+    """Every BASELINE config at full size, frame 0 of the benchmark's own synthetic workload, through the C ABI
+    with host buffers: the hashes are the real libswscale / FreeType ones (tests/golden/make_golden.py) and the
+    planes equal the port byte for byte.  Config 3 carries one overlay set per eye (text run views), config 5 is
+    4 x (4K RGBA + depth) -> composite -> dense overlay -> 2560x1440."""
+    c, wl = golden["configs"][name], N.synth.WORKLOADS[name]
+    srcs, runs = N.synth.make_sources(wl, c["frame"]), N.synth.text_runs(wl, c["frame"])
+    sc, dp = run_gpu(N, session, wl["fmt"], srcs, wl["w"], wl["h"], wl["wd"], wl["hd"], runs=runs, pinned=True)
+    want_s, want_d = O.expected_frame(srcs, wl["fmt"], runs, wl["wd"], wl["hd"], port, glyphs)
+    assert sc.cropped() == want_s.cropped(), first_diff(sc.cropped(), want_s.cropped())
+    assert dp.cropped() == want_d.cropped(), first_diff(dp.cropped(), want_d.cropped())
+    assert sha16(sc.cropped()) == c["scene"] and sha16(dp.cropped()) == c["depth"]
+
+
+def test_text_run_views(N, O, port, glyphs, session):
+    """nes_text_run.view_*: pen placement and clipping relative to a sub-rectangle (an eye of a side-by-side
+    frame); text that runs over the view's edge must not spill into the neighbouring eye, views partly outside
+    the frame are cut to it."""
+    w, h = 1024, 288
+    rgb = O.synth_rgb(w, h, 4)
+    long_line = b"a long line that certainly runs over the right edge of a 512 pixel wide eye, and then some more"
+    runs = [(O.POS_RIGHT_TOP, long_line, (0, 0, 512, h)), (O.POS_LEFT_BOTTOM, b"left eye", (0, 0, 512, h)),
+            (O.POS_CENTER, O.format_matrix_text(O.KINITIAL_CAMERA_MATRIX), (512, 0, 512, h)), (O.POS_RIGHT_TOP, long_line, (512, 0, 512, h)),
+            (O.POS_LEFT_TOP, b"odd view", (301, 33, 333, 111)), (O.POS_RIGHT_BOTTOM, b"view sticking out", (900, 200, 400, 300)),
+            (O.POS_LEFT_TOP, b"whole frame")]
+    surf = np.ascontiguousarray(rgb.copy())
+    # the last view is cut to the frame for the oracle (pen placement still uses the full 400 x 300 view)
+    for r in runs:
+        if len(r) > 2 and r[2][0] + r[2][2] > w:
+            x, y, vw, vh = r[2]
+            big = np.zeros((vh, vw, 3), np.uint8)
+            big[:h - y, :w - x] = surf[y:, x:]
+            port.render_string(big, r[0], r[1], glyphs)
+            surf[y:, x:] = big[:h - y, :w - x]
+        else:
+            O.stamp_runs(surf, [r], "rgb24", port, glyphs)
+    sc, _ = run_gpu(N, session, "rgb24", [(rgb, None)], w, h, runs=runs, want_depth=False)
+    want = port.rgb_to_yuv420p(surf, "rgb24")
+    assert sc.cropped() == want.cropped(), first_diff(sc.cropped(), want.cropped())
+    assert (surf != rgb).any()
 
 
 # ------------------------------------------------------------------ full BASELINE sizes: properties + golden

@@ -155,6 +155,110 @@ def test_product_unpack_matches_oracle(N, O):
         N.unpack_rendered_frame(bad)
 
 
+def _nesproto():
+    """nesproto.* message classes from the real protobuf runtime: a dynamic FileDescriptorProto that
+    restates /root/reference/proto/nes.proto:1-25 (no protoc in this image)."""
+    pb = pytest.importorskip("google.protobuf")
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    T = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name="nes.proto", package="nesproto", syntax="proto3")
+    cam = fd.message_type.add(name="Camera")
+    cam.field.add(name="is_left", number=2, type=T.TYPE_BOOL, label=T.LABEL_OPTIONAL)
+    cam.field.add(name="width", number=3, type=T.TYPE_UINT32, label=T.LABEL_OPTIONAL)
+    cam.field.add(name="height", number=4, type=T.TYPE_UINT32, label=T.LABEL_OPTIONAL)
+    cam.field.add(name="matrix", number=12, type=T.TYPE_FLOAT, label=T.LABEL_REPEATED)
+    rf = fd.message_type.add(name="RenderedFrame")
+    rf.field.add(name="index", number=1, type=T.TYPE_UINT64, label=T.LABEL_OPTIONAL)
+    rf.field.add(name="camera", number=2, type=T.TYPE_MESSAGE, type_name=".nesproto.Camera", label=T.LABEL_OPTIONAL)
+    rf.field.add(name="is_left", number=3, type=T.TYPE_BOOL, label=T.LABEL_OPTIONAL)
+    rf.field.add(name="frame", number=6, type=T.TYPE_BYTES, label=T.LABEL_OPTIONAL)
+    rf.field.add(name="depth", number=7, type=T.TYPE_BYTES, label=T.LABEL_OPTIONAL)
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = getattr(message_factory, "GetMessageClass", None)
+    if get is None:
+        f = message_factory.MessageFactory(pool)
+        return f.GetPrototype(pool.FindMessageTypeByName("nesproto.Camera")), f.GetPrototype(pool.FindMessageTypeByName("nesproto.RenderedFrame")), pb.__version__
+    return get(pool.FindMessageTypeByName("nesproto.Camera")), get(pool.FindMessageTypeByName("nesproto.RenderedFrame")), pb.__version__
+
+
+def test_product_unpack_of_real_protobuf_messages(N, O):
+    """nes_unpack_rendered_frame against messages serialised by the REAL protobuf runtime (what the renderer
+    sends, server.cpp:172-175), not by the oracle's own packer: proto3 defaults (zero scalars omitted), packed
+    repeated float, fields in shuffled order (concatenated partial messages merge on parse), last-one-wins."""
+    Camera, RenderedFrame, version = _nesproto()
+    rng = np.random.default_rng(42)
+    w, h = 96, 54
+    frame, depth = rng.integers(0, 256, w * h * 3, dtype=np.uint8).tobytes(), rng.integers(0, 256, w * h, dtype=np.uint8).tobytes()
+    cases = [dict(index=0, is_left=False, cam_left=False, w=w, h=h, matrix=O.KINITIAL_CAMERA_MATRIX),
+             dict(index=7, is_left=True, cam_left=True, w=w, h=h, matrix=[0.0] * 12),
+             dict(index=2**63 + 11, is_left=True, cam_left=False, w=w, h=h, matrix=[float(i) - 5.5 for i in range(12)]),
+             dict(index=300, is_left=False, cam_left=True, w=0, h=0, matrix=[])]
+    for c in cases:
+        m = RenderedFrame(index=c["index"], is_left=c["is_left"], frame=frame, depth=depth)
+        m.camera.is_left, m.camera.width, m.camera.height = c["cam_left"], c["w"], c["h"]
+        m.camera.matrix.extend(c["matrix"])
+        wire = m.SerializeToString()
+        # round trip through the real parser first: what we compare against is what protobuf itself reads back
+        back = RenderedFrame.FromString(wire)
+        for prefix in (False, True):
+            msg = (len(wire).to_bytes(8, "little") + wire) if prefix else wire
+            u = N.unpack_rendered_frame(msg, prefix=prefix)
+            assert u["index"] == back.index and u["is_left"] == back.is_left and u["cam_is_left"] == back.camera.is_left
+            assert u["width"] == back.camera.width and u["height"] == back.camera.height
+            assert u["matrix"] == pytest.approx(list(back.camera.matrix), abs=0) and len(u["matrix"]) == len(back.camera.matrix)
+            fo, fl = u["frame"]
+            do, dl = u["depth"]
+            assert msg[fo:fo + fl] == back.frame and msg[do:do + dl] == back.depth
+            assert u["consumed"] == len(msg)
+            o = O.unpack_rendered_frame(msg, prefix=prefix)
+            for k in ("index", "is_left", "cam_is_left", "width", "height", "frame", "depth"):
+                assert u[k] == o[k], k
+    # shuffled field order: serialise single-field messages and concatenate them (protobuf merges on parse);
+    # the camera is split in two partial sub-messages, the index appears twice (last wins)
+    parts = {
+        "index_old": RenderedFrame(index=1).SerializeToString(),
+        "depth": RenderedFrame(depth=depth).SerializeToString(),
+        "cam_a": RenderedFrame(camera=Camera(width=w, matrix=[1.0, 2.0, 3.0])).SerializeToString(),
+        "frame": RenderedFrame(frame=frame).SerializeToString(),
+        "is_left": RenderedFrame(is_left=True).SerializeToString(),
+        "cam_b": RenderedFrame(camera=Camera(height=h, is_left=True, matrix=[4.0])).SerializeToString(),
+        "index": RenderedFrame(index=99).SerializeToString(),
+    }
+    for seed in range(6):
+        order = list(parts)
+        np.random.default_rng(seed).shuffle(order)
+        if order.index("index_old") > order.index("index"):
+            i, j = order.index("index_old"), order.index("index")
+            order[i], order[j] = order[j], order[i]
+        wire = b"".join(parts[k] for k in order)
+        back = RenderedFrame.FromString(wire)
+        u = N.unpack_rendered_frame(wire, prefix=False)
+        assert (u["index"], u["is_left"], u["cam_is_left"], u["width"], u["height"]) == (99, True, True, w, h) == (back.index, back.is_left, back.camera.is_left, back.camera.width, back.camera.height)
+        assert u["matrix"] == list(back.camera.matrix), order
+        fo, fl = u["frame"]
+        do, dl = u["depth"]
+        assert wire[fo:fo + fl] == frame and wire[do:do + dl] == depth
+    # unpacked (non-packed) repeated float is legal wire too: tag 0x65 (field 12, fixed32) per element
+    import struct
+    cam = b"\x18" + bytes([w]) + b"".join(b"\x65" + struct.pack("<f", v) for v in (1.5, -2.5))
+    wire = b"\x12" + bytes([len(cam)]) + cam
+    assert list(RenderedFrame.FromString(wire).camera.matrix) == [1.5, -2.5]
+    assert N.unpack_rendered_frame(wire, prefix=False)["matrix"] == [1.5, -2.5]
+
+
+def test_port_matches_config_size_goldens(N, O, port, glyphs, golden):
+    """The C port (text from the golden glyph table) reproduces, at the BASELINE configs' full sizes, the hashes
+    tests/golden/make_golden.py took from the real libswscale / FreeType: 1080p 2-source composite + overlays,
+    7680x2160 with one overlay set per eye, 1080p sessions, 4 x 4K composite + dense overlay -> 1440p, 4K."""
+    assert set(golden["configs"]) == set(N.synth.WORKLOADS)
+    for name, c in golden["configs"].items():
+        wl = N.synth.WORKLOADS[name]
+        sc, dp = O.expected_frame(N.synth.make_sources(wl, c["frame"]), wl["fmt"], N.synth.text_runs(wl, c["frame"]), wl["wd"], wl["hd"], port, glyphs)
+        assert sha16(sc.cropped()) == c["scene"], name
+        assert sha16(dp.cropped()) == c["depth"], name
+
+
 def test_format_camera_matrix(N, O):
     assert N.format_camera_matrix(O.KINITIAL_CAMERA_MATRIX) == O.format_matrix_text(O.KINITIAL_CAMERA_MATRIX)
     assert N.format_camera_matrix(O.KINITIAL_CAMERA_MATRIX).startswith(b"+1.00000 +0.00000 +0.00000 +0.50000 \n+0.00000 -1.00000")
@@ -168,7 +272,7 @@ def test_abi_exports_every_declared_symbol(N):
     assert declared == set(N.ABI_SYMBOLS), declared ^ set(N.ABI_SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.nes_gpu_abi_version() == 1
+    assert L.nes_gpu_abi_version() == 2
 
 
 def test_ctypes_mirrors_match_the_header(N, tmp_path):
