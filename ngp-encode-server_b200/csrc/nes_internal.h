@@ -38,6 +38,20 @@ constexpr int RS_SMEM_MAX = 200 * 1024;   // one tile must fit this
 constexpr int RS_SMEM_GOAL = 72 * 1024;   // three CTAs per SM
 constexpr int GLYPH_BANDS = 256;          // placed glyphs of a resize job are bucketed by row band (counting sort on the host)
 
+// Strip-organised resize kernel (resize_strips.cu, k_resize_strips): a work unit is one segment (rz_seg_rows
+// destination rows) of one column strip (rz_dw destination columns) of one frame; its source window is at most
+// RZ_BOXW pixels wide (one 4-pixel group per lane) and is walked top to bottom in chunks of RZ_CH source rows through
+// the same TMA sub-stage ring as k_frame_strips; a warp takes a source row from packed pixels to horizontally
+// filtered 15-bit samples in RZ_NR-row rings, the vertical pass runs once per chunk.
+constexpr int RZ_BOXW = 128;
+constexpr int RZ_SUB = 8;        // source rows per TMA sub-stage (one per consumer warp)
+constexpr int RZ_CH = 16;        // source rows per chunk
+constexpr int RZ_NR = 48;        // ring rows: >= 31 + the longest vertical filter (RZ_MAX_TV)
+constexpr int RZ_MAX_DW = 128;   // destination columns per strip (4 per lane)
+constexpr int RZ_MAX_TH = 8;     // horizontal taps kept in registers
+constexpr int RZ_MAX_TV = 16;    // vertical taps
+constexpr int RZ_MIN_WD = 64, RZ_MIN_HD = 32;  // smaller destinations go to k_resize_tiles
+
 #if defined(__CUDACC__)
 #define NES_HD __host__ __device__
 #else
@@ -158,6 +172,11 @@ struct alignas(64) DevJob {
   RsLayout rs_lay;          // shared-memory carve-up for the largest tile of this size pair (same bases for every tile)
   const int32_t *rs_win_x;  // [tiles_x][4]: luma source columns [lc0, lc1), chroma source columns [cc0, cc1)
   const int32_t *rs_win_y;  // [tiles_y][4]: luma source rows [lr0, lr1), chroma source rows [cr0, cr1)
+  // k_resize_strips work (general jobs it can take: rz_ok; the others keep their tiles)
+  int32_t rz_ok;
+  int32_t rz_dw;                         // destination columns per strip (multiple of 16, <= RZ_MAX_DW)
+  int32_t rz_strips_x, rz_seg_rows, rz_segs_y;
+  int32_t rz_unit_base[2], rz_units;     // [bpp-3]: units of the rz jobs of that pixel class ahead of this job in the launch
 };
 
 // Launchers (frame_strips.cu, resize_tiles.cu).  jobs: device pointer to n_jobs descriptors.
@@ -169,6 +188,10 @@ int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_j
 void plan_frame_strips(DevJob *jobs_host, int n_jobs, bool text_first = true);
 constexpr int COUNTER_SLOTS = 64;  // work counters of k_frame_strips: one self re-arming {next unit, CTAs done} pair per launch in flight
 int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
+// Assigns rz_seg_rows / rz_unit_base of the jobs k_resize_strips takes (host), then the launch itself.
+void plan_resize_strips(DevJob *jobs_host, int n_jobs);
+int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream);
+int resize_strips_init();
 int kernels_init();  // opt-in shared memory sizes; returns cudaError_t
 int frame_strips_init();
 

@@ -1,0 +1,764 @@
+// resize_strips.cu -- k_resize_strips: the bicubic resize path in the strip / ring organisation of
+// k_frame_strips (any size change whose filters fit the limits below; the rest stays with k_resize_tiles).
+//
+// What it computes: libswscale's generic C path as the reference drives it
+// (/root/reference/src/base/video/type_managers.cc:143-155 via rendered_frame.h:24-33, after the overlay of
+// render_text.cc:81-110); integer spec in SURVEY.md Appendix A.3 / A.4, filter tables of csrc/filter.cc:
+//   scene : [depth-select composite] -> glyph stamp -> 14-bit Y / (pair-summed) U,V -> horizontal polyphase
+//           (>>13, 15 bit) -> vertical polyphase (>>19) -> 8-bit planes
+//   depth : GRAY8 -> horizontal polyphase (>>7) -> range compression -> vertical; U = V = 128
+//
+// Shape (HBM-bound in principle; what bounds it in practice is instruction issue, so the organisation is about
+// touching every source pixel once and keeping per-pixel instruction counts low):
+//   * work unit = one SEGMENT (rz_seg_rows destination rows) of one column STRIP (rz_dw destination columns)
+//     of one frame; persistent CTAs take units from a global counter.  The strip's source window is at most
+//     RZ_BOXW = 128 pixels wide: one 4-pixel group per lane;
+//   * the source window is walked top to bottom in CHUNKS of 16 source rows; rows travel through a ring of 8-row
+//     SUB-STAGES filled by the producer warp with 2D tensor-map TMA copies (packed pixels and GRAY8 depth of every
+//     staged source; SASS UTMALDG), exactly like k_frame_strips;
+//   * a consumer warp owns one source row of a sub-stage END TO END: composite select among the staged sources in
+//     registers -> 14-bit Y / U / V and depth bytes into a 1 KB per-warp row buffer -> horizontal pass of that row
+//     (lane = destination column, its taps live in registers for the whole unit) -> 15-bit samples into four
+//     48-row rings (Y, depth, U, V); the sub-stage is released at once;
+//   * one consumer barrier per chunk, then the vertical pass emits every destination row whose taps are now all in
+//     the rings (4 adjacent columns per thread, 16-byte ring loads, 4-byte stores).  The vertical halo is paid once
+//     per segment, not per tile, and nothing is staged twice.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "device_common.cuh"
+#include "nes_internal.h"
+#include "strips_common.cuh"
+
+namespace nes {
+
+namespace {
+
+enum { RM_ROWS = 0, RM_SELECT = 1, RM_MATERIALIZED = 2 };
+
+constexpr int RZ_DEPB = RZ_BOXW;       // bytes of a staged depth row
+constexpr int RZ_ROWBUF = 1024;        // per-warp row buffer: y14 | u14 | v14 (u16, 144 each) | depth bytes (144)
+constexpr int RZ_RB_Y = 0, RZ_RB_U = 288, RZ_RB_V = 576, RZ_RB_D = 864;
+constexpr int RZ_NS_MAX = 8;
+constexpr int RZ_NCTX = 8;
+
+// Everything the consumer warps need to know about one chunk (written by lane 0 of the producer warp).
+struct RzCtx {
+  int32_t last;       // last chunk this CTA processes
+  int32_t first;      // first chunk of a unit: (re)load the horizontal filter registers
+  int32_t unit_end;   // last chunk of a unit: the rings are reused from slot 0 by the next one
+  int32_t mode, stamp, n_src, job, n_staged;
+  int32_t wx0;        // source column of window column 0 (multiple of 16)
+  int32_t yc0, ra, rb;          // source row of chunk-local row 0; rows of this chunk that are needed [ra, rb)
+  int32_t lr0, lr1, cr0, cr1;   // source rows the luma / chroma vertical filters of this unit read
+  int32_t ya, yb, ca, cb;       // destination rows to emit after this chunk (luma, chroma)
+  int32_t rbase;                // ring slot of chunk-local row 0
+  int32_t dx0, dw, cx0, dcw;    // destination strip: luma / chroma columns
+  int32_t half, dep_staged, nv12, rgb_base;
+  int32_t hls, hcs, vls, vcs;   // filter sizes
+  uint32_t a_mask;
+  uint32_t ky[2], ku[2], kv[2];
+  const int16_t *hl_coef, *hc_coef, *vl_coef, *vc_coef;
+  const int32_t *hl_pos, *hc_pos, *vl_pos, *vc_pos;
+  int32_t sys, sus, svs, dys, dus, dvs;
+  uint8_t *sy, *su, *sv, *dy, *du, *dv;  // plane bases (not offset)
+};
+
+struct RzSmem {
+  int ringY, ringD, ringU, ringV, rowbuf, ctx, bar, hits, stage;
+};
+constexpr int RZ_CTX_BYTES = ((int)sizeof(RzCtx) + 15) & ~15;
+__host__ __device__ inline RzSmem rz_smem(int dwp) {
+  RzSmem L;
+  int o = 0;
+  L.ringY = o; o += RZ_NR * dwp * 4;
+  L.ringD = o; o += RZ_NR * dwp * 4;
+  L.ringU = o; o += RZ_NR * (dwp / 2) * 4;
+  L.ringV = o; o += RZ_NR * (dwp / 2) * 4;
+  L.rowbuf = o; o += CONSUMER_WARPS * RZ_ROWBUF;
+  L.ctx = o; o += RZ_NCTX * RZ_CTX_BYTES;
+  L.bar = o; o += 2 * RZ_NS_MAX * 8;
+  L.hits = o; o += STRIP_HITS * (int)sizeof(DevPlaced) + 16;
+  L.stage = (o + 1023) & ~1023;
+  return L;
+}
+
+__device__ __forceinline__ int lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return (int)v;
+}
+__device__ __forceinline__ int lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return (int)v;
+}
+__device__ __forceinline__ int4 lds_v4s(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+// coefficient . colour bytes of one pixel word (k0: bytes 0,1; k1: bytes 2,3; non-colour bytes carry 0)
+__device__ __forceinline__ int dot_px(uint32_t k0, uint32_t k1, uint32_t px, int acc) { return dp2a_hi(k1, px, dp2a_lo(k0, px, acc)); }
+
+__device__ __forceinline__ int job_of_rz_unit(const DevJob *jobs, int n_jobs, int cls, int u) {
+  int lo = 0, hi = n_jobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].rz_unit_base[cls] <= u) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// Depth-select composite of the 4 pixels a lane owns (columns 4*lane..+3 of the window) from the N staged
+// sources: the winner's pixel words and depth bytes (DESIGN.md "composite"; oracle nes_oracle_composite).
+// px / dep: shared addresses of source 0's row; source k's row is k*RZ_SUB rows further.
+template <int ROWB>
+__device__ __forceinline__ void select4(uint32_t px, uint32_t dep, int n_src, uint32_t a_mask, int lane, uint32_t (&p)[4], uint32_t &d4) {
+  uint32_t bd[4];
+  {
+    const uint4 q = lds128(px + lane * 16);
+    const uint32_t dw = lds32(dep + lane * 4);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const bool valid = (w[i] & a_mask) != 0;
+      bd[i] = valid ? __byte_perm(dw, 0u, 0x4440 + i) : 256u;
+      p[i] = valid ? w[i] : 0u;
+    }
+  }
+#pragma unroll
+  for (int k = 1; k < TMA_MAX_SOURCES; k++) {
+    if (k >= n_src) break;
+    const uint4 q = lds128(px + (uint32_t)(k * RZ_SUB) * ROWB + lane * 16);
+    const uint32_t dw = lds32(dep + (uint32_t)(k * RZ_SUB) * RZ_DEPB + lane * 4);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t d = __byte_perm(dw, 0u, 0x4440 + i);
+      const bool take = (w[i] & a_mask) != 0 && d < bd[i];
+      bd[i] = take ? d : bd[i];
+      p[i] = take ? w[i] : p[i];
+    }
+  }
+  const uint32_t lo = __byte_perm(min(bd[0], 255u), min(bd[1], 255u), 0x0040), hi = __byte_perm(min(bd[2], 255u), min(bd[3], 255u), 0x0040);
+  d4 = __byte_perm(lo, hi, 0x5410);
+}
+
+}  // namespace
+
+// T: horizontal taps held in registers (>= the longest horizontal filter of the launch; shorter filters are
+// padded with zero coefficients).
+template <int BPP, int T>
+__global__ void __launch_bounds__(CTA_THREADS, 2)
+k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters, int ns, int slot_bytes, int dwp) {
+  asm volatile("griddepcontrol.launch_dependents;");  // see k_frame_strips: consecutive launches overlap
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int ROWB = RZ_BOXW * BPP;
+  constexpr int NW = CONSUMER_WARPS;
+  const RzSmem L = rz_smem(dwp);
+  uint64_t *s_full = (uint64_t *)(smem + L.bar);
+  uint64_t *s_empty = s_full + RZ_NS_MAX;
+  DevPlaced *s_hits = (DevPlaced *)(smem + L.hits);
+  int *s_nhits = (int *)(s_hits + STRIP_HITS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (tid == 0) {
+    for (int i = 0; i < RZ_NS_MAX; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], NW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // =========================== producer warp ===========================================
+    int cur_u = (int)blockIdx.x, next_u = 0;
+    if (lane == 0) next_u = (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
+    next_u = __shfl_sync(0xffffffffu, next_u, 0);
+    int q = 0, par = 0, round0 = 1;
+    int chunk_it = 0;
+    while (cur_u < total_units) {
+      const int j = job_of_rz_unit(jobs, n_jobs, BPP - 3, cur_u);
+      const DevJob *jp = jobs + j;
+      const int local = cur_u - jp->rz_unit_base[BPP - 3];
+      const int strip = local % jp->rz_strips_x, seg = local / jp->rz_strips_x;
+      const int Wd = jp->Wd, Hd = jp->Hd, S = jp->rz_seg_rows, n_src = jp->n_src;
+      const int cdW = (Wd + 1) >> 1, cdH = (Hd + 1) >> 1;
+      const int half = jp->half;
+      const int dx0 = strip * jp->rz_dw, dw = min(jp->rz_dw, Wd - dx0);
+      const int cx0 = dx0 >> 1, dcw = min((dx0 + dw + 1) >> 1, cdW) - cx0;
+      const int dy0 = seg * S, dy1 = min(dy0 + S, Hd);
+      const int cy0 = dy0 >> 1, cy1 = min((dy1 + 1) >> 1, cdH);
+      const int32_t *vlp = jp->vl.pos, *vcp = jp->vc.pos;
+      const int vls = jp->vl.size, vcs = jp->vc.size;
+      // filter positions are non-decreasing: the unit's source window follows from its first / last samples
+      const int cpos0 = jp->hc.pos[cx0];
+      const int wx0 = min(jp->hl.pos[dx0], half ? 2 * cpos0 : cpos0) & ~15;  // box rows start on 16-byte boundaries
+      const int lr0 = vlp[dy0], lr1 = vlp[dy1 - 1] + vls, cr0 = vcp[cy0], cr1 = vcp[cy1 - 1] + vcs;
+      const int r0 = min(lr0, cr0), r1 = max(lr1, cr1);
+      const int nchunks = (r1 - r0 + RZ_CH - 1) / RZ_CH;
+      const int n_staged = n_src;
+      const int dep_staged = (jp->dy != nullptr) || n_src > 1;
+      const uint32_t tx_bytes = (uint32_t)(n_staged * RZ_SUB) * (uint32_t)(ROWB + (dep_staged ? RZ_DEPB : 0));
+      const TMap *my_map = nullptr;
+      uint32_t my_off = 0;
+      int my_x = 0;
+      if (lane < n_staged) {
+        my_map = &jp->tmap_px[lane]; my_off = (uint32_t)(lane * RZ_SUB) * ROWB; my_x = (wx0 * BPP) >> 2;
+      } else if (dep_staged && lane < 2 * n_staged) {
+        my_map = &jp->tmap_dep[lane - n_staged];
+        my_off = (uint32_t)(n_staged * RZ_SUB) * ROWB + (uint32_t)((lane - n_staged) * RZ_SUB) * RZ_DEPB;
+        my_x = wx0 >> 2;
+      }
+      const int strips256 = (jp->W + STRIP_W - 1) / STRIP_W;
+      const int nbands = (jp->H + (1 << MASK_BAND_SHIFT) - 1) >> MASK_BAND_SHIFT;
+      int ly = dy0, cy = cy0;  // emission cursors
+      int rbase = 0;
+      for (int k = 0; k < nchunks; k++, chunk_it++) {
+        const int yc0 = r0 + k * RZ_CH;
+        const int ra = yc0, rb = min(yc0 + RZ_CH, r1);
+        const bool last_k = (k == nchunks - 1);
+        // destination rows whose last tap row is now staged (positions are non-decreasing: count the leading hits)
+        const int ya = ly, ca = cy;
+        for (;;) {
+          const int c = ly + lane;
+          const bool ok = c < dy1 && (last_k || vlp[c] + vls <= rb);
+          const unsigned b = __ballot_sync(0xffffffffu, ok);
+          const int n = (b == 0xffffffffu) ? 32 : __ffs(~b) - 1;
+          ly += n;
+          if (n < 32) break;
+        }
+        for (;;) {
+          const int c = cy + lane;
+          const bool ok = c < cy1 && (last_k || vcp[c] + vcs <= rb);
+          const unsigned b = __ballot_sync(0xffffffffu, ok);
+          const int n = (b == 0xffffffffu) ? 32 : __ffs(~b) - 1;
+          cy += n;
+          if (n < 32) break;
+        }
+        if (lane == 0) {
+          RzCtx &c = *(RzCtx *)(smem + L.ctx + (chunk_it & (RZ_NCTX - 1)) * RZ_CTX_BYTES);
+          int stamp = 0;
+          if (jp->n_glyphs > 0) {
+            stamp = 1;
+            if (jp->use_mask) {
+              stamp = 0;
+              const int s0 = wx0 / STRIP_W, s1 = min((wx0 + RZ_BOXW - 1) / STRIP_W, strips256 - 1);
+              for (int band = ra >> MASK_BAND_SHIFT; band <= (rb - 1) >> MASK_BAND_SHIFT && band < nbands; band++)
+                for (int st = s0; st <= s1; st++) {
+                  const int bit = band * strips256 + st;
+                  stamp |= (jp->tile_mask[bit >> 5] >> (bit & 31)) & 1u;
+                }
+            }
+          }
+          c.last = last_k && next_u >= total_units;
+          c.first = (k == 0);
+          c.unit_end = last_k;
+          c.stamp = stamp;
+          c.mode = n_src > 1 ? (stamp ? RM_MATERIALIZED : RM_SELECT) : RM_ROWS;
+          c.n_src = n_src; c.job = j; c.n_staged = n_staged;
+          c.wx0 = wx0; c.yc0 = yc0; c.ra = ra; c.rb = rb;
+          c.lr0 = lr0; c.lr1 = lr1; c.cr0 = cr0; c.cr1 = cr1;
+          c.ya = ya; c.yb = ly; c.ca = ca; c.cb = cy;
+          c.rbase = rbase;
+          c.dx0 = dx0; c.dw = dw; c.cx0 = cx0; c.dcw = dcw;
+          c.half = half; c.dep_staged = dep_staged; c.nv12 = jp->nv12; c.rgb_base = jp->rgb_base;
+          c.hls = jp->hl.size; c.hcs = jp->hc.size; c.vls = vls; c.vcs = vcs;
+          c.a_mask = jp->a_off >= 0 ? (0xFFu << (8 * jp->a_off)) : 0xFFFFFFFFu;
+          c.ky[0] = jp->ky[0]; c.ky[1] = jp->ky[1]; c.ku[0] = jp->ku[0]; c.ku[1] = jp->ku[1]; c.kv[0] = jp->kv[0]; c.kv[1] = jp->kv[1];
+          c.hl_coef = jp->hl.coef; c.hc_coef = jp->hc.coef; c.vl_coef = jp->vl.coef; c.vc_coef = jp->vc.coef;
+          c.hl_pos = jp->hl.pos; c.hc_pos = jp->hc.pos; c.vl_pos = vlp; c.vc_pos = vcp;
+          c.sys = jp->sys; c.sus = jp->sus; c.svs = jp->svs; c.dys = jp->dys; c.dus = jp->dus; c.dvs = jp->dvs;
+          c.sy = jp->sy; c.su = jp->su; c.sv = jp->sv; c.dy = jp->dy; c.du = jp->du; c.dv = jp->dv;
+        }
+        __syncwarp();
+#ifdef NES_RZ_DEBUG
+        if (lane < 2 && cur_u < 3) printf("cta %d u %d j %d strip %d seg %d wx0 %d r0 %d r1 %d k %d yc0 %d rb %d ya..yb %d..%d lane %d map %p off %u x %d tx %u ns %d slot %d stage %d dwp %d\n", (int)blockIdx.x, cur_u, j, strip, seg, wx0, r0, r1, k, yc0, rb, ya, ly, lane, (const void *)my_map, my_off, my_x, tx_bytes, ns, slot_bytes, L.stage, dwp);
+#endif
+#pragma unroll 1
+        for (int sub = 0; sub < RZ_CH / RZ_SUB; sub++) {
+          if (!round0) mbar_wait(&s_empty[q], (uint32_t)(par ^ 1));
+          const int ys = yc0 + sub * RZ_SUB;
+          const bool wanted = ys < rb;
+          if (wanted) {
+            if (lane == 0) mbar_arrive_expect_tx(&s_full[q], tx_bytes);
+            __syncwarp();
+            if (my_map) tma_load_2d(smem_base + L.stage + (uint32_t)(q * slot_bytes) + my_off, my_map, my_x, ys, &s_full[q]);
+          } else if (lane == 0) {
+            mbar_arrive(&s_full[q]);
+          }
+          if (++q == ns) { q = 0; par ^= 1; round0 = 0; }
+        }
+        rbase += RZ_CH;
+        if (rbase >= RZ_NR) rbase -= RZ_NR;
+      }
+      cur_u = next_u;
+      if (lane == 0 && cur_u < total_units) next_u = (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
+      next_u = __shfl_sync(0xffffffffu, next_u, 0);
+    }
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) { counters[0] = 0; counters[1] = 0; __threadfence(); }
+    }
+    return;
+  }
+
+  // ============================= consumer warps ===========================================
+  const uint32_t full0 = smem_base + L.bar, empty0 = full0 + RZ_NS_MAX * 8;
+  const uint32_t rowbuf = smem_base + L.rowbuf + warp * RZ_ROWBUF;
+  const uint32_t ringY = smem_base + L.ringY, ringD = smem_base + L.ringD, ringU = smem_base + L.ringU, ringV = smem_base + L.ringV;
+  const int rowbY = dwp * 4, rowbC = (dwp / 2) * 4;
+  // horizontal filters of the current unit: lane = destination column (+32 per slot)
+  int pos_l[4], pos_c[2];
+  int cf_l[4][T], cf_c[2][T];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    pos_l[c] = 0;
+#pragma unroll
+    for (int jj = 0; jj < T; jj++) cf_l[c][jj] = 0;
+  }
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    pos_c[c] = 0;
+#pragma unroll
+    for (int jj = 0; jj < T; jj++) cf_c[c][jj] = 0;
+  }
+  int qc = 0, parc = 0;
+  for (int chunk_it = 0;; chunk_it++) {
+    int q[2], par[2];
+    q[0] = qc; par[0] = parc;
+    q[1] = qc + 1; par[1] = parc;
+    if (q[1] == ns) { q[1] = 0; par[1] ^= 1; }
+    mbar_wait_a(full0 + q[0] * 8, (uint32_t)par[0]);
+    const RzCtx &c = *(const RzCtx *)(smem + L.ctx + (chunk_it & (RZ_NCTX - 1)) * RZ_CTX_BYTES);
+    const int last = c.last, unit_end = c.unit_end;
+    {
+      const uint32_t sb[2] = {smem_base + L.stage + (uint32_t)(q[0] * slot_bytes), smem_base + L.stage + (uint32_t)(q[1] * slot_bytes)};
+      const uint32_t dep_off = (uint32_t)(c.n_staged * RZ_SUB) * ROWB;
+      const int wx0 = c.wx0, yc0 = c.yc0, ra = c.ra, rb = c.rb;
+      const int dw = c.dw, dcw = c.dcw;
+      const bool half = c.half != 0, dep_staged = c.dep_staged != 0;
+      const bool want_depth = c.dy != nullptr;
+      int mode = c.mode;
+
+      if (c.first) {
+        const int hls = c.hls, hcs = c.hcs;
+        const int corg = half ? (wx0 >> 1) : wx0;
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          const int col = lane + 32 * cc;
+          const bool on = col < dw;
+          pos_l[cc] = on ? __ldg(c.hl_pos + c.dx0 + col) - wx0 : 0;
+          const int16_t *cf = c.hl_coef + (size_t)(c.dx0 + (on ? col : 0)) * hls;
+#pragma unroll
+          for (int jj = 0; jj < T; jj++) cf_l[cc][jj] = (on && jj < hls) ? (int)__ldg(cf + jj) : 0;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          const int col = lane + 32 * cc;
+          const bool on = col < dcw;
+          pos_c[cc] = on ? __ldg(c.hc_pos + c.cx0 + col) - corg : 0;
+          const int16_t *cf = c.hc_coef + (size_t)(c.cx0 + (on ? col : 0)) * hcs;
+#pragma unroll
+          for (int jj = 0; jj < T; jj++) cf_c[cc][jj] = (on && jj < hcs) ? (int)__ldg(cf + jj) : 0;
+        }
+      }
+
+      if (mode == RM_MATERIALIZED || c.stamp) {
+        // whole-chunk work on the staged rows: needs both sub-stages
+        mbar_wait_a(full0 + q[1] * 8, (uint32_t)par[1]);
+        if (BPP == 4 && mode == RM_MATERIALIZED) {
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const int y = yc0 + warp + i * RZ_SUB;
+            if (y < ra || y >= rb) continue;
+            const uint32_t px = sb[i] + warp * ROWB, dp = sb[i] + dep_off + warp * RZ_DEPB;
+            uint32_t p[4], d4;
+            select4<ROWB>(px, dp, c.n_src, c.a_mask, lane, p, d4);
+            __syncwarp();
+            sts128(px + lane * 16, p[0], p[1], p[2], p[3]);
+            sts32(dp + lane * 4, d4);
+          }
+          mode = RM_ROWS;
+        }
+        __syncwarp();
+        if (c.stamp) stamp_chunk<BPP, RZ_BOXW>(jobs[c.job], smem + L.stage, qc, ns, slot_bytes, wx0, wx0 + RZ_BOXW, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
+        fence_proxy_async();
+      }
+
+      // ---- per source row: composite -> 14-bit planes (row buffer) -> horizontal pass -> rings ----------
+      {
+        const uint32_t ky0 = c.ky[0], ky1 = c.ky[1], ku0 = c.ku[0], ku1 = c.ku[1], kv0 = c.kv[0], kv1 = c.kv[1];
+        const int rbase = c.rbase;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int r = warp + i * RZ_SUB;
+          const int y = yc0 + r;
+          if (i == 1) mbar_wait_a(full0 + q[1] * 8, (uint32_t)par[1]);
+          if (y >= ra && y < rb) {
+            const uint32_t row = sb[i] + warp * ROWB;
+            const uint32_t drow = sb[i] + dep_off + warp * RZ_DEPB;
+            uint32_t p[4], d4 = 0;
+            if (BPP == 4) {
+              if (mode == RM_SELECT) {
+                select4<ROWB>(row, drow, c.n_src, c.a_mask, lane, p, d4);
+              } else {
+                const uint4 a = lds128(row + lane * 16);
+                p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w;
+                if (dep_staged) d4 = lds32(drow + lane * 4);
+              }
+            } else {
+              // 4 packed 3-byte pixels = 3 words -> pixel words r | g<<8 | b<<16 | junk<<24 (the junk byte has coefficient 0)
+              const uint32_t w0 = lds32(row + lane * 12), w1 = lds32(row + lane * 12 + 4), w2 = lds32(row + lane * 12 + 8);
+              p[0] = w0;
+              p[1] = __funnelshift_r(w0, w1, 24);
+              p[2] = __funnelshift_r(w1, w2, 16);
+              p[3] = w2 >> 8;
+              if (dep_staged) d4 = lds32(drow + lane * 4);
+            }
+            const bool need_l = y >= c.lr0 && y < c.lr1, need_c = y >= c.cr0 && y < c.cr1;
+            if (need_l) {
+              int yv[4];
+#pragma unroll
+              for (int k = 0; k < 4; k++) yv[k] = dot_px(ky0, ky1, p[k], (32 << 14) + (1 << 8)) >> 9;
+              sts64(rowbuf + RZ_RB_Y + lane * 8, pack16(yv[0], yv[1]), pack16(yv[2], yv[3]));
+              if (want_depth) sts32(rowbuf + RZ_RB_D + lane * 4, d4);
+            }
+            if (need_c) {
+              if (half) {
+                int u[2], v[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                  u[k] = dot_px(ku0, ku1, p[2 * k + 1], dot_px(ku0, ku1, p[2 * k], C_BIAS)) >> 10;
+                  v[k] = dot_px(kv0, kv1, p[2 * k + 1], dot_px(kv0, kv1, p[2 * k], C_BIAS)) >> 10;
+                }
+                sts32(rowbuf + RZ_RB_U + lane * 4, pack16(u[0], u[1]));
+                sts32(rowbuf + RZ_RB_V + lane * 4, pack16(v[0], v[1]));
+              } else {
+                int u[4], v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  u[k] = dot_px(ku0, ku1, p[k], C1_BIAS) >> 9;
+                  v[k] = dot_px(kv0, kv1, p[k], C1_BIAS) >> 9;
+                }
+                sts64(rowbuf + RZ_RB_U + lane * 8, pack16(u[0], u[1]), pack16(u[2], u[3]));
+                sts64(rowbuf + RZ_RB_V + lane * 8, pack16(v[0], v[1]), pack16(v[2], v[3]));
+              }
+            }
+            __syncwarp();
+            int slot = rbase + r;
+            if (slot >= RZ_NR) slot -= RZ_NR;
+            // ---- horizontal pass of this row: hScale16To15 (>>13, clamp) / hScale8To15 (>>7) + range compression
+            if (need_l) {
+#pragma unroll
+              for (int cc = 0; cc < 4; cc++) {
+                const int col = lane + 32 * cc;
+                if (32 * cc < dw) {  // warp-uniform
+                  const uint32_t a = rowbuf + RZ_RB_Y + pos_l[cc] * 2;
+                  int v = 0;
+#pragma unroll
+                  for (int jj = 0; jj < T; jj++) v += lds_u16(a + 2 * jj) * cf_l[cc][jj];
+                  v = min(v >> 13, 32767);
+                  if (col < dw) sts32(ringY + slot * rowbY + col * 4, (uint32_t)v);
+                  if (want_depth) {
+                    const uint32_t ad = rowbuf + RZ_RB_D + pos_l[cc];
+                    int d = 0;
+#pragma unroll
+                    for (int jj = 0; jj < T; jj++) d += lds_u8(ad + jj) * cf_l[cc][jj];
+                    d = min(d >> 7, 32767);
+                    d = (d * 14071 + 33561472) >> 14;
+                    if (col < dw) sts32(ringD + slot * rowbY + col * 4, (uint32_t)d);
+                  }
+                }
+              }
+            }
+            if (need_c) {
+#pragma unroll
+              for (int cc = 0; cc < 2; cc++) {
+                const int col = lane + 32 * cc;
+                if (32 * cc < dcw) {
+                  const uint32_t au = rowbuf + RZ_RB_U + pos_c[cc] * 2, av = rowbuf + RZ_RB_V + pos_c[cc] * 2;
+                  int u = 0, v = 0;
+#pragma unroll
+                  for (int jj = 0; jj < T; jj++) { u += lds_u16(au + 2 * jj) * cf_c[cc][jj]; v += lds_u16(av + 2 * jj) * cf_c[cc][jj]; }
+                  u = min(u >> 13, 32767);
+                  v = min(v >> 13, 32767);
+                  if (col < dcw) { sts32(ringU + slot * rowbC + col * 4, (uint32_t)u); sts32(ringV + slot * rowbC + col * 4, (uint32_t)v); }
+                }
+              }
+            }
+          }
+          __syncwarp();  // the row buffer is rewritten by this warp's next row
+          if (lane == 0) mbar_arrive_a(empty0 + q[i] * 8);
+        }
+      }
+      consumer_sync();
+
+      // ---- vertical pass: every destination row whose taps are all in the rings ---------------------
+      {
+        const int rbase = c.rbase;
+        // (the launch only takes jobs with 16-byte aligned destination planes: whole groups go out as words)
+        // luma (+ depth luma, same filter)
+        {
+          const int ya = c.ya, yb = c.yb, vls = c.vls;
+          const int gl = (dw + 3) >> 2;
+          const int total = (yb - ya) * gl;
+          const uint32_t rcp = (65536u + gl - 1) / gl;
+          uint8_t *const sy = c.sy + c.dx0, *const dyp = want_depth ? c.dy + c.dx0 : nullptr;
+          for (int idx = tid; idx < total; idx += 32 * NW) {
+            const int ry = (int)(((uint32_t)idx * rcp) >> 16), g = idx - ry * gl;
+            const int dyy = ya + ry;
+            const int pos = __ldg(c.vl_pos + dyy);
+            int slot = rbase + pos - yc0;
+            if (slot < 0) slot += RZ_NR;
+            int a[4], d[4];
+            if (vls == 1) {
+              const int4 w = lds_v4s(ringY + slot * rowbY + g * 16);
+              a[0] = (w.x + 64) >> 7; a[1] = (w.y + 64) >> 7; a[2] = (w.z + 64) >> 7; a[3] = (w.w + 64) >> 7;
+              if (want_depth) {
+                const int4 e = lds_v4s(ringD + slot * rowbY + g * 16);
+                d[0] = (e.x + 64) >> 7; d[1] = (e.y + 64) >> 7; d[2] = (e.z + 64) >> 7; d[3] = (e.w + 64) >> 7;
+              }
+            } else {
+              const int16_t *cf = c.vl_coef + (size_t)dyy * vls;
+              a[0] = a[1] = a[2] = a[3] = 64 << 12;
+              d[0] = d[1] = d[2] = d[3] = 64 << 12;
+              for (int jj = 0; jj < vls; jj++) {
+                const int k = (int)__ldg(cf + jj);
+                const int4 w = lds_v4s(ringY + slot * rowbY + g * 16);
+                a[0] += w.x * k; a[1] += w.y * k; a[2] += w.z * k; a[3] += w.w * k;
+                if (want_depth) {
+                  const int4 e = lds_v4s(ringD + slot * rowbY + g * 16);
+                  d[0] += e.x * k; d[1] += e.y * k; d[2] += e.z * k; d[3] += e.w * k;
+                }
+                if (++slot == RZ_NR) slot = 0;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; k++) { a[k] >>= 19; d[k] >>= 19; }
+            }
+            const uint32_t yw = clip8_relu(a[0]) | (clip8_relu(a[1]) << 8) | (clip8_relu(a[2]) << 16) | (clip8_relu(a[3]) << 24);
+            uint8_t *o = sy + (size_t)dyy * c.sys + 4 * g;
+            if (4 * g + 4 <= dw) stg32(o, yw);
+            else
+              for (int k = 0; 4 * g + k < dw; k++) o[k] = (uint8_t)(yw >> (8 * k));
+            if (want_depth) {
+              const uint32_t gw = clip8_relu(d[0]) | (clip8_relu(d[1]) << 8) | (clip8_relu(d[2]) << 16) | (clip8_relu(d[3]) << 24);
+              uint8_t *od = dyp + (size_t)dyy * c.dys + 4 * g;
+              if (4 * g + 4 <= dw) stg32(od, gw);
+              else
+                for (int k = 0; 4 * g + k < dw; k++) od[k] = (uint8_t)(gw >> (8 * k));
+            }
+          }
+        }
+        // chroma (U and V share the filter); depth chroma is constant 128
+        {
+          const int ca = c.ca, cb = c.cb, vcs = c.vcs;
+          const int gc = (dcw + 3) >> 2;
+          const int total = (cb - ca) * gc;
+          const uint32_t rcp = (65536u + gc - 1) / gc;
+          const bool nv12 = c.nv12 != 0;
+          for (int idx = tid; idx < total; idx += 32 * NW) {
+            const int ry = (int)(((uint32_t)idx * rcp) >> 16), g = idx - ry * gc;
+            const int cyy = ca + ry;
+            const int pos = __ldg(c.vc_pos + cyy);
+            int slot = rbase + pos - yc0;
+            if (slot < 0) slot += RZ_NR;
+            int u[4], v[4];
+            if (vcs == 1) {
+              const int4 w = lds_v4s(ringU + slot * rowbC + g * 16), e = lds_v4s(ringV + slot * rowbC + g * 16);
+              u[0] = (w.x + 64) >> 7; u[1] = (w.y + 64) >> 7; u[2] = (w.z + 64) >> 7; u[3] = (w.w + 64) >> 7;
+              v[0] = (e.x + 64) >> 7; v[1] = (e.y + 64) >> 7; v[2] = (e.z + 64) >> 7; v[3] = (e.w + 64) >> 7;
+            } else {
+              const int16_t *cf = c.vc_coef + (size_t)cyy * vcs;
+              u[0] = u[1] = u[2] = u[3] = 64 << 12;
+              v[0] = v[1] = v[2] = v[3] = 64 << 12;
+              for (int jj = 0; jj < vcs; jj++) {
+                const int k = (int)__ldg(cf + jj);
+                const int4 w = lds_v4s(ringU + slot * rowbC + g * 16), e = lds_v4s(ringV + slot * rowbC + g * 16);
+                u[0] += w.x * k; u[1] += w.y * k; u[2] += w.z * k; u[3] += w.w * k;
+                v[0] += e.x * k; v[1] += e.y * k; v[2] += e.z * k; v[3] += e.w * k;
+                if (++slot == RZ_NR) slot = 0;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; k++) { u[k] >>= 19; v[k] >>= 19; }
+            }
+            const uint32_t ub = clip8_relu(u[0]) | (clip8_relu(u[1]) << 8) | (clip8_relu(u[2]) << 16) | (clip8_relu(u[3]) << 24);
+            const uint32_t vb = clip8_relu(v[0]) | (clip8_relu(v[1]) << 8) | (clip8_relu(v[2]) << 16) | (clip8_relu(v[3]) << 24);
+            const bool full = 4 * g + 4 <= dcw;
+            if (nv12) {
+              // U0 V0 U1 V1 | U2 V2 U3 V3: chroma column x sits at byte 2x of the UV row
+              const uint32_t w0 = __byte_perm(ub, vb, 0x5140), w1 = __byte_perm(ub, vb, 0x7362);
+              uint8_t *o = c.su + (size_t)cyy * c.sus + 2 * c.cx0 + 8 * g;
+              if (full) stg64(o, w0, w1);
+              else
+                for (int k = 0; 4 * g + (k >> 1) < dcw; k++) o[k] = (uint8_t)((k < 4 ? w0 : w1) >> (8 * (k & 3)));
+              if (want_depth) {
+                uint8_t *od = c.du + (size_t)cyy * c.dus + 2 * c.cx0 + 8 * g;
+                if (full) stg64(od, 0x80808080u, 0x80808080u);
+                else
+                  for (int k = 0; 4 * g + (k >> 1) < dcw; k++) od[k] = 128;
+              }
+            } else {
+              uint8_t *ou = c.su + (size_t)cyy * c.sus + c.cx0 + 4 * g, *ov = c.sv + (size_t)cyy * c.svs + c.cx0 + 4 * g;
+              if (full) { stg32(ou, ub); stg32(ov, vb); }
+              else
+                for (int k = 0; 4 * g + k < dcw; k++) { ou[k] = (uint8_t)(ub >> (8 * k)); ov[k] = (uint8_t)(vb >> (8 * k)); }
+              if (want_depth) {
+                uint8_t *du_ = c.du + (size_t)cyy * c.dus + c.cx0 + 4 * g, *dv_ = c.dv + (size_t)cyy * c.dvs + c.cx0 + 4 * g;
+                if (full) { stg32(du_, 0x80808080u); stg32(dv_, 0x80808080u); }
+                else
+                  for (int k = 0; 4 * g + k < dcw; k++) { du_[k] = 128; dv_[k] = 128; }
+              }
+            }
+          }
+        }
+      }
+    }
+    if (last) break;
+    if (unit_end) consumer_sync();  // the next unit's first rows reuse ring slots this vertical pass was reading
+    qc = q[1] + 1; parc = par[1];
+    if (qc == ns) { qc = 0; parc ^= 1; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side: planning and launch
+// ---------------------------------------------------------------------------
+static int g_rz_sms = 0, g_rz_smem_sm = 0, g_rz_reserved = 1024, g_rz_optin = 0;
+static bool g_rz_pdl = true;
+
+template <int BPP, int T>
+static cudaError_t rz_set_attr() {
+  return cudaFuncSetAttribute(k_resize_strips<BPP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_rz_optin);
+}
+
+int resize_strips_init() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaError_t e = cudaDeviceGetAttribute(&g_rz_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaDeviceGetAttribute(&g_rz_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  if (e != cudaSuccess) return (int)e;
+  cudaDeviceGetAttribute(&g_rz_reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+  e = cudaDeviceGetAttribute(&g_rz_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e != cudaSuccess) return (int)e;
+  if ((e = rz_set_attr<3, 4>()) != cudaSuccess || (e = rz_set_attr<3, 6>()) != cudaSuccess || (e = rz_set_attr<3, 8>()) != cudaSuccess ||
+      (e = rz_set_attr<4, 4>()) != cudaSuccess || (e = rz_set_attr<4, 6>()) != cudaSuccess || (e = rz_set_attr<4, 8>()) != cudaSuccess)
+    return (int)e;
+  if (const char *v = getenv("NES_NO_PDL")) g_rz_pdl = atoi(v) == 0;
+  return 0;
+}
+
+struct RzConfig {
+  int ns, slot, smem, ctas, dwp, taps;
+};
+// Launch shape of one pixel class: rings sized for the widest destination strip of the launch, sub-stage slots
+// for the most sources; two CTAs per SM when two sub-stages (one chunk) fit half an SM, else one CTA with a deeper ring.
+static RzConfig rz_config(const DevJob *jobs, int n_jobs, int bpp) {
+  int dwp = 16, staged = 1, taps = 1;
+  for (int j = 0; j < n_jobs; j++) {
+    const DevJob &jb = jobs[j];
+    if (!jb.rz_ok || jb.bpp != bpp) continue;
+    dwp = std::max(dwp, (jb.rz_dw + 15) & ~15);
+    staged = std::max(staged, jb.n_src);
+    taps = std::max(taps, std::max(jb.hl.size, jb.hc.size));
+  }
+  const RzSmem L = rz_smem(dwp);
+  const int slot = staged * RZ_SUB * (RZ_BOXW * bpp + RZ_DEPB);
+  const int smem_sm = g_rz_smem_sm > 0 ? g_rz_smem_sm : 233472;
+  RzConfig c{0, slot, 0, 0, dwp, taps <= 4 ? 4 : taps <= 6 ? 6 : 8};
+  for (int ctas = 2; ctas >= 1; ctas--) {
+    const int budget = std::min(smem_sm / ctas - g_rz_reserved, g_rz_optin > 0 ? g_rz_optin : 232448) - L.stage;
+    const int ns = std::min(RZ_NS_MAX, budget / slot);
+    if (ns >= 2) { c.ns = ns; c.ctas = ctas; c.smem = L.stage + ns * slot; break; }
+  }
+  return c;
+}
+
+// One segment height (destination rows) per pixel class: the vertical halo (about the longest vertical filter, in
+// source rows, per segment) against the one-unit tail of the persistent grid.  Unit numbering: a prefix sum over the
+// launch in which the jobs of the other class (and the jobs k_resize_tiles keeps) take no units.
+void plan_resize_strips(DevJob *jobs, int n_jobs) {
+  const int sms = g_rz_sms > 0 ? g_rz_sms : 148;
+  for (int cls = 0; cls < 2; cls++) {
+    const int bpp = 3 + cls;
+    bool any = false;
+    for (int j = 0; j < n_jobs; j++) any = any || (jobs[j].rz_ok && jobs[j].bpp == bpp);
+    int best_s = 32;
+    if (any) {
+      const RzConfig cfg = rz_config(jobs, n_jobs, bpp);
+      const int grid = sms * std::max(cfg.ctas, 1);
+      double best_cost = 1e30;
+      for (int S = 16; S <= 512; S *= 2) {
+        double work = 0, unit_max = 0;
+        long units = 0;
+        for (int j = 0; j < n_jobs; j++) {
+          const DevJob &jb = jobs[j];
+          if (!jb.rz_ok || jb.bpp != bpp) continue;
+          const int strips = (jb.Wd + jb.rz_dw - 1) / jb.rz_dw, segs = (jb.Hd + S - 1) / S;
+          const double ratio = (double)jb.H / jb.Hd;
+          const double halo = std::max(jb.vl.size, jb.vc.size);
+          units += (long)strips * segs;
+          work += (double)strips * (jb.H + segs * halo);
+          unit_max = std::max(unit_max, S * ratio + halo);
+        }
+        const double cost = units <= grid ? unit_max : work / grid + 0.7 * unit_max;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_s = S; }
+      }
+    }
+    int base = 0;
+    for (int j = 0; j < n_jobs; j++) {
+      DevJob &jb = jobs[j];
+      jb.rz_unit_base[cls] = base;
+      if (!jb.rz_ok || jb.bpp != bpp) continue;
+      jb.rz_seg_rows = best_s;
+      jb.rz_strips_x = (jb.Wd + jb.rz_dw - 1) / jb.rz_dw;
+      jb.rz_segs_y = (jb.Hd + best_s - 1) / best_s;
+      jb.rz_units = jb.rz_strips_x * jb.rz_segs_y;
+      base += jb.rz_units;
+    }
+  }
+}
+
+template <int BPP, int T>
+static cudaError_t rz_launch_one(int grid, const RzConfig &c, cudaStream_t st, const DevJob *jobs, int n_jobs, int total, uint32_t *ctr) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(CTA_THREADS);
+  cfg.dynamicSmemBytes = (size_t)c.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_rz_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_resize_strips<BPP, T>, jobs, n_jobs, total, ctr, c.ns, c.slot, c.dwp);
+}
+
+int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream) {
+  int launches = 0;
+  for (int bpp = 3; bpp <= 4; bpp++) {
+    int total = 0;
+    for (int j = 0; j < n_jobs; j++)
+      if (jobs_host[j].rz_ok && jobs_host[j].bpp == bpp) total += jobs_host[j].rz_units;
+    if (total == 0) continue;
+    const RzConfig c = rz_config(jobs_host, n_jobs, bpp);
+    if (c.ns < 2) return -1;
+    const int grid = std::min(total, g_rz_sms * c.ctas);
+    uint32_t *ctr = counters + 2 * ((*seq)++ % COUNTER_SLOTS);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (bpp == 3) e = c.taps == 4 ? rz_launch_one<3, 4>(grid, c, st, jobs_dev, n_jobs, total, ctr) : c.taps == 6 ? rz_launch_one<3, 6>(grid, c, st, jobs_dev, n_jobs, total, ctr) : rz_launch_one<3, 8>(grid, c, st, jobs_dev, n_jobs, total, ctr);
+    else e = c.taps == 4 ? rz_launch_one<4, 4>(grid, c, st, jobs_dev, n_jobs, total, ctr) : c.taps == 6 ? rz_launch_one<4, 6>(grid, c, st, jobs_dev, n_jobs, total, ctr) : rz_launch_one<4, 8>(grid, c, st, jobs_dev, n_jobs, total, ctr);
+    if (e != cudaSuccess) return -1;
+    launches++;
+  }
+  return launches;
+}
+
+}  // namespace nes

@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_resize_tiles(const DevJob *__
   const DevJob *jp = find_job(jobs, n_jobs, blockIdx.x, &tile);
   // a launch serves the jobs of one pixel class that share one shared-memory carve-up (kernel parameter:
   // constant-bank operands; derived per tile in registers it cost 6 % of the kernel's instructions)
-  if (!jp->general || jp->bpp != BPP || !same_layout(jp->rs_lay, L)) return;
+  if (!jp->general || jp->rz_ok || jp->bpp != BPP || !same_layout(jp->rs_lay, L)) return;
   const DevJob &jb = *jp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARP = RS_THREADS / 32;
@@ -564,6 +564,7 @@ static int g_resize_smem_cap = 0;
 int kernels_init() {
   cudaError_t e;
   if (int r = frame_strips_init()) return r;
+  if (int r = resize_strips_init()) return r;
   g_resize_smem_cap = RS_SMEM_MAX;
   e = cudaFuncSetAttribute(k_resize_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_resize_smem_cap);
   if (e != cudaSuccess) return (int)e;
@@ -581,11 +582,11 @@ int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_j
   int launches = 0;
   for (int j = 0; j < n_jobs; j++) {
     const DevJob &jb = jobs_host[j];
-    if (!jb.general) continue;
+    if (!jb.general || jb.rz_ok) continue;
     bool seen = false;
     for (int i = 0; i < j && !seen; i++) {
       const DevJob &o = jobs_host[i];
-      seen = o.general && o.bpp == jb.bpp && same_layout(o.rs_lay, jb.rs_lay);
+      seen = o.general && !o.rz_ok && o.bpp == jb.bpp && same_layout(o.rs_lay, jb.rs_lay);
     }
     if (seen) continue;
     const int sm = (jb.rs_lay.total + 1023) & ~1023;

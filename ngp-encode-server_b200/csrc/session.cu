@@ -46,6 +46,7 @@ struct FilterSet {  // device tables for one (W,H,Wd,Hd)
   int smem_need = 0;       // shared memory of its worst tile
   RsLayout layout{};       // carve-up for the largest tile dimensions (one layout for all tiles)
   const int32_t *win_x = nullptr, *win_y = nullptr;  // device: per tile column / row source windows
+  int rz_dw = 0;           // destination strip width of k_resize_strips for this size pair (0: it cannot take it)
 };
 
 struct StagedCopy {  // pinned staging -> caller memory, done in wait()
@@ -275,6 +276,25 @@ int get_filters(nes_gpu_session *s, int W, int H, int Wd, int Hd, FilterSet **ou
     CU_TRY(s, cudaMemcpy(dw_ + wx.size(), wy.data(), wy.size() * 4, cudaMemcpyHostToDevice));
     fs.win_x = dw_; fs.win_y = dw_ + wx.size();
   }
+  // k_resize_strips: the widest destination strip (multiple of 16) whose source window -- luma taps and chroma taps of
+  // every column of the strip, from a 16-pixel aligned origin -- fits RZ_BOXW pixels, for every strip of the frame
+  fs.rz_dw = 0;
+  if (fs.hl.size <= RZ_MAX_TH && fs.hc.size <= RZ_MAX_TH && fs.vl.size <= RZ_MAX_TV && fs.vc.size <= RZ_MAX_TV && Wd >= RZ_MIN_WD && Hd >= RZ_MIN_HD) {
+    const int taps = std::max(fs.hl.size, fs.hc.size);
+    const int T = taps <= 4 ? 4 : taps <= 6 ? 6 : 8;  // taps the kernel reads per sample (zero-padded)
+    for (int dw = RZ_MAX_DW; dw >= 16 && !fs.rz_dw; dw -= 16) {
+      bool fits = true;
+      for (int dx0 = 0; dx0 < Wd && fits; dx0 += dw) {
+        const int dx1 = std::min(dx0 + dw, Wd), cx0 = dx0 >> 1, cx1 = std::min((dx1 + 1) >> 1, cdW);
+        const int cmul = fs.half ? 2 : 1;
+        const int wx0 = std::min(fs.h_hl.pos[dx0], cmul * fs.h_hc.pos[cx0]) & ~15;
+        const int lend = fs.h_hl.pos[dx1 - 1] + T, cend = cmul * (fs.h_hc.pos[cx1 - 1] + T);
+        fits = std::max(lend, cend) - wx0 <= RZ_BOXW + (T - taps);  // padded taps may read the row buffer's slack, real ones may not
+        fits = fits && (fs.h_hl.pos[dx1 - 1] + fs.hl.size - wx0 <= RZ_BOXW) && (cmul * (fs.h_hc.pos[cx1 - 1] + fs.hc.size) - wx0 <= RZ_BOXW);
+      }
+      if (fits) fs.rz_dw = dw;
+    }
+  }
   auto ins = s->filters.emplace(key, std::move(fs));
   *out = &ins.first->second;
   return NES_OK;
@@ -379,7 +399,7 @@ void job_common(DevJob *jb, const nes_frame_in *in, const nes_frame_out *out, in
 void job_tile_mask(DevJob *jb, const DevPlaced *placed) {
   jb->use_mask = 0;
   std::memset(jb->band_text, 0, sizeof(jb->band_text));
-  if (jb->general || jb->n_glyphs <= 0) return;
+  if ((jb->general && !jb->rz_ok) || jb->n_glyphs <= 0) return;
   const int strips = (jb->W + STRIP_W - 1) / STRIP_W;
   const int nbands = (jb->H + (1 << MASK_BAND_SHIFT) - 1) >> MASK_BAND_SHIFT;
   if (strips * nbands > 32 * MASK_WORDS) return;
@@ -401,7 +421,7 @@ void job_tile_mask(DevJob *jb, const DevPlaced *placed) {
 // Resize tiles of the general jobs of a launch (the same-size jobs are planned by plan_frame_strips).
 void job_tiles(DevJob *jb, int tile_base) {
   jb->tiles_x = jb->tiles_y = 0;
-  if (jb->general) {
+  if (jb->general && !jb->rz_ok) {
     jb->tiles_x = (jb->Wd + jb->rs_tw - 1) / jb->rs_tw;
     jb->tiles_y = (jb->Hd + jb->rs_th - 1) / jb->rs_th;
   }
@@ -420,6 +440,8 @@ void job_alignment(DevJob *jb) {
   jb->out_vec = ov;
   // rows staged by tensor-map TMA: 16-byte aligned rows; composites only for 4-byte pixels
   jb->tma_ok = iv && (jb->W % 16) == 0 && jb->n_src <= TMA_MAX_SOURCES && (jb->n_src == 1 || jb->bpp == 4);
+  // k_resize_strips: the size pair must fit its limits (rz_dw, get_filters) and the planes must suit TMA / word stores
+  jb->rz_ok = jb->general && jb->rz_dw > 0 && iv && ov && (jb->W % 4) == 0 && jb->n_src <= TMA_MAX_SOURCES && (jb->n_src == 1 || jb->bpp == 4);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -466,12 +488,13 @@ int plane_tmap(nes_gpu_session *s, const uint8_t *base, int stride, int width_by
 
 // Tensor maps of every plane the fused kernel stages for this job.
 int job_tmaps(nes_gpu_session *s, DevJob *jb) {
-  if (jb->general || !jb->tma_ok) return NES_OK;
+  if (jb->general ? !jb->rz_ok : !jb->tma_ok) return NES_OK;
   const bool dep = jb->dy != nullptr || jb->n_src > 1;
+  const int boxw = jb->general ? RZ_BOXW : STRIP_W;  // pixels per staged row
   for (int k = 0; k < jb->n_src; k++) {
-    int st = plane_tmap(s, jb->src[k].rgb, jb->src[k].rgb_stride, jb->W * jb->bpp, jb->H, STRIP_W * jb->bpp, &jb->tmap_px[k]);
+    int st = plane_tmap(s, jb->src[k].rgb, jb->src[k].rgb_stride, jb->W * jb->bpp, jb->H, boxw * jb->bpp, &jb->tmap_px[k]);
     if (st) return st;
-    if (dep && (st = plane_tmap(s, jb->src[k].depth, jb->src[k].depth_stride, jb->W, jb->H, STRIP_W, &jb->tmap_dep[k]))) return st;
+    if (dep && (st = plane_tmap(s, jb->src[k].depth, jb->src[k].depth_stride, jb->W, jb->H, boxw, &jb->tmap_dep[k]))) return st;
   }
   return NES_OK;
 }
@@ -539,6 +562,8 @@ int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, 
   int l = 0;
   const int r0 = launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, &s->strips_seq, st);
   if (r0 > 0) l += r0;
+  const int r1 = launch_resize_strips(d_jobs, h_jobs, n, s->d_counters, &s->strips_seq, st);
+  if (r1 > 0) l += r1;
   const int r = launch_resize_tiles(d_jobs, h_jobs, n, st);
   if (r > 0) l += r;
   s->launches += (uint64_t)l;
@@ -894,13 +919,15 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
     jb->hl = fs->hl; jb->hc = fs->hc; jb->vl = fs->vl; jb->vc = fs->vc;
     jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need;
     jb->rs_tw = fs->tw; jb->rs_th = fs->th; jb->rs_win_x = fs->win_x; jb->rs_win_y = fs->win_y; jb->rs_lay = fs->layout;
+    jb->rz_dw = getenv("NES_NO_RZ") ? 0 : fs->rz_dw;
   }
-  job_tiles(jb, 0);
   job_alignment(jb);
+  job_tiles(jb, 0);
   if ((st = job_tmaps(s, jb))) return st;
   job_tile_mask(jb, sl.h_glyphs);
   // (banded submits launch unit ranges that must be whole row bands: segments stay in frame order)
   plan_frame_strips(jb, 1, /*text_first=*/!banded);
+  plan_resize_strips(jb, 1);
 
   if (n_gl > 0) CU_TRY(s, cudaMemcpyAsync(sl.d_glyphs, sl.h_glyphs, (size_t)n_gl * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaMemcpyAsync(sl.d_job, sl.h_job, sizeof(DevJob), cudaMemcpyHostToDevice, s->st_in));
@@ -1096,14 +1123,16 @@ static int build_batch(nes_gpu_session *s, BatchTables &bt, int n_frames, const 
       jb->hl = fs->hl; jb->hc = fs->hc; jb->vl = fs->vl; jb->vc = fs->vc;
       jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need;
       jb->rs_tw = fs->tw; jb->rs_th = fs->th; jb->rs_win_x = fs->win_x; jb->rs_win_y = fs->win_y; jb->rs_lay = fs->layout;
+      jb->rz_dw = getenv("NES_NO_RZ") ? 0 : fs->rz_dw;
     }
+    job_alignment(jb);
     job_tiles(jb, tile_base);
     tile_base += jb->tiles_x * jb->tiles_y;
-    job_alignment(jb);
     if ((st = job_tmaps(s, jb))) return st;
     job_tile_mask(jb, bt.h_glyphs + gl_used - n_gl);
   }
   plan_frame_strips(bt.h_jobs, n_frames);
+  plan_resize_strips(bt.h_jobs, n_frames);
   // descriptor upload on the copy stream, so that it overlaps the kernels of the previous batch
   if (gl_used > 0) CU_TRY(s, cudaMemcpyAsync(bt.d_glyphs, bt.h_glyphs, (size_t)gl_used * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaMemcpyAsync(bt.d_jobs, bt.h_jobs, sizeof(DevJob) * n_frames, cudaMemcpyHostToDevice, s->st_in));

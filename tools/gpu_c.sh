@@ -1,13 +1,10 @@
 #!/bin/bash
-out=gpurun_out/r2c; mkdir -p $out
-(timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "pytest rc=$?" >> $out/pytest.log)
-tail -5 $out/pytest.log
+out=gpurun_out/r2d; mkdir -p $out
 export NES_GPU_LIB=$PWD/ngp-encode-server_b200/libnes_gpu_trace.so
-for pdl in 0 1; do
-for cfg in "c2_1080p_2src_composite 16" "4k_rgb24 8" "c4_1080p_sessions 29" "c2_1080p_2src_composite 1" "4k_rgb24 1"; do
+for mode in convert prepared; do
+for cfg in "c2_1080p_2src_composite 16" "c4_1080p_sessions 29" "c2_1080p_2src_composite 1" "4k_rgb24 1" "c2_1080p_2src_composite 64" "c4_1080p_sessions 64"; do
   set -- $cfg
-  echo "NO_PDL=$pdl"
-  NES_NO_PDL=$pdl timeout 300 python tools/diag_trace.py --workload $1 --frames $2 2>&1 | tail -1
-  cp gpurun_out/trace_$1_$2.json $out/trace_$1_$2_nopdl$pdl.json
+  timeout 300 python tools/diag_trace.py --workload $1 --frames $2 --mode $mode 2>&1 | tail -2
+  cp gpurun_out/trace_$1_$2.json $out/trace_$1_$2_$mode.json
 done
 done
