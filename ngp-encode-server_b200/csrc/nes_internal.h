@@ -44,9 +44,9 @@ constexpr int GLYPH_BANDS = 256;          // placed glyphs of a resize job are b
 // the same TMA sub-stage ring as k_frame_strips; a warp takes a source row from packed pixels to horizontally
 // filtered 15-bit samples in RZ_NR-row rings, the vertical pass runs once per chunk.
 constexpr int RZ_BOXW = 128;
+constexpr int RZ_DEPB = RZ_BOXW + 16;  // bytes of a staged depth row: its box starts on the 16-pixel boundary at or below the window origin
 constexpr int RZ_SUB = 8;        // source rows per TMA sub-stage (one per consumer warp)
 constexpr int RZ_CH = 16;        // source rows per chunk
-constexpr int RZ_NR = 48;        // ring rows: >= 31 + the longest vertical filter (RZ_MAX_TV)
 constexpr int RZ_MAX_DW = 128;   // destination columns per strip (4 per lane)
 constexpr int RZ_MAX_TH = 8;     // horizontal taps kept in registers
 constexpr int RZ_MAX_TV = 16;    // vertical taps
@@ -174,7 +174,7 @@ struct alignas(64) DevJob {
   const int32_t *rs_win_y;  // [tiles_y][4]: luma source rows [lr0, lr1), chroma source rows [cr0, cr1)
   // k_resize_strips work (general jobs it can take: rz_ok; the others keep their tiles)
   int32_t rz_ok;
-  int32_t rz_dw;                         // destination columns per strip (multiple of 16, <= RZ_MAX_DW)
+  int32_t rz_dw;                         // destination columns per strip (multiple of 16, <= RZ_MAX_DW; 0: the size pair does not fit)
   int32_t rz_strips_x, rz_seg_rows, rz_segs_y;
   int32_t rz_unit_base[2], rz_units;     // [bpp-3]: units of the rz jobs of that pixel class ahead of this job in the launch
 };

@@ -40,11 +40,11 @@ namespace {
 
 enum { RM_ROWS = 0, RM_SELECT = 1, RM_MATERIALIZED = 2 };
 
-constexpr int RZ_DEPB = RZ_BOXW;       // bytes of a staged depth row
 constexpr int RZ_ROWBUF = 1024;        // per-warp row buffer: y14 | u14 | v14 (u16, 144 each) | depth bytes (144)
 constexpr int RZ_RB_Y = 0, RZ_RB_U = 288, RZ_RB_V = 576, RZ_RB_D = 864;
 constexpr int RZ_NS_MAX = 8;
 constexpr int RZ_NCTX = 8;
+constexpr int RZ_HITS = 64;            // glyph rect tests per pass of an overlay chunk
 
 // Everything the consumer warps need to know about one chunk (written by lane 0 of the producer warp).
 struct RzCtx {
@@ -52,11 +52,12 @@ struct RzCtx {
   int32_t first;      // first chunk of a unit: (re)load the horizontal filter registers
   int32_t unit_end;   // last chunk of a unit: the rings are reused from slot 0 by the next one
   int32_t mode, stamp, n_src, job, n_staged;
-  int32_t wx0;        // source column of window column 0 (multiple of 16)
+  int32_t wx0;        // source column of window column 0 (4-byte pixels: multiple of 4; 3-byte pixels: of 16 -- TMA box rows start on 16-byte boundaries)
+  int32_t dshift;     // window column 0 inside the staged depth rows (their box starts at wx0 & ~15)
   int32_t yc0, ra, rb;          // source row of chunk-local row 0; rows of this chunk that are needed [ra, rb)
   int32_t lr0, lr1, cr0, cr1;   // source rows the luma / chroma vertical filters of this unit read
   int32_t ya, yb, ca, cb;       // destination rows to emit after this chunk (luma, chroma)
-  int32_t rbase;                // ring slot of chunk-local row 0
+  int32_t rbase_y, rbase_c;     // luma / chroma ring slot of chunk-local row 0
   int32_t dx0, dw, cx0, dcw;    // destination strip: luma / chroma columns
   int32_t half, dep_staged, nv12, rgb_base;
   int32_t hls, hcs, vls, vcs;   // filter sizes
@@ -69,20 +70,24 @@ struct RzCtx {
 };
 
 struct RzSmem {
-  int ringY, ringD, ringU, ringV, rowbuf, ctx, bar, hits, stage;
+  int ringY, ringD, ringU, ringV, rowbuf, ctx, bar, hits, mask, stage;
 };
 constexpr int RZ_CTX_BYTES = ((int)sizeof(RzCtx) + 15) & ~15;
-__host__ __device__ inline RzSmem rz_smem(int dwp) {
+// nry / nrc: rows of the luma (+ depth) and chroma rings: a ring must hold 31 + (vertical filter size) rows so that
+// the rows one chunk's vertical pass still reads are never overwritten by the next chunk's horizontal pass
+__host__ __device__ inline int rz_ring_rows(int vsize) { return (31 + vsize + 7) & ~7; }
+__host__ __device__ inline RzSmem rz_smem(int dwp, int nry, int nrc) {
   RzSmem L;
   int o = 0;
-  L.ringY = o; o += RZ_NR * dwp * 4;
-  L.ringD = o; o += RZ_NR * dwp * 4;
-  L.ringU = o; o += RZ_NR * (dwp / 2) * 4;
-  L.ringV = o; o += RZ_NR * (dwp / 2) * 4;
+  L.ringY = o; o += nry * dwp * 4;
+  L.ringD = o; o += nry * dwp * 4;
+  L.ringU = o; o += nrc * (dwp / 2) * 4;
+  L.ringV = o; o += nrc * (dwp / 2) * 4;
   L.rowbuf = o; o += CONSUMER_WARPS * RZ_ROWBUF;
   L.ctx = o; o += RZ_NCTX * RZ_CTX_BYTES;
   L.bar = o; o += 2 * RZ_NS_MAX * 8;
-  L.hits = o; o += STRIP_HITS * (int)sizeof(DevPlaced) + 16;
+  L.hits = o; o += RZ_HITS * (int)sizeof(DevPlaced) + 16;
+  L.mask = o; o += RZ_CH * (RZ_BOXW / 32) * 4;  // overlay bits of one chunk of the window
   L.stage = (o + 1023) & ~1023;
   return L;
 }
@@ -136,6 +141,9 @@ __device__ __forceinline__ void select4(uint32_t px, uint32_t dep, int n_src, ui
   for (int k = 1; k < TMA_MAX_SOURCES; k++) {
     if (k >= n_src) break;
     const uint4 q = lds128(px + (uint32_t)(k * RZ_SUB) * ROWB + lane * 16);
+    // a renderer's partial view leaves most of a row transparent: a source without one valid pixel in this row of
+    // the window is skipped by the whole warp
+    if (!__any_sync(0xffffffffu, ((q.x | q.y | q.z | q.w) & a_mask) != 0)) continue;
     const uint32_t dw = lds32(dep + (uint32_t)(k * RZ_SUB) * RZ_DEPB + lane * 4);
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -150,29 +158,90 @@ __device__ __forceinline__ void select4(uint32_t px, uint32_t dep, int n_src, ui
   d4 = __byte_perm(lo, hi, 0x5410);
 }
 
+// Overlay bits of one chunk: s_mask[RZ_CH][RZ_BOXW / 32] (zero on entry; window column x of chunk row r is bit x & 31
+// of word r * 4 + (x >> 5)).  The glyph list is bucketed by row band on the host; one thread tests one glyph, the hits
+// are staged as whole descriptors, then a warp takes a glyph and a lane one word of one of its rows (the atlas holds
+// one bit per glyph pixel) and ORs it in, shifted to the window's column grid.  Rows outside [ra, rb) are never set.
+// pass: running count of passes (selects one of the two hit counters; the other one is re-armed in the meantime).
+__device__ __forceinline__ int mask_chunk(const DevJob &jb, uint32_t *s_mask, int x0, int yc0, int ra, int rb, DevPlaced *s_hits, int *s_nhits, int pass) {
+  constexpr int NT = 32 * CONSUMER_WARPS;
+  constexpr int MW = RZ_BOXW / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x1 = x0 + RZ_BOXW;
+  int g_begin = 0, g_end = jb.n_glyphs;
+  if (jb.glyph_band_shift >= 0) {
+    const int b0 = max(ra - jb.glyph_max_h, 0) >> jb.glyph_band_shift, b1 = (rb - 1) >> jb.glyph_band_shift;
+    g_begin = jb.glyph_band[b0]; g_end = jb.glyph_band[b1 + 1];
+  }
+  const DevPlaced *__restrict__ glyphs = jb.glyphs;
+  const uint32_t *__restrict__ atlas = jb.atlas;
+  auto or_rows = [&](const DevPlaced &pg, int first, int step) {
+    const int q0 = max(0, ra - pg.y), q1 = min(pg.h, rb - pg.y);
+    const int p0 = max(0, x0 - pg.x), p1 = min(pg.w, x1 - pg.x);
+    const int bit_lo = pg.bit0 + p0, bit_hi = pg.bit0 + p1;
+    const int w_lo = bit_lo >> 5, w_hi = (bit_hi - 1) >> 5, nw = w_hi - w_lo + 1;
+    for (int i = first; i < (q1 - q0) * nw; i += step) {
+      const int qq = i / nw, wi = w_lo + (i - qq * nw), q = q0 + qq;
+      uint32_t m = __ldg(atlas + pg.mask_off + (uint32_t)(q * pg.wpr + wi));
+      const int lo = max(bit_lo - 32 * wi, 0), hi = min(bit_hi - 32 * wi, 32);
+      m &= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (32 - hi));
+      if (m == 0) continue;
+      const int xb = pg.x - pg.bit0 + 32 * wi - x0;  // window column of bit 0 of this word (negative only for masked-off bits)
+      const int wd = xb >> 5, sh = xb & 31;
+      uint32_t *mrow = s_mask + (pg.y + q - yc0) * MW;
+      const uint32_t lo_part = m << sh;
+      if (lo_part && wd >= 0) atomicOr(&mrow[wd], lo_part);
+      if (sh) {
+        const uint32_t hi_part = m >> (32 - sh);
+        if (hi_part) atomicOr(&mrow[wd + 1], hi_part);
+      }
+    }
+  };
+  for (int base = g_begin; base < g_end; base += NT, pass++) {
+    int *cnt = s_nhits + (pass & 1);
+    if (base + tid < g_end) {
+      const DevPlaced pg = glyphs[base + tid];
+      if (pg.x < x1 && pg.x + pg.w > x0 && pg.y < rb && pg.y + pg.h > ra) {
+        const int i = atomicAdd(cnt, 1);
+        if (i < RZ_HITS) s_hits[i] = pg;
+        else or_rows(pg, 0, 1);  // more hits than staging slots (tiny glyphs): this thread does the whole glyph
+      }
+    }
+    consumer_sync();
+    const int nh = min(*cnt, RZ_HITS);
+    if (tid == 0) s_nhits[(pass + 1) & 1] = 0;
+    for (int h = warp; h < nh; h += CONSUMER_WARPS) or_rows(s_hits[h], lane, 32);
+    consumer_sync();
+  }
+  return pass;
+}
+
 }  // namespace
 
 // T: horizontal taps held in registers (>= the longest horizontal filter of the launch; shorter filters are
 // padded with zero coefficients).
 template <int BPP, int T>
 __global__ void __launch_bounds__(CTA_THREADS, 2)
-k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters, int ns, int slot_bytes, int dwp) {
+k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters, int ns, int slot_bytes, int dwp, int nry, int nrc) {
   asm volatile("griddepcontrol.launch_dependents;");  // see k_frame_strips: consecutive launches overlap
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int ROWB = RZ_BOXW * BPP;
   constexpr int NW = CONSUMER_WARPS;
-  const RzSmem L = rz_smem(dwp);
+  const RzSmem L = rz_smem(dwp, nry, nrc);
   uint64_t *s_full = (uint64_t *)(smem + L.bar);
   uint64_t *s_empty = s_full + RZ_NS_MAX;
   DevPlaced *s_hits = (DevPlaced *)(smem + L.hits);
-  int *s_nhits = (int *)(s_hits + STRIP_HITS);
+  int *s_nhits = (int *)(s_hits + RZ_HITS);  // [2]: alternate from pass to pass (the idle one is re-armed meanwhile)
+  uint32_t *s_mask = (uint32_t *)(smem + L.mask);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t smem_base = smem_u32(smem);
 
   if (tid == 0) {
     for (int i = 0; i < RZ_NS_MAX; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_nhits[0] = s_nhits[1] = 0;
   }
+  if (tid < RZ_CH * (RZ_BOXW / 32)) s_mask[tid] = 0;
   __syncthreads();
 
   if (warp == NW) {
@@ -198,7 +267,8 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
       const int vls = jp->vl.size, vcs = jp->vc.size;
       // filter positions are non-decreasing: the unit's source window follows from its first / last samples
       const int cpos0 = jp->hc.pos[cx0];
-      const int wx0 = min(jp->hl.pos[dx0], half ? 2 * cpos0 : cpos0) & ~15;  // box rows start on 16-byte boundaries
+      const int wx0 = min(jp->hl.pos[dx0], half ? 2 * cpos0 : cpos0) & (BPP == 4 ? ~3 : ~15);  // box rows start on 16-byte boundaries
+      const int wxd = wx0 & ~15;
       const int lr0 = vlp[dy0], lr1 = vlp[dy1 - 1] + vls, cr0 = vcp[cy0], cr1 = vcp[cy1 - 1] + vcs;
       const int r0 = min(lr0, cr0), r1 = max(lr1, cr1);
       const int nchunks = (r1 - r0 + RZ_CH - 1) / RZ_CH;
@@ -213,12 +283,12 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
       } else if (dep_staged && lane < 2 * n_staged) {
         my_map = &jp->tmap_dep[lane - n_staged];
         my_off = (uint32_t)(n_staged * RZ_SUB) * ROWB + (uint32_t)((lane - n_staged) * RZ_SUB) * RZ_DEPB;
-        my_x = wx0 >> 2;
+        my_x = wxd >> 2;
       }
       const int strips256 = (jp->W + STRIP_W - 1) / STRIP_W;
       const int nbands = (jp->H + (1 << MASK_BAND_SHIFT) - 1) >> MASK_BAND_SHIFT;
       int ly = dy0, cy = cy0;  // emission cursors
-      int rbase = 0;
+      int rbase_y = 0, rbase_c = 0;
       for (int k = 0; k < nchunks; k++, chunk_it++) {
         const int yc0 = r0 + k * RZ_CH;
         const int ra = yc0, rb = min(yc0 + RZ_CH, r1);
@@ -260,12 +330,12 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           c.first = (k == 0);
           c.unit_end = last_k;
           c.stamp = stamp;
-          c.mode = n_src > 1 ? (stamp ? RM_MATERIALIZED : RM_SELECT) : RM_ROWS;
+          c.mode = n_src > 1 ? RM_SELECT : RM_ROWS;
           c.n_src = n_src; c.job = j; c.n_staged = n_staged;
-          c.wx0 = wx0; c.yc0 = yc0; c.ra = ra; c.rb = rb;
+          c.wx0 = wx0; c.dshift = wx0 - wxd; c.yc0 = yc0; c.ra = ra; c.rb = rb;
           c.lr0 = lr0; c.lr1 = lr1; c.cr0 = cr0; c.cr1 = cr1;
           c.ya = ya; c.yb = ly; c.ca = ca; c.cb = cy;
-          c.rbase = rbase;
+          c.rbase_y = rbase_y; c.rbase_c = rbase_c;
           c.dx0 = dx0; c.dw = dw; c.cx0 = cx0; c.dcw = dcw;
           c.half = half; c.dep_staged = dep_staged; c.nv12 = jp->nv12; c.rgb_base = jp->rgb_base;
           c.hls = jp->hl.size; c.hcs = jp->hc.size; c.vls = vls; c.vcs = vcs;
@@ -282,7 +352,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
 #endif
 #pragma unroll 1
         for (int sub = 0; sub < RZ_CH / RZ_SUB; sub++) {
-          if (!round0) mbar_wait(&s_empty[q], (uint32_t)(par ^ 1));
+          if (!round0) mbar_wait_hint_a(smem_u32(&s_empty[q]), (uint32_t)(par ^ 1), 2000u);
           const int ys = yc0 + sub * RZ_SUB;
           const bool wanted = ys < rb;
           if (wanted) {
@@ -294,8 +364,10 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           }
           if (++q == ns) { q = 0; par ^= 1; round0 = 0; }
         }
-        rbase += RZ_CH;
-        if (rbase >= RZ_NR) rbase -= RZ_NR;
+        rbase_y += RZ_CH;
+        if (rbase_y >= nry) rbase_y -= nry;
+        rbase_c += RZ_CH;
+        if (rbase_c >= nrc) rbase_c -= nrc;
       }
       cur_u = next_u;
       if (lane == 0 && cur_u < total_units) next_u = (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
@@ -329,17 +401,18 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
     for (int jj = 0; jj < T; jj++) cf_c[c][jj] = 0;
   }
   int qc = 0, parc = 0;
+  int mask_pass = 0;  // overlay passes so far (selects the hit counter; the same in every consumer thread)
   for (int chunk_it = 0;; chunk_it++) {
     int q[2], par[2];
     q[0] = qc; par[0] = parc;
     q[1] = qc + 1; par[1] = parc;
     if (q[1] == ns) { q[1] = 0; par[1] ^= 1; }
-    mbar_wait_a(full0 + q[0] * 8, (uint32_t)par[0]);
+    mbar_wait_hint_a(full0 + q[0] * 8, (uint32_t)par[0], 2000u);
     const RzCtx &c = *(const RzCtx *)(smem + L.ctx + (chunk_it & (RZ_NCTX - 1)) * RZ_CTX_BYTES);
     const int last = c.last, unit_end = c.unit_end;
     {
       const uint32_t sb[2] = {smem_base + L.stage + (uint32_t)(q[0] * slot_bytes), smem_base + L.stage + (uint32_t)(q[1] * slot_bytes)};
-      const uint32_t dep_off = (uint32_t)(c.n_staged * RZ_SUB) * ROWB;
+      const uint32_t dep_off = (uint32_t)(c.n_staged * RZ_SUB) * ROWB + (uint32_t)c.dshift;
       const int wx0 = c.wx0, yc0 = c.yc0, ra = c.ra, rb = c.rb;
       const int dw = c.dw, dcw = c.dcw;
       const bool half = c.half != 0, dep_staged = c.dep_staged != 0;
@@ -369,37 +442,20 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
         }
       }
 
-      if (mode == RM_MATERIALIZED || c.stamp) {
-        // whole-chunk work on the staged rows: needs both sub-stages
-        mbar_wait_a(full0 + q[1] * 8, (uint32_t)par[1]);
-        if (BPP == 4 && mode == RM_MATERIALIZED) {
-#pragma unroll
-          for (int i = 0; i < 2; i++) {
-            const int y = yc0 + warp + i * RZ_SUB;
-            if (y < ra || y >= rb) continue;
-            const uint32_t px = sb[i] + warp * ROWB, dp = sb[i] + dep_off + warp * RZ_DEPB;
-            uint32_t p[4], d4;
-            select4<ROWB>(px, dp, c.n_src, c.a_mask, lane, p, d4);
-            __syncwarp();
-            sts128(px + lane * 16, p[0], p[1], p[2], p[3]);
-            sts32(dp + lane * 4, d4);
-          }
-          mode = RM_ROWS;
-        }
-        __syncwarp();
-        if (c.stamp) stamp_chunk<BPP, RZ_BOXW>(jobs[c.job], smem + L.stage, qc, ns, slot_bytes, wx0, wx0 + RZ_BOXW, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
-        fence_proxy_async();
-      }
+      // ---- text overlay: the chunk's glyph pixels as a bit mask of the window (render_text.cc:94-106: coverage != 0
+      // -> white); the rows apply it in registers after the composite, nothing is written back to the staged rows
+      const bool stamped = c.stamp != 0;
+      if (stamped) mask_pass = mask_chunk(jobs[c.job], s_mask, wx0, yc0, ra, rb, s_hits, s_nhits, mask_pass);
 
       // ---- per source row: composite -> 14-bit planes (row buffer) -> horizontal pass -> rings ----------
       {
         const uint32_t ky0 = c.ky[0], ky1 = c.ky[1], ku0 = c.ku[0], ku1 = c.ku[1], kv0 = c.kv[0], kv1 = c.kv[1];
-        const int rbase = c.rbase;
+        const int rbase_y = c.rbase_y, rbase_c = c.rbase_c;
 #pragma unroll
         for (int i = 0; i < 2; i++) {
           const int r = warp + i * RZ_SUB;
           const int y = yc0 + r;
-          if (i == 1) mbar_wait_a(full0 + q[1] * 8, (uint32_t)par[1]);
+          if (i == 1) mbar_wait_hint_a(full0 + q[1] * 8, (uint32_t)par[1], 2000u);
           if (y >= ra && y < rb) {
             const uint32_t row = sb[i] + warp * ROWB;
             const uint32_t drow = sb[i] + dep_off + warp * RZ_DEPB;
@@ -420,6 +476,15 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
               p[2] = __funnelshift_r(w1, w2, 16);
               p[3] = w2 >> 8;
               if (dep_staged) d4 = lds32(drow + lane * 4);
+            }
+            if (stamped) {
+              const uint32_t m = (s_mask[r * (RZ_BOXW / 32) + (lane >> 3)] >> ((lane & 7) * 4)) & 15u;
+              const uint32_t white = BPP == 4 ? (0x00FFFFFFu << (8 * c.rgb_base)) : 0x00FFFFFFu;
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                if ((m >> k) & 1u) p[k] |= white;
+              __syncwarp();
+              if (lane < RZ_BOXW / 32) s_mask[r * (RZ_BOXW / 32) + lane] = 0;  // this warp owns the row: leave it clean for the next chunk
             }
             const bool need_l = y >= c.lr0 && y < c.lr1, need_c = y >= c.cr0 && y < c.cr1;
             if (need_l) {
@@ -451,8 +516,9 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
               }
             }
             __syncwarp();
-            int slot = rbase + r;
-            if (slot >= RZ_NR) slot -= RZ_NR;
+            int slot = rbase_y + r, slot_c = rbase_c + r;
+            if (slot >= nry) slot -= nry;
+            if (slot_c >= nrc) slot_c -= nrc;
             // ---- horizontal pass of this row: hScale16To15 (>>13, clamp) / hScale8To15 (>>7) + range compression
             if (need_l) {
 #pragma unroll
@@ -488,7 +554,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
                   for (int jj = 0; jj < T; jj++) { u += lds_u16(au + 2 * jj) * cf_c[cc][jj]; v += lds_u16(av + 2 * jj) * cf_c[cc][jj]; }
                   u = min(u >> 13, 32767);
                   v = min(v >> 13, 32767);
-                  if (col < dcw) { sts32(ringU + slot * rowbC + col * 4, (uint32_t)u); sts32(ringV + slot * rowbC + col * 4, (uint32_t)v); }
+                  if (col < dcw) { sts32(ringU + slot_c * rowbC + col * 4, (uint32_t)u); sts32(ringV + slot_c * rowbC + col * 4, (uint32_t)v); }
                 }
               }
             }
@@ -501,7 +567,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
 
       // ---- vertical pass: every destination row whose taps are all in the rings ---------------------
       {
-        const int rbase = c.rbase;
+        const int rbase_y = c.rbase_y, rbase_c = c.rbase_c;
         // (the launch only takes jobs with 16-byte aligned destination planes: whole groups go out as words)
         // luma (+ depth luma, same filter)
         {
@@ -514,8 +580,9 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
             const int ry = (int)(((uint32_t)idx * rcp) >> 16), g = idx - ry * gl;
             const int dyy = ya + ry;
             const int pos = __ldg(c.vl_pos + dyy);
-            int slot = rbase + pos - yc0;
-            if (slot < 0) slot += RZ_NR;
+            int slot = rbase_y + pos - yc0;
+            if (slot < 0) slot += nry;
+            if (slot >= nry) slot -= nry;
             int a[4], d[4];
             if (vls == 1) {
               const int4 w = lds_v4s(ringY + slot * rowbY + g * 16);
@@ -536,7 +603,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
                   const int4 e = lds_v4s(ringD + slot * rowbY + g * 16);
                   d[0] += e.x * k; d[1] += e.y * k; d[2] += e.z * k; d[3] += e.w * k;
                 }
-                if (++slot == RZ_NR) slot = 0;
+                if (++slot == nry) slot = 0;
               }
 #pragma unroll
               for (int k = 0; k < 4; k++) { a[k] >>= 19; d[k] >>= 19; }
@@ -566,8 +633,9 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
             const int ry = (int)(((uint32_t)idx * rcp) >> 16), g = idx - ry * gc;
             const int cyy = ca + ry;
             const int pos = __ldg(c.vc_pos + cyy);
-            int slot = rbase + pos - yc0;
-            if (slot < 0) slot += RZ_NR;
+            int slot = rbase_c + pos - yc0;
+            if (slot < 0) slot += nrc;
+            if (slot >= nrc) slot -= nrc;
             int u[4], v[4];
             if (vcs == 1) {
               const int4 w = lds_v4s(ringU + slot * rowbC + g * 16), e = lds_v4s(ringV + slot * rowbC + g * 16);
@@ -582,7 +650,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
                 const int4 w = lds_v4s(ringU + slot * rowbC + g * 16), e = lds_v4s(ringV + slot * rowbC + g * 16);
                 u[0] += w.x * k; u[1] += w.y * k; u[2] += w.z * k; u[3] += w.w * k;
                 v[0] += e.x * k; v[1] += e.y * k; v[2] += e.z * k; v[3] += e.w * k;
-                if (++slot == RZ_NR) slot = 0;
+                if (++slot == nrc) slot = 0;
               }
 #pragma unroll
               for (int k = 0; k < 4; k++) { u[k] >>= 19; v[k] >>= 19; }
@@ -655,23 +723,27 @@ int resize_strips_init() {
 }
 
 struct RzConfig {
-  int ns, slot, smem, ctas, dwp, taps;
+  int ns, slot, smem, ctas, dwp, taps, nry, nrc;
 };
-// Launch shape of one pixel class: rings sized for the widest destination strip of the launch, sub-stage slots
-// for the most sources; two CTAs per SM when two sub-stages (one chunk) fit half an SM, else one CTA with a deeper ring.
+// Launch shape of one pixel class: rings sized for the widest destination strip and the longest vertical filters of
+// the launch, sub-stage slots for the most sources; two CTAs per SM when two sub-stages (one chunk) fit half an SM,
+// else one CTA with a deeper ring.
 static RzConfig rz_config(const DevJob *jobs, int n_jobs, int bpp) {
-  int dwp = 16, staged = 1, taps = 1;
+  int dwp = 16, staged = 1, taps = 1, vl = 1, vc = 1;
   for (int j = 0; j < n_jobs; j++) {
     const DevJob &jb = jobs[j];
     if (!jb.rz_ok || jb.bpp != bpp) continue;
     dwp = std::max(dwp, (jb.rz_dw + 15) & ~15);
     staged = std::max(staged, jb.n_src);
     taps = std::max(taps, std::max(jb.hl.size, jb.hc.size));
+    vl = std::max(vl, jb.vl.size);
+    vc = std::max(vc, jb.vc.size);
   }
-  const RzSmem L = rz_smem(dwp);
+  const int nry = rz_ring_rows(vl), nrc = rz_ring_rows(vc);
+  const RzSmem L = rz_smem(dwp, nry, nrc);
   const int slot = staged * RZ_SUB * (RZ_BOXW * bpp + RZ_DEPB);
   const int smem_sm = g_rz_smem_sm > 0 ? g_rz_smem_sm : 233472;
-  RzConfig c{0, slot, 0, 0, dwp, taps <= 4 ? 4 : taps <= 6 ? 6 : 8};
+  RzConfig c{0, slot, 0, 0, dwp, taps <= 4 ? 4 : taps <= 6 ? 6 : 8, nry, nrc};
   for (int ctas = 2; ctas >= 1; ctas--) {
     const int budget = std::min(smem_sm / ctas - g_rz_reserved, g_rz_optin > 0 ? g_rz_optin : 232448) - L.stage;
     const int ns = std::min(RZ_NS_MAX, budget / slot);
@@ -737,7 +809,7 @@ static cudaError_t rz_launch_one(int grid, const RzConfig &c, cudaStream_t st, c
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = g_rz_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k_resize_strips<BPP, T>, jobs, n_jobs, total, ctr, c.ns, c.slot, c.dwp);
+  return cudaLaunchKernelEx(&cfg, k_resize_strips<BPP, T>, jobs, n_jobs, total, ctr, c.ns, c.slot, c.dwp, c.nry, c.nrc);
 }
 
 int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream) {

@@ -46,7 +46,7 @@ struct FilterSet {  // device tables for one (W,H,Wd,Hd)
   int smem_need = 0;       // shared memory of its worst tile
   RsLayout layout{};       // carve-up for the largest tile dimensions (one layout for all tiles)
   const int32_t *win_x = nullptr, *win_y = nullptr;  // device: per tile column / row source windows
-  int rz_dw = 0;           // destination strip width of k_resize_strips for this size pair (0: it cannot take it)
+  int rz_dw[2] = {0, 0};   // [bpp-3]: destination strip width of k_resize_strips for this size pair (0: it cannot take it)
 };
 
 struct StagedCopy {  // pinned staging -> caller memory, done in wait()
@@ -277,22 +277,27 @@ int get_filters(nes_gpu_session *s, int W, int H, int Wd, int Hd, FilterSet **ou
     fs.win_x = dw_; fs.win_y = dw_ + wx.size();
   }
   // k_resize_strips: the widest destination strip (multiple of 16) whose source window -- luma taps and chroma taps of
-  // every column of the strip, from a 16-pixel aligned origin -- fits RZ_BOXW pixels, for every strip of the frame
-  fs.rz_dw = 0;
+  // every column of the strip, from an origin TMA can start a box row at (4 pixels for 4-byte pixels, 16 for 3-byte
+  // ones) -- fits RZ_BOXW pixels, for every strip of the frame
+  fs.rz_dw[0] = fs.rz_dw[1] = 0;
   if (fs.hl.size <= RZ_MAX_TH && fs.hc.size <= RZ_MAX_TH && fs.vl.size <= RZ_MAX_TV && fs.vc.size <= RZ_MAX_TV && Wd >= RZ_MIN_WD && Hd >= RZ_MIN_HD) {
     const int taps = std::max(fs.hl.size, fs.hc.size);
     const int T = taps <= 4 ? 4 : taps <= 6 ? 6 : 8;  // taps the kernel reads per sample (zero-padded)
-    for (int dw = RZ_MAX_DW; dw >= 16 && !fs.rz_dw; dw -= 16) {
-      bool fits = true;
-      for (int dx0 = 0; dx0 < Wd && fits; dx0 += dw) {
-        const int dx1 = std::min(dx0 + dw, Wd), cx0 = dx0 >> 1, cx1 = std::min((dx1 + 1) >> 1, cdW);
-        const int cmul = fs.half ? 2 : 1;
-        const int wx0 = std::min(fs.h_hl.pos[dx0], cmul * fs.h_hc.pos[cx0]) & ~15;
-        const int lend = fs.h_hl.pos[dx1 - 1] + T, cend = cmul * (fs.h_hc.pos[cx1 - 1] + T);
-        fits = std::max(lend, cend) - wx0 <= RZ_BOXW + (T - taps);  // padded taps may read the row buffer's slack, real ones may not
-        fits = fits && (fs.h_hl.pos[dx1 - 1] + fs.hl.size - wx0 <= RZ_BOXW) && (cmul * (fs.h_hc.pos[cx1 - 1] + fs.hc.size) - wx0 <= RZ_BOXW);
+    for (int cls = 0; cls < 2; cls++) {
+      const int amask = cls == 0 ? ~15 : ~3;
+      static const int max_dw = [] { const char *v = getenv("NES_RZ_MAXDW"); const int x = v ? atoi(v) : RZ_MAX_DW; return std::min(std::max(x & ~15, 16), RZ_MAX_DW); }();
+      for (int dw = max_dw; dw >= 16 && !fs.rz_dw[cls]; dw -= 16) {
+        bool fits = true;
+        for (int dx0 = 0; dx0 < Wd && fits; dx0 += dw) {
+          const int dx1 = std::min(dx0 + dw, Wd), cx0 = dx0 >> 1, cx1 = std::min((dx1 + 1) >> 1, cdW);
+          const int cmul = fs.half ? 2 : 1;
+          const int wx0 = std::min(fs.h_hl.pos[dx0], cmul * fs.h_hc.pos[cx0]) & amask;
+          // real taps must stay inside the window; the zero-padded ones may read the row buffers' 16-sample slack
+          fits = (fs.h_hl.pos[dx1 - 1] + fs.hl.size - wx0 <= RZ_BOXW) && (cmul * (fs.h_hc.pos[cx1 - 1] + fs.hc.size) - wx0 <= RZ_BOXW) &&
+                 (fs.h_hl.pos[dx1 - 1] + T - wx0 <= RZ_BOXW + 16) && (fs.h_hc.pos[cx1 - 1] + T - wx0 / cmul <= RZ_BOXW / cmul + 16);
+        }
+        if (fits) fs.rz_dw[cls] = dw;
       }
-      if (fits) fs.rz_dw = dw;
     }
   }
   auto ins = s->filters.emplace(key, std::move(fs));
@@ -494,7 +499,7 @@ int job_tmaps(nes_gpu_session *s, DevJob *jb) {
   for (int k = 0; k < jb->n_src; k++) {
     int st = plane_tmap(s, jb->src[k].rgb, jb->src[k].rgb_stride, jb->W * jb->bpp, jb->H, boxw * jb->bpp, &jb->tmap_px[k]);
     if (st) return st;
-    if (dep && (st = plane_tmap(s, jb->src[k].depth, jb->src[k].depth_stride, jb->W, jb->H, boxw, &jb->tmap_dep[k]))) return st;
+    if (dep && (st = plane_tmap(s, jb->src[k].depth, jb->src[k].depth_stride, jb->W, jb->H, jb->general ? RZ_DEPB : boxw, &jb->tmap_dep[k]))) return st;
   }
   return NES_OK;
 }
@@ -919,7 +924,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
     jb->hl = fs->hl; jb->hc = fs->hc; jb->vl = fs->vl; jb->vc = fs->vc;
     jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need;
     jb->rs_tw = fs->tw; jb->rs_th = fs->th; jb->rs_win_x = fs->win_x; jb->rs_win_y = fs->win_y; jb->rs_lay = fs->layout;
-    jb->rz_dw = getenv("NES_NO_RZ") ? 0 : fs->rz_dw;
+    jb->rz_dw = getenv("NES_NO_RZ") ? 0 : fs->rz_dw[bpp - 3];
   }
   job_alignment(jb);
   job_tiles(jb, 0);
@@ -1123,7 +1128,7 @@ static int build_batch(nes_gpu_session *s, BatchTables &bt, int n_frames, const 
       jb->hl = fs->hl; jb->hc = fs->hc; jb->vl = fs->vl; jb->vc = fs->vc;
       jb->half = fs->half; jb->csW = fs->csW; jb->rs_smem = fs->smem_need;
       jb->rs_tw = fs->tw; jb->rs_th = fs->th; jb->rs_win_x = fs->win_x; jb->rs_win_y = fs->win_y; jb->rs_lay = fs->layout;
-      jb->rz_dw = getenv("NES_NO_RZ") ? 0 : fs->rz_dw;
+      jb->rz_dw = getenv("NES_NO_RZ") ? 0 : fs->rz_dw[bpp - 3];
     }
     job_alignment(jb);
     job_tiles(jb, tile_base);

@@ -34,6 +34,18 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// the same, letting the hardware keep the warp suspended for up to ~hint_ns before the try returns (fewer polls)
+__device__ __forceinline__ void mbar_wait_hint_a(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -157,7 +169,7 @@ __device__ __forceinline__ void stg64(uint8_t *p, uint32_t w0, uint32_t w1) { *(
 // The glyph list is bucketed by row band on the host, so only the glyphs near the chunk's rows are tested
 // (one thread each); the descriptors that hit are staged in shared memory; then a warp takes a glyph and a
 // lane one of its rows: ONE load of the row's bit mask (1 bit per pixel, DevPlaced) and a loop over its set bits.
-template <int BPP, int SW>
+template <int BPP, int SW, int HITS = STRIP_HITS>
 __device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *stage0, int qc, int ns, int slot_bytes, int x0, int x1, int yc0, int ra, int rb,
                                             int rgb_base, DevPlaced *s_hits, int *s_nhits) {
   constexpr int ROWB = SW * BPP;
@@ -169,10 +181,10 @@ __device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *stage0, i
   }
   const DevPlaced *__restrict__ glyphs = jb.glyphs;
   const uint32_t *__restrict__ atlas = jb.atlas;
-  for (int base = g_begin; base < g_end; base += STRIP_HITS) {
+  for (int base = g_begin; base < g_end; base += HITS) {
     if (tid == 0) *s_nhits = 0;
     consumer_sync();
-    if (tid < STRIP_HITS && base + tid < g_end) {
+    if (tid < HITS && base + tid < g_end) {
       const DevPlaced pg = glyphs[base + tid];
       if (pg.x < x1 && pg.x + pg.w > x0 && pg.y < rb && pg.y + pg.h > ra) s_hits[atomicAdd(s_nhits, 1)] = pg;
     }

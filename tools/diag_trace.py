@@ -51,10 +51,16 @@ def main():
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--mode", default="prepared", choices=["prepared", "convert"])
+    ap.add_argument("--text", default=None, help="override the workload's overlay: none | reference | dense")
+    ap.add_argument("--nsrc", type=int, default=0, help="override the number of sources")
     args = ap.parse_args()
     import ngp_encode_server_b200 as n
     import torch
-    wl = n.synth.WORKLOADS[args.workload]
+    wl = dict(n.synth.WORKLOADS[args.workload])
+    if args.text:
+        wl["text"] = args.text
+    if args.nsrc:
+        wl["n_src"] = args.nsrc
     s = n.Session(device=0, max_width=max(wl["w"], wl["wd"]), max_height=max(wl["h"], wl["hd"]), max_sources=wl["n_src"])
     m, b = n.synth.load_glyph_table()
     s.atlas_set(m, b)
