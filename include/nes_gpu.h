@@ -67,7 +67,8 @@ typedef enum nes_status {
   NES_ERR_PARSE = -7,         /* malformed / truncated nesproto.RenderedFrame           */
   NES_ERR_NO_ATLAS = -8,      /* text runs submitted before nes_gpu_atlas_set           */
   NES_ERR_FREETYPE = -9,      /* FreeType could not be loaded / font could not be opened */
-  NES_ERR_BUSY = -10          /* ring full: wait on an older ticket first               */
+  NES_ERR_BUSY = -10,         /* ring full: wait on an older ticket first               */
+  NES_ERR_UNSUPPORTED = -11   /* optional run-time dependency missing or of an unknown version */
 } nes_status;
 
 /* Pixel formats accepted on the scene input (AV_PIX_FMT_* names in the
@@ -323,6 +324,23 @@ NES_API int nes_ingest_acquire(nes_ingest_ring *r, int *slot, uint8_t **buf, uin
 NES_API int nes_ingest_commit(nes_ingest_ring *r, int slot, uint64_t len, int has_length_prefix,
                               int bytes_per_pixel, nes_unpacked_frame *info, nes_source *src);
 NES_API int nes_ingest_release(nes_ingest_ring *r, int slot);
+
+/* ---- encoder hand-off: planes as a ref-counted AVFrame ---------------------------------
+ * Replaces FrameManager::AVFrameWrapper / to_avframe() (type_managers.h:187-239), whose frame is not
+ * ref-counted -- avcodec_send_frame copies every plane (encode.cpp:136-137,164-165) -- and whose
+ * av_image_alloc block leaks.  The planes are wrapped with av_buffer_create (libavutil bound with dlopen:
+ * avutil_so may be NULL -> NES_AVUTIL_SO / the default soname): the encoder takes a reference instead of a copy;
+ * `release(opaque, planes[0])` runs when the last reference (the returned frame's, or the encoder's) is dropped.
+ * planes[1..2] may be NULL (one-plane formats).  av_pix_fmt is libavutil's AVPixelFormat value (0 = YUV420P).
+ * *out_frame is an AVFrame*; free it with nes_avframe_free (= av_frame_free).  Returns NES_ERR_UNSUPPORTED when
+ * libavutil is missing or its AVFrame layout is not the one this build knows (checked against the live library). */
+NES_API int nes_avframe_wrap(const char *avutil_so, uint8_t *const planes[3], const int linesize[3], int width, int height,
+                             int av_pix_fmt, int64_t pts, void (*release)(void *opaque, uint8_t *base), void *opaque,
+                             void **out_frame);
+NES_API void nes_avframe_free(void **frame);
+/* av_buffer_get_ref_count of the frame's first plane (tests: the encoder holds a reference, not a copy). */
+NES_API int nes_avframe_ref_count(void *frame);
+NES_API const char *nes_avframe_error(void);
 
 #ifdef __cplusplus
 }

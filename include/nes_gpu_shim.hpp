@@ -18,9 +18,14 @@
 //     the stamp happens on the device copy inside convert_frame(), in call order, before the
 //     colour conversion -- exactly the order of encode.cpp:76-98.  Nobody reads the source
 //     frame after convert_frame() in the reference, so the result is the same.
-//   * RenderedFrame is built from the wire bytes (zero-copy unpack) instead of a parsed
-//     nesproto::RenderedFrame; the accessors index()/is_left()/camera matrix come from the same
-//     fields.  With protobuf available, pass msg.frame().data() etc. to the pointer constructor.
+//   * RenderedFrame has the reference's constructor (a parsed nesproto::RenderedFrame + the two codec managers,
+//     rendered_frame.h:17-20) and a zero-copy one from the wire bytes.  Without protobuf (NES_SHIM_WITH_PROTOBUF
+//     undefined) a minimal nesproto::Camera / nesproto::RenderedFrame with the generated accessors
+//     (index(), is_left(), camera().matrix(), frame(), depth(), ParseFromString) stands in, parsed by
+//     nes_unpack_rendered_frame.
+//   * FrameManager::to_avframe() returns a REF-COUNTED AVFrame over the (pinned) planes: avcodec_send_frame
+//     takes a reference instead of copying, nothing leaks (the reference's wrapper orphans an av_image_alloc
+//     block per call, type_managers.h:201-218).
 //   * every thread that converts gets its own nes_gpu_session (lazily, device from
 //     NES_GPU_DEVICE or nes_shim::set_thread_device); errors become std::runtime_error like
 //     the reference's.
@@ -41,9 +46,12 @@
 
 #ifdef NES_SHIM_WITH_LIBAV
 extern "C" {
+#include <libavutil/buffer.h>
+#include <libavutil/frame.h>
 #include <libavutil/pixfmt.h>
 }
 #else
+struct AVFrame;  // opaque here: created and freed by libavutil through nes_avframe_wrap / nes_avframe_free
 // the few AVPixelFormat values the path uses (libavutil/pixfmt.h numbering)
 enum AVPixelFormat {
   AV_PIX_FMT_NONE = -1,
@@ -116,6 +124,62 @@ class ThreadSession {
 
 }  // namespace nes_shim
 
+#ifndef NES_SHIM_WITH_PROTOBUF
+// Stand-ins for the classes protoc generates from proto/nes.proto:4-25 (only what the hot path touches).
+namespace nesproto {
+class Camera {
+ public:
+  bool is_left() const { return m_is_left; }
+  uint32_t width() const { return m_width; }
+  uint32_t height() const { return m_height; }
+  const std::vector<float> &matrix() const { return m_matrix; }
+  int matrix_size() const { return (int)m_matrix.size(); }
+  void set_is_left(bool v) { m_is_left = v; }
+  void set_width(uint32_t v) { m_width = v; }
+  void set_height(uint32_t v) { m_height = v; }
+  void add_matrix(float v) { m_matrix.push_back(v); }
+
+ private:
+  bool m_is_left = false;
+  uint32_t m_width = 0, m_height = 0;
+  std::vector<float> m_matrix;
+};
+class RenderedFrame {
+ public:
+  uint64_t index() const { return m_index; }
+  bool is_left() const { return m_is_left; }
+  const Camera &camera() const { return m_camera; }
+  Camera *mutable_camera() { return &m_camera; }
+  const std::string &frame() const { return m_frame; }
+  const std::string &depth() const { return m_depth; }
+  void set_index(uint64_t v) { m_index = v; }
+  void set_is_left(bool v) { m_is_left = v; }
+  void set_frame(std::string v) { m_frame = std::move(v); }
+  void set_depth(std::string v) { m_depth = std::move(v); }
+  // server.cpp:175: the message without the 8-byte length prefix
+  bool ParseFromArray(const void *data, int size) {
+    nes_unpacked_frame u;
+    if (nes_unpack_rendered_frame(static_cast<const uint8_t *>(data), (uint64_t)size, 0, &u) != NES_OK) return false;
+    m_index = u.index; m_is_left = u.is_left != 0;
+    m_camera = Camera();
+    m_camera.set_is_left(u.cam_is_left != 0); m_camera.set_width((uint32_t)u.width); m_camera.set_height((uint32_t)u.height);
+    for (int i = 0; i < u.n_matrix; i++) m_camera.add_matrix(u.matrix[i]);
+    const char *p = static_cast<const char *>(data);
+    m_frame.assign(p + u.frame_off, u.frame_len);
+    m_depth.assign(p + u.depth_off, u.depth_len);
+    return true;
+  }
+  bool ParseFromString(const std::string &s) { return ParseFromArray(s.data(), (int)s.size()); }
+
+ private:
+  uint64_t m_index = 0;
+  bool m_is_left = false;
+  Camera m_camera;
+  std::string m_frame, m_depth;
+};
+}  // namespace nesproto
+#endif
+
 namespace types {
 
 // types::FrameManager (type_managers.h:159-247)
@@ -129,6 +193,10 @@ class FrameManager {
   };
   struct FrameContext {
     FrameContext(unsigned width, unsigned height, AVPixelFormat pix_fmt) : width(width), height(height), pix_fmt(pix_fmt) {}
+    // FrameContext(types::AVCodecContextManager::CodecInfoProvider) of the reference (type_managers.h:176-179):
+    // anything whose operator-> yields width / height / pix_fmt
+    template <class CodecInfoProvider, class = decltype(std::declval<CodecInfoProvider &>()->width)>
+    FrameContext(CodecInfoProvider codecinfo) : width(codecinfo->width), height(codecinfo->height), pix_fmt(codecinfo->pix_fmt) {}
     unsigned width;
     unsigned height;
     AVPixelFormat pix_fmt;
@@ -155,18 +223,20 @@ class FrameManager {
         total = (size_t)m_data.linesize[0] * h;
       }
       void *p = nullptr;
+      bool pinned = false;
       if (nes_gpu_host_alloc(total + 32, &p) == NES_OK) {
-        m_pinned = true;
+        pinned = true;
       } else if (!(p = std::malloc(total + 32))) {
         throw std::runtime_error{"Failed to allocate frame data."};
       }
+      // the block is shared with every AVFrame made from it (to_avframe): freed when the last owner lets go
+      m_block = std::shared_ptr<uint8_t>(static_cast<uint8_t *>(p), [pinned](uint8_t *q) { if (pinned) nes_gpu_host_free(q); else std::free(q); });
       m_data.data[0] = static_cast<uint8_t *>(p);
       if (context.pix_fmt == AV_PIX_FMT_YUV420P) {
         m_data.data[1] = m_data.data[0] + (size_t)m_data.linesize[0] * h;
         m_data.data[2] = m_data.data[1] + (size_t)m_data.linesize[1] * ((h + 1) / 2);
       }
     } else {
-      m_should_free_buffer = false;
       if (context.pix_fmt == AV_PIX_FMT_YUV420P) {
         m_data.linesize[0] = (int)w; m_data.linesize[1] = m_data.linesize[2] = (int)((w + 1) / 2);
         m_data.data[1] = buffer + (size_t)w * h;
@@ -184,19 +254,66 @@ class FrameManager {
   inline FrameData &data() { return m_data; }
   inline std::vector<TextRun> &text_runs() { return m_runs; }
 
-  ~FrameManager() {
-    if (m_should_free_buffer && m_data.data[0]) {
-      if (m_pinned) nes_gpu_host_free(m_data.data[0]);
-      else std::free(m_data.data[0]);
+  // FrameManager::AVFrameWrapper (type_managers.h:187-231): an AVFrame over this frame's planes, freed with the
+  // wrapper.  Unlike the reference's it is ref-counted (av_buffer_create over the shared block), so
+  // avcodec_send_frame keeps a reference instead of copying the planes, and it allocates nothing it then orphans.
+  class AVFrameWrapper {
+   public:
+    AVFrameWrapper(FrameData &data, FrameContext &context, std::shared_ptr<uint8_t> block) {
+      auto *keep = new std::shared_ptr<uint8_t>(std::move(block));  // dropped by the release callback
+      auto release = [](void *opaque, uint8_t *) { delete static_cast<std::shared_ptr<uint8_t> *>(opaque); };
+#ifdef NES_SHIM_WITH_LIBAV
+      m_avframe = av_frame_alloc();
+      if (m_avframe == nullptr) { delete keep; throw std::runtime_error{"Failed to allocate AVFrame."}; }
+      m_avframe->format = context.pix_fmt; m_avframe->width = (int)context.width; m_avframe->height = (int)context.height;
+      const int planes = context.pix_fmt == AV_PIX_FMT_YUV420P ? 3 : 1;
+      auto *count = new std::pair<int, std::shared_ptr<uint8_t> *>(planes, keep);
+      for (int p = 0; p < planes; p++) {
+        const int rows = p == 0 ? (int)context.height : ((int)context.height + 1) / 2;
+        m_avframe->buf[p] = av_buffer_create(data.data[p], (size_t)data.linesize[p] * rows,
+                                             [](void *o, uint8_t *) { auto *c = static_cast<std::pair<int, std::shared_ptr<uint8_t> *> *>(o); if (--c->first == 0) { delete c->second; delete c; } },
+                                             count, 0);
+        m_avframe->data[p] = data.data[p]; m_avframe->linesize[p] = data.linesize[p];
+      }
+      (void)release;
+#else
+      void *f = nullptr;
+      uint8_t *const planes[3] = {data.data[0], data.data[1], data.data[2]};
+      const int st = nes_avframe_wrap(nullptr, planes, data.linesize, (int)context.width, (int)context.height, (int)context.pix_fmt, 0, release, keep, &f);
+      if (st != NES_OK) {
+        delete keep;
+        throw std::runtime_error{std::string("AVFrameWrapper: Failed to allocate AVFrame data: ") + nes_gpu_strerror(st) + " (" + nes_avframe_error() + ")"};
+      }
+      m_avframe = static_cast<AVFrame *>(f);
+#endif
     }
+    AVFrameWrapper(const AVFrameWrapper &) = delete;
+    AVFrameWrapper(AVFrameWrapper &&o) noexcept : m_avframe(o.m_avframe) { o.m_avframe = nullptr; }
+    inline AVFrame *get() { return m_avframe; }
+    ~AVFrameWrapper() {
+#ifdef NES_SHIM_WITH_LIBAV
+      av_frame_free(&m_avframe);
+#else
+      void *f = m_avframe;
+      nes_avframe_free(&f);
+#endif
+    }
+
+   private:
+    AVFrame *m_avframe = nullptr;
+  };
+  inline AVFrameWrapper to_avframe() {
+    if (!m_block) throw std::runtime_error{"to_avframe: the frame borrows its buffer (only converted frames are handed to the encoder)"};
+    return AVFrameWrapper(m_data, m_context, m_block);
   }
+
+  ~FrameManager() {}
 
  private:
   FrameData m_data;
   FrameContext m_context;
   std::vector<TextRun> m_runs;  // overlays queued by RenderTextContext::render_string_to_frame
-  bool m_should_free_buffer = true;
-  bool m_pinned = false;
+  std::shared_ptr<uint8_t> m_block;  // owning mode: the planes' block (null when the buffer is borrowed)
 };
 
 namespace detail {
@@ -289,22 +406,36 @@ class RenderTextContext {
 // (server.cpp:91-112 framing + nes.proto:18-25), without copying the payload.
 class RenderedFrame {
  public:
-  // `message` must outlive the object (the reference copies it; here it is borrowed).
+  // The reference's constructor (rendered_frame.h:17-20, rendered_frame.cc:5-27): the parsed message is copied
+  // into the object, the source frames borrow its two byte strings, the destination frames take their size from
+  // the codec managers (anything with get_codec_info()-> width / height / pix_fmt).
+  template <class CodecContextManager>
+  RenderedFrame(nesproto::RenderedFrame frame, AVPixelFormat pix_fmt_scene, AVPixelFormat pix_fmt_depth,
+                std::shared_ptr<CodecContextManager> ctxmgr_scene, std::shared_ptr<CodecContextManager> ctxmgr_depth)
+      : m_frame_response(std::move(frame)),
+        m_source_avframe_scene(types::FrameManager::FrameContext(m_frame_response.camera().width(), m_frame_response.camera().height(), pix_fmt_scene),
+                               (uint8_t *)m_frame_response.frame().data()),
+        m_converted_avframe_scene(types::FrameManager::FrameContext(ctxmgr_scene->get_codec_info())),
+        m_source_avframe_depth(types::FrameManager::FrameContext(m_frame_response.camera().width(), m_frame_response.camera().height(), pix_fmt_depth),
+                               (uint8_t *)m_frame_response.depth().data()),
+        m_converted_avframe_depth(types::FrameManager::FrameContext(ctxmgr_depth->get_codec_info())),
+        m_converted(false) {
+    check_payload(m_frame_response.frame().size(), m_frame_response.depth().size(), pix_fmt_scene);
+  }
+
+  // Zero-copy variant: built straight from the wire bytes (server.cpp:91-112 framing + nes.proto:18-25); `message`
+  // must outlive the object (the payload is borrowed, not copied; scalar fields and the camera are extracted).
   RenderedFrame(const uint8_t *message, size_t len, bool has_length_prefix, AVPixelFormat pix_fmt_scene, AVPixelFormat pix_fmt_depth,
                 unsigned dst_width, unsigned dst_height)
-      : m_fields(unpack(message, len, has_length_prefix)),
-        m_source_avframe_scene(types::FrameManager::FrameContext(m_fields.width, m_fields.height, pix_fmt_scene),
-                               const_cast<uint8_t *>(message) + m_fields.frame_off),
+      : m_frame_response(scalars(message, len, has_length_prefix)),
+        m_source_avframe_scene(types::FrameManager::FrameContext(m_frame_response.camera().width(), m_frame_response.camera().height(), pix_fmt_scene),
+                               const_cast<uint8_t *>(message) + m_wire.frame_off),
         m_converted_avframe_scene(types::FrameManager::FrameContext(dst_width, dst_height, AV_PIX_FMT_YUV420P)),
-        m_source_avframe_depth(types::FrameManager::FrameContext(m_fields.width, m_fields.height, pix_fmt_depth),
-                               const_cast<uint8_t *>(message) + m_fields.depth_off),
+        m_source_avframe_depth(types::FrameManager::FrameContext(m_frame_response.camera().width(), m_frame_response.camera().height(), pix_fmt_depth),
+                               const_cast<uint8_t *>(message) + m_wire.depth_off),
         m_converted_avframe_depth(types::FrameManager::FrameContext(dst_width, dst_height, AV_PIX_FMT_YUV420P)),
         m_converted(false) {
-    const uint64_t px = (uint64_t)m_fields.width * m_fields.height;
-    // the reference trusts camera.width/height (rendered_frame.cc:14-25); a short payload is an
-    // out-of-bounds read there, an exception here
-    if (m_fields.frame_len < px * nes_shim::bytes_per_pixel(pix_fmt_scene) || m_fields.depth_len < px)
-      throw std::runtime_error{"RenderedFrame: payload shorter than width*height"};
+    check_payload(m_wire.frame_len, m_wire.depth_len, pix_fmt_scene);
   }
 
   inline void convert_frame() {
@@ -313,20 +444,33 @@ class RenderedFrame {
     m_converted = true;
   }
 
-  inline uint64_t index() const { return m_fields.index; }
-  inline bool is_left() const { return m_fields.is_left != 0; }
-  inline const nes_unpacked_frame &get_cam() const { return m_fields; }  // width, height, matrix[n_matrix]
+  inline uint64_t index() const { return m_frame_response.index(); }
+  inline bool is_left() const { return m_frame_response.is_left(); }
+  inline const nesproto::Camera &get_cam() const { return m_frame_response.camera(); }
   inline types::FrameManager &source_frame_scene() { return m_source_avframe_scene; }
   inline types::FrameManager &converted_frame_scene() { return m_converted_avframe_scene; }
   inline types::FrameManager &converted_frame_depth() { return m_converted_avframe_depth; }
 
  private:
-  static nes_unpacked_frame unpack(const uint8_t *message, size_t len, bool prefix) {
-    nes_unpacked_frame u;
-    nes_shim::check(nes_unpack_rendered_frame(message, len, prefix ? 1 : 0, &u), "nes_unpack_rendered_frame");
-    return u;
+  // scalar fields + camera of a wire message (the two byte strings stay where they are: m_wire keeps their offsets)
+  nesproto::RenderedFrame scalars(const uint8_t *message, size_t len, bool prefix) {
+    nes_shim::check(nes_unpack_rendered_frame(message, len, prefix ? 1 : 0, &m_wire), "nes_unpack_rendered_frame");
+    nesproto::RenderedFrame f;
+    f.set_index(m_wire.index); f.set_is_left(m_wire.is_left != 0);
+    nesproto::Camera *c = f.mutable_camera();
+    c->set_is_left(m_wire.cam_is_left != 0); c->set_width((uint32_t)m_wire.width); c->set_height((uint32_t)m_wire.height);
+    for (int i = 0; i < m_wire.n_matrix; i++) c->add_matrix(m_wire.matrix[i]);
+    return f;
   }
-  nes_unpacked_frame m_fields;
+  void check_payload(uint64_t frame_len, uint64_t depth_len, AVPixelFormat pix_fmt_scene) const {
+    const uint64_t px = (uint64_t)m_frame_response.camera().width() * m_frame_response.camera().height();
+    // the reference trusts camera.width/height (rendered_frame.cc:14-25); a short payload is an
+    // out-of-bounds read there, an exception here
+    if (frame_len < px * nes_shim::bytes_per_pixel(pix_fmt_scene) || depth_len < px)
+      throw std::runtime_error{"RenderedFrame: payload shorter than width*height"};
+  }
+  nes_unpacked_frame m_wire{};             // declared before m_frame_response: scalars() fills it
+  nesproto::RenderedFrame m_frame_response;
   types::FrameManager m_source_avframe_scene;
   types::FrameManager m_converted_avframe_scene;
   types::FrameManager m_source_avframe_depth;

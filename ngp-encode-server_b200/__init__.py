@@ -8,3 +8,4 @@ from .api import *  # noqa: F401,F403
 from . import api  # noqa: F401
 from . import synth  # noqa: F401,E402
 from . import shard  # noqa: F401,E402
+from . import avhandoff  # noqa: F401,E402

@@ -37,7 +37,7 @@ RENDER_POSITION_LEFT_TOP, RENDER_POSITION_LEFT_BOTTOM, RENDER_POSITION_RIGHT_TOP
 
 NES_OK = 0
 NES_ERR_INVALID_ARG, NES_ERR_SHORT_BUFFER, NES_ERR_TOO_LARGE, NES_ERR_CUDA = -1, -2, -3, -4
-NES_ERR_NO_MEMORY, NES_ERR_BAD_TICKET, NES_ERR_PARSE, NES_ERR_NO_ATLAS, NES_ERR_FREETYPE, NES_ERR_BUSY = -5, -6, -7, -8, -9, -10
+NES_ERR_NO_MEMORY, NES_ERR_BAD_TICKET, NES_ERR_PARSE, NES_ERR_NO_ATLAS, NES_ERR_FREETYPE, NES_ERR_BUSY, NES_ERR_UNSUPPORTED = -5, -6, -7, -8, -9, -10, -11
 
 
 class NesGpuError(RuntimeError):
@@ -96,6 +96,7 @@ ABI_SYMBOLS = [
     "nes_gpu_memcpy_h2d", "nes_gpu_memcpy_d2h", "nes_gpu_atlas_set", "nes_gpu_atlas_load_font",
     "nes_font_rasterise", "nes_gpu_submit", "nes_gpu_wait", "nes_gpu_convert", "nes_gpu_convert_batch_device", "nes_gpu_last_timing",
     "nes_gpu_batch_prepare", "nes_gpu_batch_run", "nes_gpu_batch_free",
+    "nes_avframe_wrap", "nes_avframe_free", "nes_avframe_ref_count", "nes_avframe_error",
     "nes_gpu_filter_table", "nes_gpu_text_layout", "nes_unpack_rendered_frame",
     "nes_ingest_ring_create", "nes_ingest_ring_destroy", "nes_ingest_acquire", "nes_ingest_commit", "nes_ingest_release",
 ]
@@ -154,6 +155,11 @@ def lib() -> C.CDLL:
     L.nes_ingest_acquire.argtypes = [vp, C.POINTER(i32), C.POINTER(vp), C.POINTER(u64)]
     L.nes_ingest_commit.argtypes = [vp, i32, u64, i32, i32, C.POINTER(nes_unpacked_frame), C.POINTER(nes_source)]
     L.nes_ingest_release.argtypes = [vp, i32]
+    L.nes_avframe_wrap.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(i32), i32, i32, i32, C.c_int64, vp, vp, C.POINTER(vp)]
+    L.nes_avframe_free.argtypes = [C.POINTER(vp)]
+    L.nes_avframe_free.restype = None
+    L.nes_avframe_ref_count.argtypes = [vp]
+    L.nes_avframe_error.restype = C.c_char_p
     _lib = L
     return L
 
@@ -300,11 +306,15 @@ class Session:
             raise NesGpuError(r, "nes_gpu_session_create", strerror(r))
         self.device = device
         self._keep = {}
+        self._dev = set()
 
     def close(self):
         """Destroys the session and frees the pinned buffers host_array() handed out (arrays obtained from
         host_array must not be touched afterwards)."""
         if self.h:
+            for p in list(self._dev):
+                self.L.nes_gpu_device_free(self.h, p)
+            self._dev.clear()
             self.L.nes_gpu_session_destroy(self.h)
             self.h = C.c_void_p()
             for p in self._keep.values():
@@ -349,9 +359,11 @@ class Session:
     def device_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
         self._check(self.L.nes_gpu_device_alloc(self.h, nbytes, C.byref(p)), "nes_gpu_device_alloc")
+        self._dev.add(p.value)
         return p.value
 
     def device_free(self, p: int):
+        self._dev.discard(p)
         self.L.nes_gpu_device_free(self.h, p)
 
     def h2d(self, dst: int, src: np.ndarray):

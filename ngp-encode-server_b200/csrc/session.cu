@@ -595,6 +595,7 @@ const char *nes_gpu_strerror(int st) {
     case NES_ERR_NO_ATLAS: return "text submitted before a glyph atlas was set";
     case NES_ERR_FREETYPE: return "FreeType unavailable or font could not be opened";
     case NES_ERR_BUSY: return "frame ring full; wait on an older ticket";
+    case NES_ERR_UNSUPPORTED: return "optional run-time dependency missing or of an unknown version";
     default: return "unknown status";
   }
 }

@@ -31,15 +31,23 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> wire((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
     auto etctx = std::make_shared<RenderTextContext>(argv[2], argv[3]);
     const unsigned dw = (unsigned)std::atoi(argv[4]), dh = (unsigned)std::atoi(argv[5]);
-    // server.cpp:193-194: RGB24 scene + GRAY8 depth
-    std::unique_ptr<RenderedFrame> frame = std::make_unique<RenderedFrame>(wire.data(), wire.size(), true, AV_PIX_FMT_RGB24, AV_PIX_FMT_GRAY8, dw, dh);
+    // server.cpp:172-194: ParseFromString of the message, then the reference's RenderedFrame constructor
+    // (RGB24 scene + GRAY8 depth, destination size from the codec managers)
+    struct Codec {
+      struct Info { unsigned width, height; AVPixelFormat pix_fmt; };
+      Info info;
+      Info *get_codec_info() { return &info; }
+    };
+    auto ctx_scene = std::make_shared<Codec>(Codec{{dw, dh, AV_PIX_FMT_YUV420P}}), ctx_depth = std::make_shared<Codec>(Codec{{dw, dh, AV_PIX_FMT_YUV420P}});
+    nesproto::RenderedFrame msg;
+    if (!msg.ParseFromArray(wire.data() + 8, (int)wire.size() - 8)) { std::fprintf(stderr, "ParseFromArray failed\n"); return 4; }
+    std::unique_ptr<RenderedFrame> frame = std::make_unique<RenderedFrame>(msg, AV_PIX_FMT_RGB24, AV_PIX_FMT_GRAY8, ctx_scene, ctx_depth);
 
     // ---- encode.cpp:55-98 ----------------------------------------------------------------
     uint64_t frame_index = frame->index();
     std::stringstream cam_matrix;
     int idx = 0;
-    for (int i = 0; i < frame->get_cam().n_matrix; i++) {
-      float it = frame->get_cam().matrix[i];
+    for (auto it : frame->get_cam().matrix()) {
       idx++;
       cam_matrix << std::fixed << std::showpos << std::setw(7) << std::setprecision(5) << std::setfill('0') << it << ' ';
       if (idx % 4 == 0) cam_matrix << '\n';
@@ -61,6 +69,19 @@ int main(int argc, char **argv) {
 
     dump(frame->converted_frame_scene(), std::string(argv[7]) + ".scene.yuv");
     dump(frame->converted_frame_depth(), std::string(argv[7]) + ".depth.yuv");
+
+    // the zero-copy constructor (wire bytes, payload borrowed) gives the same planes
+    {
+      RenderedFrame z(wire.data(), wire.size(), true, AV_PIX_FMT_RGB24, AV_PIX_FMT_GRAY8, dw, dh);
+      for (auto &r : frame->source_frame_scene().text_runs()) z.source_frame_scene().text_runs().push_back(r);
+      z.convert_frame();
+      dump(z.converted_frame_scene(), std::string(argv[7]) + ".zero.yuv");
+    }
+    // encoder hand-off (encode.cpp:136-137): to_avframe() is a ref-counted AVFrame over the converted planes
+    {
+      auto wrapped = frame->converted_frame_scene().to_avframe();
+      if (nes_avframe_ref_count(wrapped.get()) != 1) { std::fprintf(stderr, "to_avframe: unexpected reference count\n"); return 5; }
+    }
 
     // types::SwsContextManager on its own (type_managers.cc:143-155)
     types::FrameManager dst(types::FrameManager::FrameContext(dw, dh, AV_PIX_FMT_YUV420P));

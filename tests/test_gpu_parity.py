@@ -2,6 +2,8 @@
 (oracle/liboracle_port.so, pinned to libswscale 9.1.100 / FreeType 2.14.3 by
 tests/test_oracle.py) and against the committed golden vectors.  Bit-exact everywhere:
 this is integer / byte work."""
+import os
+
 import numpy as np
 import pytest
 
@@ -459,6 +461,39 @@ def test_cpp_shim_process_frame(N, O, port, glyphs, tmp_path):
     assert (tmp_path / "o.scene.yuv").read_bytes() == want_s
     assert (tmp_path / "o.depth.yuv").read_bytes() == want_d
     assert (tmp_path / "o.sws.yuv").read_bytes() == want_s
+    assert (tmp_path / "o.zero.yuv").read_bytes() == want_s   # zero-copy constructor (wire bytes borrowed)
+
+
+def test_reference_encode_cpp_text_runs(N, O, port, glyphs, tmp_path):
+    """The reference's OWN process_frame_thread + send_frame_thread text (extracted from /root/reference at test time,
+    where it is mounted) run against the shim on the GPU: one frame goes through the four overlays, convert_frame()
+    and the to_avframe() hand-off.  The timestamp overlay is wall-clock text: the planes are compared with the oracle
+    outside the rows it can touch; the depth planes entirely."""
+    import subprocess
+    from conftest import FONT
+    import test_host
+    if not os.path.exists(test_host.REFERENCE_ENCODE_CPP):
+        pytest.skip("the reference tree is only mounted in the build container (tests/cpp/process_frame.cpp is the committed restatement)")
+    if N.find_freetype() is None:
+        pytest.skip("no FreeType binary in this image")
+    exe = test_host.build_encode_text_driver(tmp_path)
+    w, h = 1280, 720
+    rgb, dep = O.synth_rgb(w, h, 5), O.synth_depth(w, h, 5)
+    (tmp_path / "m.bin").write_bytes(O.pack_rendered_frame(0, True, w, h, O.KINITIAL_CAMERA_MATRIX, rgb.tobytes(), dep.tobytes()))
+    r = subprocess.run([exe, str(tmp_path / "m.bin"), FONT, N.find_freetype(), str(w), str(h), str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip().startswith("ok index=0 sent=1+1")
+    surf = np.ascontiguousarray(rgb.copy())
+    for pos, txt in O.reference_strings(index=0, is_left=True):
+        if pos != O.POS_LEFT_TOP:
+            port.render_string(surf, pos, txt, glyphs)
+    want = port.rgb_to_yuv420p(surf, "rgb24")
+    got = np.frombuffer((tmp_path / "o.scene.yuv").read_bytes(), np.uint8)
+    gy = got[: w * h].reshape(h, w)
+    assert np.array_equal(gy[80:], want.y[80:, :w])                 # below the timestamp line (LEFT_TOP: baseline y = 50)
+    assert np.array_equal(gy[:80, 400:], want.y[:80, 400:w])        # right of it
+    assert (gy[:80, :400] != want.y[:80, :400]).any()               # and the timestamp was stamped
+    assert (tmp_path / "o.depth.yuv").read_bytes() == port.gray_to_yuv420p(dep).cropped()
 
 
 # ------------------------------------------------------------------ wider coverage of the kernels' paths

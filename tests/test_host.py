@@ -38,6 +38,102 @@ def test_cpp_shim_compiles_and_fails_loudly_without_gpu(N, O, tmp_path):
     assert r.returncode == 1 and "payload shorter" in r.stderr
 
 
+REFERENCE_ENCODE_CPP = "/root/reference/src/encode.cpp"
+
+
+def extract_reference_encode_text(dst_path):
+    """The reference's own text of timestamp(), process_frame_thread and send_frame_thread
+    (/root/reference/src/encode.cpp:23-212), verbatim, into `dst_path` -- read at test time, never committed."""
+    src = open(REFERENCE_ENCODE_CPP).read()
+    a, b = src.index("std::string timestamp() {"), src.index("int receive_packet_handler(")
+    text = src[a:b]
+    assert "void process_frame_thread(" in text and "void send_frame_thread(" in text and "frame->get_cam().matrix()" in text
+    assert ".to_avframe().get()" in text
+    with open(dst_path, "w") as f:
+        f.write(text)
+
+
+def build_encode_text_driver(tmp_path):
+    extract_reference_encode_text(str(tmp_path / "encode_text.inc"))
+    exe = str(tmp_path / "encode_text_driver")
+    lib_dir = os.path.join(ROOT, "ngp-encode-server_b200")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp"), "-I", str(tmp_path),
+                    os.path.join(ROOT, "tests", "cpp", "encode_text_driver.cpp"), "-o", exe, "-L", lib_dir, "-l:libnes_gpu.so", f"-Wl,-rpath,{lib_dir}", "-pthread"],
+                   check=True)
+    return exe
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_ENCODE_CPP), reason="the reference tree is only mounted in the build container")
+def test_reference_encode_cpp_text_compiles_against_the_shim(N, O, tmp_path):
+    """Signature fidelity of the drop-in: the UNMODIFIED text of the reference's process_frame_thread and
+    send_frame_thread (src/encode.cpp:23-212) compiles and links against include/nes_gpu_shim.hpp (+ stand-ins for the
+    queues / logger / codec manager that are out of scope): get_cam().matrix(), the RenderedFrame constructor taking the
+    parsed message and the two codec managers, render_string_to_frame, convert_frame(), to_avframe().get().
+    Without a GPU the run stops at the first conversion with a CUDA error (no CPU fallback)."""
+    exe = build_encode_text_driver(tmp_path)
+    if N.device_count() > 0 or N.find_freetype() is None:
+        return
+    msg = O.pack_rendered_frame(0, True, 64, 32, O.KINITIAL_CAMERA_MATRIX, O.synth_rgb(64, 32).tobytes(), O.synth_depth(64, 32).tobytes())
+    (tmp_path / "m.bin").write_bytes(msg)
+    r = subprocess.run([exe, str(tmp_path / "m.bin"), os.path.join(ROOT, "tests", "golden", "Aileron-Regular.ttf"), N.find_freetype(), "64", "32", str(tmp_path / "o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "CUDA error" in r.stderr, (r.returncode, r.stderr)
+
+
+def test_avframe_handoff(N):
+    """nes_avframe_wrap (replaces FrameManager::AVFrameWrapper / to_avframe, type_managers.h:187-239): the planes of a
+    converted frame as a ref-counted AVFrame of the REAL libavutil bundled in this image -- fields where libavutil
+    expects them, no copy (the frame's data pointers are the FrameManager's), release callback on the last unref,
+    and a real encoder (libavcodec mpeg4; no H.264 encoder exists here) accepts it."""
+    import ctypes as C
+    import numpy as np
+    av = N.avhandoff
+    paths = av.bundled_ffmpeg()
+    if not paths["avutil"] or not paths["avcodec"]:
+        pytest.skip("no bundled FFmpeg in this image")
+    w, h = 640, 360
+    fm = N.FrameManager(N.FrameContext(w, h, "yuv420p"))
+    yy, xx = np.mgrid[0:h, 0:fm.linesize[0]]
+    fm.planes[0][:] = ((3 * xx + 5 * yy) & 255).astype(np.uint8)
+    fm.planes[1][:] = 100
+    fm.planes[2][:] = 160
+    L = N.lib()
+    released = []
+    CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+    cb = CB(lambda opaque, base: released.append(base))
+    planes = (C.c_void_p * 3)(*fm.data[:3])
+    ls = (C.c_int * 3)(*fm.linesize[:3])
+    fr = C.c_void_p()
+    r = L.nes_avframe_wrap(paths["avutil"].encode(), planes, ls, w, h, 0, 42, C.cast(cb, C.c_void_p), None, C.byref(fr))
+    assert r == 0, L.nes_avframe_error()
+    # the public head of AVFrame (libavutil/frame.h): data[8], linesize[8], extended_data, width, height, nb_samples, format
+    base = fr.value
+    assert [C.c_uint64.from_address(base + 8 * i).value for i in range(3)] == list(fm.data[:3])          # no copy
+    assert [C.c_int.from_address(base + 64 + 4 * i).value for i in range(3)] == list(fm.linesize[:3])
+    assert C.c_uint64.from_address(base + 96).value == base                                                  # extended_data == data
+    assert (C.c_int.from_address(base + 104).value, C.c_int.from_address(base + 108).value, C.c_int.from_address(base + 116).value) == (w, h, 0)
+    assert L.nes_avframe_ref_count(fr) == 1
+    # libavutil itself agrees: av_frame_clone takes references to the same buffers (no new allocation of planes)
+    avutil = C.CDLL(paths["avutil"])
+    avutil.av_frame_clone.restype = C.c_void_p
+    avutil.av_frame_clone.argtypes = [C.c_void_p]
+    avutil.av_frame_free.argtypes = [C.POINTER(C.c_void_p)]
+    clone = C.c_void_p(avutil.av_frame_clone(fr))
+    assert clone.value and C.c_uint64.from_address(clone.value).value == fm.data[0] and L.nes_avframe_ref_count(fr) == 2
+    # a real encoder takes it
+    enc = av.Encoder("mpeg4", w, h)
+    assert enc.send(fr) >= 0
+    enc.close()
+    L.nes_avframe_free(C.byref(fr))
+    assert fr.value is None and released == []        # the clone still references the planes
+    avutil.av_frame_free(C.byref(clone))
+    assert released == [fm.data[0]]                   # last reference gone: the block goes back to its owner, once
+    # bad arguments
+    assert L.nes_avframe_wrap(None, planes, ls, 0, h, 0, 0, None, None, C.byref(fr)) == N.NES_ERR_INVALID_ARG
+    t = av.time_substitute_encoder(320, 180, 8)
+    assert t["status"] == "substitute" and t["encoder"] == "mpeg4" and t["packets"] >= 1 and t["value"] > 0
+
+
 def test_shard_partition(N):
     for world in (1, 2, 4, 8):
         shards = [N.shard.sessions_of_rank(r, world, 64) for r in range(world)]
