@@ -499,7 +499,117 @@ class Harness:
         for b in batches:
             s.batch_free(b)
         s.close()
+        if wl.get("sessions", 1) > 1 and not args.no_e2e:
+            out["sessions"] = self.measure_sessions(name, 2.0 if full else 1.2)
+            out["verified"] = bool(out["verified"] and out["sessions"]["verified"])
         return out
+
+    def measure_sessions(self, name: str, seconds: float):
+        """BASELINE config 4: `sessions` concurrent client sessions sharded s -> GPU s % n (this rank serves its shard),
+        one host thread per 8 sessions, every session submits single frames from pinned host buffers through
+        nes_gpu_submit / nes_gpu_wait with 2 frames in flight; the rank's mux coalesces the ready frames of all its
+        sessions into shared launches.  -> aggregate frames/s (H2D + D2H inside), mux statistics."""
+        import threading
+        n, torch = self.n, self.torch
+        wl = n.synth.WORKLOADS[name]
+        total_sessions = wl["sessions"]
+        mine = n.shard.sessions_of_rank(self.rank, self.world, total_sessions)
+        w, h, wd, hd = wl["w"], wl["h"], wl["wd"], wl["hd"]
+        bpp = n.PIX_BPP[wl["fmt"]]
+        metrics, bitmaps = n.synth.load_glyph_table()
+        mux = n.Mux(device=self.local, max_batch=64)
+        sess = []
+        base_frames = [n.synth.make_sources(wl, f) for f in range(2)]  # two distinct frames, copied per session
+        for sid in mine:
+            s_ = n.Session(device=self.local, max_width=max(w, wd), max_height=max(h, hd), max_sources=wl["n_src"], ring_depth=2)
+            s_.atlas_set(metrics, bitmaps)
+            mux.attach(s_)
+            slots = []
+            for f in range(2):
+                src_host = []
+                for px, dep in base_frames[f]:
+                    hp, hd_ = s_.host_array(px.nbytes), s_.host_array(dep.nbytes)
+                    hp[:] = px.reshape(-1); hd_[:] = dep.reshape(-1)
+                    src_host.append((hp, hd_, 0, 0))
+                fin = n.Session.frame_in(wl["fmt"], w, h, src_host)
+                sc = n.FrameManager(n.FrameContext(wd, hd, "yuv420p"), session=s_)
+                dp = n.FrameManager(n.FrameContext(wd, hd, "yuv420p"), session=s_)
+                runs = n.Session.make_runs(n.synth.text_runs(wl, f))
+                slots.append((fin, runs, n.api._frame_out(sc, dp), sc, dp, src_host))
+            sess.append((s_, slots))
+        n_threads = max(1, len(sess) // 8)
+        counts = [0] * n_threads
+        stop = threading.Event()
+        go = threading.Event()
+        errors = []
+
+        def drive(tid):
+            try:
+                my = sess[tid::n_threads]
+                tickets = [[None, None] for _ in my]
+                go.wait()
+                it = 0
+                while not stop.is_set():
+                    f = it & 1
+                    for i, (s_, slots) in enumerate(my):
+                        if tickets[i][f] is not None:
+                            s_.wait(tickets[i][f])
+                            counts[tid] += 1
+                        tickets[i][f] = s_.submit_prepared(slots[f][0], slots[f][1], slots[f][2])
+                    it += 1
+                for i, (s_, slots) in enumerate(my):
+                    for f in range(2):
+                        if tickets[i][f] is not None:
+                            s_.wait(tickets[i][f])
+                            counts[tid] += 1
+            except Exception as e:  # noqa: BLE001
+                errors.append(repr(e))
+                stop.set()
+
+        ths = [threading.Thread(target=drive, args=(t,)) for t in range(n_threads)]
+        for t in ths:
+            t.start()
+        torch.cuda.synchronize()
+        self.barrier()
+        t0 = time.time()
+        p0 = time.perf_counter()
+        go.set()
+        time.sleep(0.3)  # ramp: every session has frames in flight
+        c0, p1 = sum(counts), time.perf_counter()
+        time.sleep(seconds)
+        c1, p2 = sum(counts), time.perf_counter()
+        stop.set()
+        for t in ths:
+            t.join()
+        t1 = time.time()
+        if self.sampler:
+            self.sampler.window(t0, t1)
+        fps_rank = (c1 - c0) / (p2 - p1)
+        if self.world > 1:
+            tt = torch.tensor([fps_rank], device="cuda", dtype=torch.float64)
+            self.dist.all_reduce(tt, op=self.dist.ReduceOp.SUM)
+            fps = float(tt.item())
+        else:
+            fps = fps_rank
+        self.barrier()
+        st = mux.stats()
+        # one output of the last round against the golden hash of frame 0 / 1 (frame 0's is committed)
+        g = self.golden.get(name)
+        s0, slots0 = sess[0]
+        ok = (not errors) and g is not None and sha16(slots0[0][3].cropped()) == g["scene"] and sha16(slots0[0][4].cropped()) == g["depth"]
+        in_bytes = wl["n_src"] * (bpp + 1) * w * h
+        out_bytes = 2 * (n.align32(wd) * hd + 2 * n.align32(wd // 2) * (hd // 2))
+        res = {"value": fps, "unit": UNIT, "sessions": total_sessions, "sessions_this_rank": len(mine), "host_threads_per_rank": n_threads, "frames_in_flight_per_session": 2,
+               "seconds": round(p2 - p1, 3), "h2d_bytes_per_frame": in_bytes, "d2h_bytes_per_frame": out_bytes, "verified": bool(ok),
+               "mux": {"frames": st["frames"], "launch_sets": st["launch_sets"], "launches": st["launches"], "max_batch": st["max_batch"],
+                       "mean_batch": round(st["frames"] / max(st["launch_sets"], 1), 2)},
+               "what": "sessions s -> GPU s % n, nes_gpu_submit / nes_gpu_wait per frame from pinned host buffers, one nes_gpu_mux per GPU"}
+        if errors:
+            res["errors"] = errors[:3]
+        for s_, _ in sess:
+            s_.close()
+        mux.close()
+        return res
 
     def copy_ceiling(self, host_srcs, fouts_host, seconds: float):
         torch = self.torch
@@ -622,7 +732,7 @@ def main():
     line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(n.synth, args.workload)}
-    for k in ("frames_per_step", "frames_per_launch", "launches_per_step", "l2", "roofline", "e2e", "gpu_launches", "verified", "verify",
+    for k in ("frames_per_step", "frames_per_launch", "launches_per_step", "l2", "roofline", "e2e", "gpu_launches", "verified", "verify", "sessions",
               "p50_frame_latency_ms", "p50_frame_latency_ms_2_bands", "single_frame_launch_fps", "single_frame_api_fps", "single_frame_api_host_us",
               "host_issue_ms_per_step"):
         if k in main_res:
@@ -638,7 +748,7 @@ def main():
             try:
                 r = H.measure(name, max(5, min(args.steps, 40)), 3, full=False)
                 extra[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "frames_per_step", "frames_per_launch", "roofline", "e2e", "verified",
-                                                 "p50_frame_latency_ms", "gpu_launches") if k in r}
+                                                 "p50_frame_latency_ms", "gpu_launches", "sessions") if k in r}
                 extra[name]["config"] = workload_config(n.synth, name)
             except Exception as e:  # noqa: BLE001
                 extra[name] = {"error": repr(e)[:300]}

@@ -325,6 +325,26 @@ NES_API int nes_ingest_commit(nes_ingest_ring *r, int slot, uint64_t len, int ha
                               int bytes_per_pixel, nes_unpacked_frame *info, nes_source *src);
 NES_API int nes_ingest_release(nes_ingest_ring *r, int slot);
 
+/* ---- many client sessions on one GPU: one launch for all their ready frames --------------
+ * BASELINE config 4 (64 concurrent sessions sharded over the GPUs; the reference is one process per session,
+ * main.cpp:133-171, one process_frame_thread per eye, :274-282).  Create one mux per GPU and attach that GPU's
+ * sessions: nes_gpu_submit on an attached session stages the frame on the caller's thread (descriptor, H2D copies on
+ * the session's own stream) and hands it to the mux's dispatcher thread, which gathers whatever frames are ready --
+ * it never waits for a batch to fill -- into one descriptor table and one kernel launch, then enqueues every frame's
+ * download on its session's stream.  nes_gpu_wait / nes_gpu_convert work as before.  Destroy the sessions first. */
+typedef struct nes_gpu_mux nes_gpu_mux;
+typedef struct nes_mux_stats {
+  uint64_t frames;      /* frames dispatched                                             */
+  uint64_t launch_sets; /* dispatches (one descriptor table each)                        */
+  uint64_t launches;    /* kernel launches                                               */
+  uint64_t max_batch;   /* most frames in one dispatch                                   */
+} nes_mux_stats;
+NES_API int nes_gpu_mux_create(int device, int max_batch /* frames per launch; 0 -> 64 */, nes_gpu_mux **out);
+NES_API void nes_gpu_mux_destroy(nes_gpu_mux *m);
+NES_API int nes_gpu_mux_attach(nes_gpu_mux *m, nes_gpu_session *s);
+NES_API int nes_gpu_mux_stats(nes_gpu_mux *m, nes_mux_stats *out);
+NES_API const char *nes_gpu_mux_error(nes_gpu_mux *m);
+
 /* ---- encoder hand-off: planes as a ref-counted AVFrame ---------------------------------
  * Replaces FrameManager::AVFrameWrapper / to_avframe() (type_managers.h:187-239), whose frame is not
  * ref-counted -- avcodec_send_frame copies every plane (encode.cpp:136-137,164-165) -- and whose

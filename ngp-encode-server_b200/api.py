@@ -77,6 +77,10 @@ class nes_timing(C.Structure):
     _fields_ = [("h2d_us", C.c_float), ("kernels_us", C.c_float), ("d2h_us", C.c_float), ("total_us", C.c_float), ("n_launches", C.c_int32), ("reserved", C.c_int32)]
 
 
+class nes_mux_stats(C.Structure):
+    _fields_ = [("frames", C.c_uint64), ("launch_sets", C.c_uint64), ("launches", C.c_uint64), ("max_batch", C.c_uint64)]
+
+
 class nes_placed_glyph(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("code", C.c_int32), ("reserved", C.c_int32),
                 ("clip_x", C.c_int32), ("clip_y", C.c_int32), ("clip_w", C.c_int32), ("clip_h", C.c_int32)]
@@ -97,6 +101,7 @@ ABI_SYMBOLS = [
     "nes_font_rasterise", "nes_gpu_submit", "nes_gpu_wait", "nes_gpu_convert", "nes_gpu_convert_batch_device", "nes_gpu_last_timing",
     "nes_gpu_batch_prepare", "nes_gpu_batch_run", "nes_gpu_batch_free",
     "nes_avframe_wrap", "nes_avframe_free", "nes_avframe_ref_count", "nes_avframe_error",
+    "nes_gpu_mux_create", "nes_gpu_mux_destroy", "nes_gpu_mux_attach", "nes_gpu_mux_stats", "nes_gpu_mux_error",
     "nes_gpu_filter_table", "nes_gpu_text_layout", "nes_unpack_rendered_frame",
     "nes_ingest_ring_create", "nes_ingest_ring_destroy", "nes_ingest_acquire", "nes_ingest_commit", "nes_ingest_release",
 ]
@@ -155,6 +160,13 @@ def lib() -> C.CDLL:
     L.nes_ingest_acquire.argtypes = [vp, C.POINTER(i32), C.POINTER(vp), C.POINTER(u64)]
     L.nes_ingest_commit.argtypes = [vp, i32, u64, i32, i32, C.POINTER(nes_unpacked_frame), C.POINTER(nes_source)]
     L.nes_ingest_release.argtypes = [vp, i32]
+    L.nes_gpu_mux_create.argtypes = [i32, i32, C.POINTER(vp)]
+    L.nes_gpu_mux_destroy.argtypes = [vp]
+    L.nes_gpu_mux_destroy.restype = None
+    L.nes_gpu_mux_attach.argtypes = [vp, vp]
+    L.nes_gpu_mux_stats.argtypes = [vp, C.POINTER(nes_mux_stats)]
+    L.nes_gpu_mux_error.argtypes = [vp]
+    L.nes_gpu_mux_error.restype = C.c_char_p
     L.nes_avframe_wrap.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(i32), i32, i32, i32, C.c_int64, vp, vp, C.POINTER(vp)]
     L.nes_avframe_free.argtypes = [C.POINTER(vp)]
     L.nes_avframe_free.restype = None
@@ -499,6 +511,41 @@ class Session:
         t = nes_timing()
         self._check(self.L.nes_gpu_last_timing(self.h, C.byref(t)), "nes_gpu_last_timing")
         return {"h2d_us": t.h2d_us, "kernels_us": t.kernels_us, "d2h_us": t.d2h_us, "total_us": t.total_us, "n_launches": t.n_launches}
+
+
+class Mux:
+    """nes_gpu_mux: the client sessions of one GPU share one dispatcher -- nes_gpu_submit on an attached session only
+    stages the frame, the ready frames of all sessions go out in one launch (BASELINE config 4)."""
+
+    def __init__(self, device: int = 0, max_batch: int = 64):
+        self.L = lib()
+        self.h = C.c_void_p()
+        r = self.L.nes_gpu_mux_create(device, max_batch, C.byref(self.h))
+        if r:
+            self.h = C.c_void_p()
+            raise NesGpuError(r, "nes_gpu_mux_create", strerror(r))
+        self.device = device
+
+    def attach(self, session: "Session"):
+        r = self.L.nes_gpu_mux_attach(self.h, session.h)
+        if r:
+            raise NesGpuError(r, "nes_gpu_mux_attach", strerror(r))
+
+    def stats(self) -> dict:
+        st = nes_mux_stats()
+        r = self.L.nes_gpu_mux_stats(self.h, C.byref(st))
+        if r:
+            raise NesGpuError(r, "nes_gpu_mux_stats", strerror(r))
+        return {"frames": st.frames, "launch_sets": st.launch_sets, "launches": st.launches, "max_batch": st.max_batch}
+
+    def error(self) -> str:
+        return self.L.nes_gpu_mux_error(self.h).decode()
+
+    def close(self):
+        """Destroy the attached sessions first."""
+        if self.h:
+            self.L.nes_gpu_mux_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class FrameContext:

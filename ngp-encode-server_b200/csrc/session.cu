@@ -11,12 +11,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <unordered_map>
 #include <vector>
@@ -55,7 +57,25 @@ struct StagedCopy {  // pinned staging -> caller memory, done in wait()
   size_t bytes;
 };
 
+struct PlaneLayout {  // where one YUV420P image sits inside a linear buffer
+  size_t off[3];
+  size_t bytes[3];
+  size_t total;
+};
+
+// what the download of a frame needs to know (kept with the slot: a multiplexed frame is downloaded by the dispatcher)
+struct Download {
+  nes_frame_out out{};
+  PlaneLayout ps{}, pd{};
+  bool direct = false, want_depth = false;
+  int nimg = 1, nplanes = 3;
+};
+
 struct Slot {
+  Download dl;
+  int deferred = 0;    // staged by nes_gpu_submit, launched and downloaded by the session's mux
+  int dispatched = 0;  // (guarded by the mux's done_mu) the mux has enqueued kernels + download: e_out is recorded
+  int dl_status = 0;   // status of the dispatcher's part
   uint8_t *d_in = nullptr, *d_out = nullptr;
   size_t d_in_cap = 0, d_out_cap = 0;
   uint8_t *h_in = nullptr, *h_out = nullptr;
@@ -87,6 +107,10 @@ struct BatchTables {
 
 }  // namespace
 
+struct nes_gpu_mux;
+static int mux_enqueue(nes_gpu_mux *m, nes_gpu_session *s, int slot_index);
+static void mux_wait_dispatched(nes_gpu_mux *m, nes_gpu_session *s, int slot_index);
+
 struct nes_gpu_session {
   nes_gpu_cfg cfg{};
   std::mutex mu;
@@ -113,6 +137,7 @@ struct nes_gpu_session {
   uint64_t atlas_gen = 0;  // bumped by every atlas upload (invalidates run_cache)
   std::vector<DevPlaced> scratch_banded;
   int latency_bands = 1;  // > 1: upload / convert / download a frame in that many row bands (nes_gpu_session_set_latency_bands)
+  nes_gpu_mux *mux = nullptr;  // attached: submit only stages, the mux launches the ready frames of all its sessions together
 };
 
 namespace {
@@ -304,12 +329,6 @@ int get_filters(nes_gpu_session *s, int W, int H, int Wd, int Hd, FilterSet **ou
   *out = &ins.first->second;
   return NES_OK;
 }
-
-struct PlaneLayout {  // where one YUV420P image sits inside a linear buffer
-  size_t off[3];
-  size_t bytes[3];
-  size_t total;
-};
 
 PlaneLayout yuv_layout(const int32_t ls[3], int Hd, size_t base, bool nv12) {
   PlaneLayout p;
@@ -561,6 +580,28 @@ void band_glyphs(DevJob *jb, DevPlaced *gl, int n, std::vector<DevPlaced> *tmp) 
   for (int b = 0; b <= GLYPH_BANDS; b++) jb->glyph_band[b] = count[b];
   tmp->assign(gl, gl + n);
   for (int i = 0; i < n; i++) gl[count[band_of((*tmp)[i])]++] = (*tmp)[i];
+}
+
+// D2H of one converted frame on the session's download stream (which already waits for the kernels): straight into the
+// caller's planes when they are pinned and laid out like av_image_alloc, else through pinned staging (copied out in wait).
+int enqueue_download(nes_gpu_session *s, Slot &sl) {
+  const Download &d = sl.dl;
+  if (d.out.mem != NES_MEM_HOST) return NES_OK;
+  const size_t total = d.pd.off[0] + (d.want_depth ? d.pd.total : 0);
+  if (d.direct) {
+    CU_TRY(s, cudaMemcpyAsync(d.out.scene[0], sl.d_out + d.ps.off[0], d.ps.total, cudaMemcpyDeviceToHost, s->st_out));
+    if (d.want_depth) CU_TRY(s, cudaMemcpyAsync(d.out.depth[0], sl.d_out + d.pd.off[0], d.pd.total, cudaMemcpyDeviceToHost, s->st_out));
+  } else {
+    int st;
+    if ((st = ensure_host(s, &sl.h_out, &sl.h_out_cap, total))) return st;
+    CU_TRY(s, cudaMemcpyAsync(sl.h_out, sl.d_out, total, cudaMemcpyDeviceToHost, s->st_out));
+    for (int im = 0; im < d.nimg; im++) {
+      uint8_t *const *pl = im ? d.out.depth : d.out.scene;
+      const PlaneLayout &L = im ? d.pd : d.ps;
+      for (int p = 0; p < d.nplanes; p++) sl.staged.push_back(StagedCopy{pl[p], sl.h_out + L.off[p], L.bytes[p]});
+    }
+  }
+  return NES_OK;
 }
 
 int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, int n, cudaStream_t st) {
@@ -873,7 +914,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
     if (!all_pinned && (st = ensure_host(s, &sl.h_in, &sl.h_in_cap, need))) return st;
     // banded low-latency submit: pinned host buffers both ways, same-size path; the uploads are issued band by
     // band further down, interleaved with the launches
-    banded = s->latency_bands > 1 && all_pinned && !resize && out->mem == NES_MEM_HOST;
+    banded = s->latency_bands > 1 && all_pinned && !resize && out->mem == NES_MEM_HOST && !s->mux;
     for (int k = 0; k < in->n_sources; k++) {
       const nes_source &sr = in->src[k];
       const size_t o_rgb = (rgb_sz + dep_sz) * k, o_dep = o_rgb + rgb_sz;
@@ -965,7 +1006,20 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
     direct = contiguous && is_pinned(pl[0]);
   }
   banded = banded && direct && jb->segs_y >= 2;
+  sl.dl.out = *out; sl.dl.ps = ps; sl.dl.pd = pd; sl.dl.direct = direct; sl.dl.want_depth = want_depth; sl.dl.nimg = nimg; sl.dl.nplanes = nplanes;
+  sl.deferred = 0;
 
+  if (s->mux) {
+    // ---- multiplexed session: the frame is staged (uploads enqueued, descriptor built); the mux's dispatcher launches it
+    // together with the ready frames of its other sessions and enqueues the download
+    if (pinned_upload && (st = upload_rows(0, H))) return st;
+    CU_TRY(s, cudaEventRecord(sl.e_in, s->st_in));
+    sl.deferred = 1; sl.dispatched = 0; sl.dl_status = NES_OK;
+    sl.busy = true;
+    sl.ticket = s->next_ticket++;
+    *ticket = sl.ticket;
+    return mux_enqueue(s->mux, s, (int)(&sl - s->slots.data()));
+  }
   if (banded) {
     // ---- low-latency path: upload, convert and download the frame in row bands, so that the download of
     // band b overlaps the upload of band b+1 and only the last band's kernel + download follow the last
@@ -1014,21 +1068,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
 
     // ---- download ----
     CU_TRY(s, cudaStreamWaitEvent(s->st_out, sl.e_k1, 0));
-    if (out->mem == NES_MEM_HOST) {
-      const size_t total = pd.off[0] + (want_depth ? pd.total : 0);
-      if (direct) {
-        CU_TRY(s, cudaMemcpyAsync(out->scene[0], sl.d_out + ps.off[0], ps.total, cudaMemcpyDeviceToHost, s->st_out));
-        if (want_depth) CU_TRY(s, cudaMemcpyAsync(out->depth[0], sl.d_out + pd.off[0], pd.total, cudaMemcpyDeviceToHost, s->st_out));
-      } else {
-        if ((st = ensure_host(s, &sl.h_out, &sl.h_out_cap, total))) return st;
-        CU_TRY(s, cudaMemcpyAsync(sl.h_out, sl.d_out, total, cudaMemcpyDeviceToHost, s->st_out));
-        for (int im = 0; im < nimg; im++) {
-          uint8_t *const *pl = im ? out->depth : out->scene;
-          const PlaneLayout &L = im ? pd : ps;
-          for (int p = 0; p < nplanes; p++) sl.staged.push_back(StagedCopy{pl[p], sl.h_out + L.off[p], L.bytes[p]});
-        }
-      }
-    }
+    if ((st = enqueue_download(s, sl))) return st;
   }
   CU_TRY(s, cudaEventRecord(sl.e_out, s->st_out));
 
@@ -1046,14 +1086,21 @@ int nes_gpu_wait(nes_gpu_session *s, uint64_t ticket) {
     if (c.busy && c.ticket == ticket) sl = &c;
   if (!sl) return NES_ERR_BAD_TICKET;
   CU_TRY(s, cudaSetDevice(s->cfg.device));
+  if (sl->deferred) {
+    mux_wait_dispatched(s->mux, s, (int)(sl - s->slots.data()));
+    if (sl->dl_status != NES_OK) { sl->busy = false; return sl->dl_status; }
+  }
   CU_TRY(s, cudaEventSynchronize(sl->e_out));
   for (const StagedCopy &c : sl->staged) std::memcpy(c.dst, c.src, c.bytes);
   sl->staged.clear();
   float h2d = 0, k = 0, d2h = 0, tot = 0;
   cudaEventElapsedTime(&h2d, sl->e_start, sl->e_in);
-  cudaEventElapsedTime(&k, sl->e_k0, sl->e_k1);
-  cudaEventElapsedTime(&d2h, sl->e_k1, sl->e_out);
+  if (!sl->deferred) {  // a multiplexed frame shares its launch with other sessions' frames: no per-frame kernel interval
+    cudaEventElapsedTime(&k, sl->e_k0, sl->e_k1);
+    cudaEventElapsedTime(&d2h, sl->e_k1, sl->e_out);
+  }
   cudaEventElapsedTime(&tot, sl->e_start, sl->e_out);
+  cudaGetLastError();
   s->last.h2d_us = h2d * 1000.f; s->last.kernels_us = k * 1000.f; s->last.d2h_us = d2h * 1000.f; s->last.total_us = tot * 1000.f;
   s->last.n_launches = sl->n_launches;
   sl->busy = false;
@@ -1219,5 +1266,188 @@ void nes_gpu_batch_free(nes_gpu_session *s, nes_gpu_batch *b) {
   cudaGetLastError();
   delete b;
 }
+
+}  // extern "C"
+
+// ============================================================================
+// nes_gpu_mux: many client sessions of one GPU, one launch set for all their ready frames
+// (BASELINE config 4: 64 concurrent 1080p sessions; the reference runs one process per session, main.cpp:133-171,
+// and one process_frame_thread per eye, :274-282).  A session attached to a mux keeps its own upload / download
+// streams, frame slots, atlas and caches; nes_gpu_submit stages the frame (descriptor, H2D copies) on the caller's
+// thread and hands the slot to the dispatcher thread, which gathers whatever is ready -- never waiting for a batch to
+// fill -- into ONE descriptor table and ONE launch of k_frame_strips / k_resize_strips, then enqueues each frame's
+// download on its session's stream.  nes_gpu_wait is unchanged for the caller.
+// ============================================================================
+struct nes_gpu_mux {
+  int device = 0, max_batch = 64;
+  cudaStream_t st_k = nullptr;
+  uint32_t *d_counters = nullptr;
+  uint64_t strips_seq = 0;
+  static constexpr int kTables = 4;
+  BatchTables tables[kTables];
+  uint64_t table_seq = 0;
+  std::mutex q_mu;
+  std::condition_variable q_cv;
+  std::vector<std::pair<nes_gpu_session *, int>> pending;
+  bool stop = false;
+  std::mutex done_mu;
+  std::condition_variable done_cv;
+  std::thread worker;
+  uint64_t frames = 0, launch_sets = 0, launches = 0, max_batch_seen = 0;
+  std::string err;
+};
+
+static int mux_enqueue(nes_gpu_mux *m, nes_gpu_session *s, int slot_index) {
+  {
+    std::lock_guard<std::mutex> lk(m->q_mu);
+    m->pending.emplace_back(s, slot_index);
+  }
+  m->q_cv.notify_one();
+  return NES_OK;
+}
+
+static void mux_wait_dispatched(nes_gpu_mux *m, nes_gpu_session *s, int slot_index) {
+  std::unique_lock<std::mutex> lk(m->done_mu);
+  m->done_cv.wait(lk, [&] { return s->slots[(size_t)slot_index].dispatched != 0; });
+}
+
+static void mux_dispatch(nes_gpu_mux *m, std::vector<std::pair<nes_gpu_session *, int>> &batch) {
+  const int n = (int)batch.size();
+  BatchTables &bt = m->tables[m->table_seq++ % nes_gpu_mux::kTables];
+  int status = NES_OK;
+  auto cu = [&](cudaError_t e, const char *what) {
+    if (e != cudaSuccess && status == NES_OK) { status = NES_ERR_CUDA; m->err = std::string(what) + ": " + cudaGetErrorString(e); }
+  };
+  if (bt.used) cu(cudaEventSynchronize(bt.done), "cudaEventSynchronize(table)");
+  // one descriptor table: the staged jobs of every session, re-planned as one launch
+  int tile_base = 0;
+  for (int i = 0; i < n; i++) {
+    Slot &sl = batch[i].first->slots[(size_t)batch[i].second];
+    std::memcpy(&bt.h_jobs[i], sl.h_job, sizeof(DevJob));
+    job_tiles(&bt.h_jobs[i], tile_base);
+    tile_base += bt.h_jobs[i].tiles_x * bt.h_jobs[i].tiles_y;
+  }
+  plan_frame_strips(bt.h_jobs, n);
+  plan_resize_strips(bt.h_jobs, n);
+  cu(cudaMemcpyAsync(bt.d_jobs, bt.h_jobs, sizeof(DevJob) * (size_t)n, cudaMemcpyHostToDevice, m->st_k), "cudaMemcpyAsync(table)");
+  for (int i = 0; i < n; i++) cu(cudaStreamWaitEvent(m->st_k, batch[i].first->slots[(size_t)batch[i].second].e_in, 0), "cudaStreamWaitEvent(upload)");
+  int l = 0;
+  if (status == NES_OK) {
+    const int r0 = launch_frame_strips(bt.d_jobs, bt.h_jobs, n, m->d_counters, &m->strips_seq, m->st_k);
+    const int r1 = launch_resize_strips(bt.d_jobs, bt.h_jobs, n, m->d_counters, &m->strips_seq, m->st_k);
+    const int r2 = launch_resize_tiles(bt.d_jobs, bt.h_jobs, n, m->st_k);
+    if (r0 < 0 || r1 < 0 || r2 < 0) { status = NES_ERR_CUDA; m->err = "kernel launch failed"; }
+    l = std::max(r0, 0) + std::max(r1, 0) + std::max(r2, 0);
+    cu(cudaGetLastError(), "launch");
+  }
+  cu(cudaEventRecord(bt.done, m->st_k), "cudaEventRecord(done)");
+  bt.used = true;
+  for (int i = 0; i < n; i++) {
+    nes_gpu_session *s = batch[i].first;
+    Slot &sl = s->slots[(size_t)batch[i].second];
+    int st = status;
+    if (st == NES_OK) {
+      cu(cudaStreamWaitEvent(s->st_out, bt.done, 0), "cudaStreamWaitEvent(done)");
+      st = enqueue_download(s, sl);
+    }
+    cu(cudaEventRecord(sl.e_out, s->st_out), "cudaEventRecord(out)");
+    sl.n_launches = l;
+    sl.dl_status = st != NES_OK ? st : status;
+  }
+  {
+    std::lock_guard<std::mutex> lk(m->done_mu);
+    for (int i = 0; i < n; i++) batch[i].first->slots[(size_t)batch[i].second].dispatched = 1;
+    m->frames += (uint64_t)n; m->launch_sets++; m->launches += (uint64_t)l;
+    m->max_batch_seen = std::max<uint64_t>(m->max_batch_seen, (uint64_t)n);
+  }
+  m->done_cv.notify_all();
+}
+
+static void mux_worker(nes_gpu_mux *m) {
+  cudaSetDevice(m->device);
+  std::vector<std::pair<nes_gpu_session *, int>> batch;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(m->q_mu);
+      m->q_cv.wait(lk, [&] { return m->stop || !m->pending.empty(); });
+      if (m->pending.empty() && m->stop) return;
+      const size_t take = std::min(m->pending.size(), (size_t)m->max_batch);
+      batch.assign(m->pending.begin(), m->pending.begin() + (long)take);
+      m->pending.erase(m->pending.begin(), m->pending.begin() + (long)take);
+    }
+    mux_dispatch(m, batch);
+  }
+}
+
+extern "C" {
+
+int nes_gpu_mux_create(int device, int max_batch, nes_gpu_mux **out) {
+  if (!out) return NES_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return NES_ERR_CUDA; }
+  if (device < 0 || device >= ndev) return NES_ERR_INVALID_ARG;
+  nes_gpu_mux *m = new (std::nothrow) nes_gpu_mux();
+  if (!m) return NES_ERR_NO_MEMORY;
+  m->device = device;
+  m->max_batch = max_batch < 1 ? 64 : std::min(max_batch, kMaxBatch);
+  bool ok = cudaSetDevice(device) == cudaSuccess && kernels_init() == 0 && cudaStreamCreateWithFlags(&m->st_k, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMalloc((void **)&m->d_counters, 2 * COUNTER_SLOTS * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemset(m->d_counters, 0, 2 * COUNTER_SLOTS * sizeof(uint32_t)) == cudaSuccess;
+  for (BatchTables &bt : m->tables) {
+    ok = ok && cudaHostAlloc((void **)&bt.h_jobs, sizeof(DevJob) * (size_t)m->max_batch, cudaHostAllocDefault) == cudaSuccess &&
+         cudaMalloc((void **)&bt.d_jobs, sizeof(DevJob) * (size_t)m->max_batch) == cudaSuccess &&
+         cudaEventCreateWithFlags(&bt.done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    cudaGetLastError();
+    nes_gpu_mux_destroy(m);
+    return NES_ERR_CUDA;
+  }
+  m->worker = std::thread(mux_worker, m);
+  *out = m;
+  return NES_OK;
+}
+
+void nes_gpu_mux_destroy(nes_gpu_mux *m) {
+  if (!m) return;
+  if (m->worker.joinable()) {
+    {
+      std::lock_guard<std::mutex> lk(m->q_mu);
+      m->stop = true;
+    }
+    m->q_cv.notify_all();
+    m->worker.join();
+  }
+  cudaSetDevice(m->device);
+  if (m->st_k) cudaStreamSynchronize(m->st_k);
+  for (BatchTables &bt : m->tables) {
+    cudaFreeHost(bt.h_jobs); cudaFree(bt.d_jobs);
+    if (bt.done) cudaEventDestroy(bt.done);
+  }
+  cudaFree(m->d_counters);
+  if (m->st_k) cudaStreamDestroy(m->st_k);
+  cudaGetLastError();
+  delete m;
+}
+
+int nes_gpu_mux_attach(nes_gpu_mux *m, nes_gpu_session *s) {
+  if (!m || !s) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (s->cfg.device != m->device) return NES_ERR_INVALID_ARG;
+  for (const Slot &sl : s->slots)
+    if (sl.busy) return NES_ERR_BUSY;
+  s->mux = m;
+  return NES_OK;
+}
+
+int nes_gpu_mux_stats(nes_gpu_mux *m, nes_mux_stats *out) {
+  if (!m || !out) return NES_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(m->done_mu);
+  out->frames = m->frames; out->launch_sets = m->launch_sets; out->launches = m->launches; out->max_batch = m->max_batch_seen;
+  return NES_OK;
+}
+
+const char *nes_gpu_mux_error(nes_gpu_mux *m) { return m ? m->err.c_str() : ""; }
 
 }  // extern "C"

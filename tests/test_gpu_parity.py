@@ -451,7 +451,11 @@ def test_cpp_shim_process_frame(N, O, port, glyphs, tmp_path):
     w, h = 1280, 720
     rgb, dep = O.synth_rgb(w, h, 9), O.synth_depth(w, h, 9)
     (tmp_path / "m.bin").write_bytes(O.pack_rendered_frame(9, False, w, h, O.KINITIAL_CAMERA_MATRIX, rgb.tobytes(), dep.tobytes()))
-    r = subprocess.run([exe, str(tmp_path / "m.bin"), FONT, N.find_freetype(), str(w), str(h), "12:34:56.789", str(tmp_path / "o")], capture_output=True, text=True)
+    avutil = N.avhandoff.bundled_ffmpeg()["avutil"]
+    if avutil is None:
+        pytest.skip("no libavutil in this image (to_avframe is part of the flow)")
+    r = subprocess.run([exe, str(tmp_path / "m.bin"), FONT, N.find_freetype(), str(w), str(h), "12:34:56.789", str(tmp_path / "o")], capture_output=True, text=True,
+                       env=dict(os.environ, NES_AVUTIL_SO=avutil))
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip() == "ok index=9 left=0"
     surf = np.ascontiguousarray(rgb.copy())
@@ -464,23 +468,92 @@ def test_cpp_shim_process_frame(N, O, port, glyphs, tmp_path):
     assert (tmp_path / "o.zero.yuv").read_bytes() == want_s   # zero-copy constructor (wire bytes borrowed)
 
 
+def test_mux_many_sessions(N, O, port, glyphs):
+    """nes_gpu_mux: 12 client sessions (two pixel formats, with and without text, one of them resizing) driven by 4 host
+    threads; every frame equals the oracle, and the dispatcher coalesced frames of several sessions into shared launches."""
+    import threading
+    mux = N.Mux(device=0, max_batch=32)
+    n_sess, frames_per = 12, 10
+    sessions, errors = [], []
+    try:
+        for k in range(n_sess):
+            s = N.Session(device=0, max_width=640, max_height=360, max_sources=2, ring_depth=2)
+            s.atlas_set(glyphs.metrics, glyphs.bitmaps)
+            mux.attach(s)
+            sessions.append(s)
+
+        def drive(tid):
+            try:
+                mine = [k for k in range(n_sess) if k % 4 == tid]
+                state = {}
+                for k in mine:
+                    s = sessions[k]
+                    w, h = (640, 360) if k % 3 else (320, 200)
+                    wd, hd = (426, 240) if k == 5 else (w, h)
+                    fmt = "rgba" if k % 2 else "rgb24"
+                    nsrc = 2 if k % 2 else 1
+                    state[k] = dict(w=w, h=h, wd=wd, hd=hd, fmt=fmt, nsrc=nsrc, pending=None)
+                for f in range(frames_per + 1):
+                    for k in mine:
+                        st_, s = state[k], sessions[k]
+                        if st_["pending"] is not None:  # collect the previous frame of this session
+                            t, sc, dp, want, keep = st_["pending"]
+                            s.wait(t)
+                            assert sc.cropped() == want[0].cropped(), (k, f - 1, first_diff(sc.cropped(), want[0].cropped()))
+                            assert dp.cropped() == want[1].cropped(), (k, f - 1)
+                            st_["pending"] = None
+                        if f == frames_per:
+                            continue
+                        wl = dict(w=st_["w"], h=st_["h"], fmt=st_["fmt"], n_src=st_["nsrc"])
+                        srcs = N.synth.make_sources(wl, 100 * k + f)
+                        runs = O.reference_strings(index=f) if (k + f) % 2 else None
+                        want = O.expected_frame(srcs, st_["fmt"], runs, st_["wd"], st_["hd"], port, glyphs)
+                        sc = N.FrameManager(N.FrameContext(st_["wd"], st_["hd"], "yuv420p"), session=s)
+                        dp = N.FrameManager(N.FrameContext(st_["wd"], st_["hd"], "yuv420p"), session=s)
+                        keep = [(np.ascontiguousarray(a).reshape(-1), np.ascontiguousarray(d).reshape(-1)) for a, d in srcs]
+                        fin = N.Session.frame_in(st_["fmt"], st_["w"], st_["h"], [(a, d, 0, 0) for a, d in keep])
+                        t = s.submit(fin, runs, N.api._frame_out(sc, dp))
+                        st_["pending"] = (t, sc, dp, want, keep)
+            except Exception as e:  # noqa: BLE001
+                errors.append(repr(e))
+
+        ths = [threading.Thread(target=drive, args=(t,)) for t in range(4)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        assert not errors, errors[:3]
+        st = mux.stats()
+        assert st["frames"] == n_sess * frames_per
+        assert st["launch_sets"] <= st["frames"] and st["max_batch"] >= 1
+        assert mux.error() == ""
+    finally:
+        for s in sessions:
+            s.close()
+        mux.close()
+
+
 def test_reference_encode_cpp_text_runs(N, O, port, glyphs, tmp_path):
-    """The reference's OWN process_frame_thread + send_frame_thread text (extracted from /root/reference at test time,
-    where it is mounted) run against the shim on the GPU: one frame goes through the four overlays, convert_frame()
+    """The reference's OWN process_frame_thread + send_frame_thread text (extracted from /root/reference in the build
+    container into the git-ignored tests/cpp/_ref/, which travels to the GPU box like oracle/_ref) run against the shim on the GPU: one frame goes through the four overlays, convert_frame()
     and the to_avframe() hand-off.  The timestamp overlay is wall-clock text: the planes are compared with the oracle
     outside the rows it can touch; the depth planes entirely."""
     import subprocess
     from conftest import FONT
     import test_host
-    if not os.path.exists(test_host.REFERENCE_ENCODE_CPP):
-        pytest.skip("the reference tree is only mounted in the build container (tests/cpp/process_frame.cpp is the committed restatement)")
+    if not test_host.reference_text_available():
+        pytest.skip("the reference's text was not extracted in the build container (tests/cpp/process_frame.cpp is the committed restatement)")
     if N.find_freetype() is None:
         pytest.skip("no FreeType binary in this image")
     exe = test_host.build_encode_text_driver(tmp_path)
     w, h = 1280, 720
     rgb, dep = O.synth_rgb(w, h, 5), O.synth_depth(w, h, 5)
     (tmp_path / "m.bin").write_bytes(O.pack_rendered_frame(0, True, w, h, O.KINITIAL_CAMERA_MATRIX, rgb.tobytes(), dep.tobytes()))
-    r = subprocess.run([exe, str(tmp_path / "m.bin"), FONT, N.find_freetype(), str(w), str(h), str(tmp_path / "o")], capture_output=True, text=True)
+    avutil = N.avhandoff.bundled_ffmpeg()["avutil"]
+    if avutil is None:
+        pytest.skip("no libavutil in this image (to_avframe is part of the flow)")
+    r = subprocess.run([exe, str(tmp_path / "m.bin"), FONT, N.find_freetype(), str(w), str(h), str(tmp_path / "o")], capture_output=True, text=True,
+                       env=dict(os.environ, NES_AVUTIL_SO=avutil))
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip().startswith("ok index=0 sent=1+1")
     surf = np.ascontiguousarray(rgb.copy())

@@ -53,11 +53,22 @@ def extract_reference_encode_text(dst_path):
         f.write(text)
 
 
+# where the extracted text is parked so that it travels to the GPU box (git-ignored, like oracle/_ref: built from the
+# reference's sources where they lie, never part of the history)
+REF_TEXT_DIR = os.path.join(ROOT, "tests", "cpp", "_ref")
+
+
+def reference_text_available() -> bool:
+    return os.path.exists(REFERENCE_ENCODE_CPP) or os.path.exists(os.path.join(REF_TEXT_DIR, "encode_text.inc"))
+
+
 def build_encode_text_driver(tmp_path):
-    extract_reference_encode_text(str(tmp_path / "encode_text.inc"))
+    if os.path.exists(REFERENCE_ENCODE_CPP):
+        os.makedirs(REF_TEXT_DIR, exist_ok=True)
+        extract_reference_encode_text(os.path.join(REF_TEXT_DIR, "encode_text.inc"))
     exe = str(tmp_path / "encode_text_driver")
     lib_dir = os.path.join(ROOT, "ngp-encode-server_b200")
-    subprocess.run(["g++", "-std=c++20", "-O1", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp"), "-I", str(tmp_path),
+    subprocess.run(["g++", "-std=c++20", "-O1", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp"), "-I", REF_TEXT_DIR,
                     os.path.join(ROOT, "tests", "cpp", "encode_text_driver.cpp"), "-o", exe, "-L", lib_dir, "-l:libnes_gpu.so", f"-Wl,-rpath,{lib_dir}", "-pthread"],
                    check=True)
     return exe
