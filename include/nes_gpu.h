@@ -151,9 +151,17 @@ typedef struct nes_frame_in {
   int32_t width;     /* source size (Camera.width/height, rendered_frame.cc:14-25)    */
   int32_t height;
   int32_t mem;       /* nes_mem_kind of the source pointers                           */
-  int32_t reserved;
+  int32_t depth_fmt; /* nes_depth_fmt: 0 = GRAY8 (the reference, server.cpp:193-194), 1 = GRAY16LE */
   nes_source src[NES_MAX_SOURCES];
 } nes_frame_in;
+
+/* Sample format of the depth planes.  GRAY16LE (2 bytes per sample, depth_stride in bytes) is converted like libswscale
+ * converts it: the 16-bit horizontal scaler and the 8x8 ordered dither of its vertical scaler.  Only frames with ONE
+ * source can carry 16-bit depth (a 16-bit depth composite is not defined): NES_ERR_INVALID_ARG otherwise. */
+typedef enum nes_depth_fmt {
+  NES_DEPTH_GRAY8 = 0,
+  NES_DEPTH_GRAY16LE = 1
+} nes_depth_fmt;
 
 /* Destination pixel layouts.  YUV420P is what the reference hands to libavcodec
  * (three planes).  NV12 (Y plane + one interleaved U0 V0 U1 V1 ... plane: [1] with

@@ -64,7 +64,7 @@ class nes_source(C.Structure):
 
 
 class nes_frame_in(C.Structure):
-    _fields_ = [("n_sources", C.c_int32), ("pix_fmt", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("mem", C.c_int32), ("reserved", C.c_int32), ("src", nes_source * NES_MAX_SOURCES)]
+    _fields_ = [("n_sources", C.c_int32), ("pix_fmt", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("mem", C.c_int32), ("depth_fmt", C.c_int32), ("src", nes_source * NES_MAX_SOURCES)]
 
 
 class nes_frame_out(C.Structure):
@@ -421,11 +421,12 @@ class Session:
         return arr, n
 
     @staticmethod
-    def frame_in(fmt: str, width: int, height: int, sources, mem: int = NES_MEM_HOST) -> nes_frame_in:
+    def frame_in(fmt: str, width: int, height: int, sources, mem: int = NES_MEM_HOST, depth_fmt: str = "gray") -> nes_frame_in:
         """sources: [(rgb, depth_or_None, rgb_stride, depth_stride)] with numpy arrays (host) or
-        (ptr, nbytes) tuples (device)."""
+        (ptr, nbytes) tuples (device).  depth_fmt "gray16le": the depth arrays hold 2 bytes per sample (stride in bytes)."""
         fi = nes_frame_in()
         fi.n_sources, fi.pix_fmt, fi.width, fi.height, fi.mem = len(sources), PIX_FMT[fmt], width, height, mem
+        fi.depth_fmt = {"gray": 0, "gray8": 0, "gray16le": 1}[depth_fmt]
         for k, (rgb, depth, rs, ds) in enumerate(sources):
             s = fi.src[k]
             if isinstance(rgb, np.ndarray):

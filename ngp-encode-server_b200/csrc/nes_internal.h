@@ -172,6 +172,12 @@ struct alignas(64) DevJob {
   RsLayout rs_lay;          // shared-memory carve-up for the largest tile of this size pair (same bases for every tile)
   const int32_t *rs_win_x;  // [tiles_x][4]: luma source columns [lc0, lc1), chroma source columns [cc0, cc1)
   const int32_t *rs_win_y;  // [tiles_y][4]: luma source rows [lr0, lr1), chroma source rows [cr0, cr1)
+  // 16-bit depth stream (depth16.cu; host use only: these kernels take their arguments by value).  d16_src != null: the
+  // job's own depth stream is off (dy == null) and this image is written by k_depth16_* after the scene kernels
+  const uint8_t *d16_src;
+  int32_t d16_stride;
+  uint8_t *d16_y, *d16_u, *d16_v;
+  int32_t d16_ys, d16_us, d16_vs;
   // k_resize_strips work (general jobs it can take: rz_ok; the others keep their tiles)
   int32_t rz_ok;
   int32_t rz_dw;                         // destination columns per strip (multiple of 16, <= RZ_MAX_DW; 0: the size pair does not fit)
@@ -192,6 +198,8 @@ int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_j
 void plan_resize_strips(DevJob *jobs_host, int n_jobs);
 int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream);
 int resize_strips_init();
+// GRAY16LE depth images of the jobs that carry one (depth16.cu); returns launches or -1
+int launch_depth16(const DevJob *jobs_host, int n_jobs, void *stream);
 int kernels_init();  // opt-in shared memory sizes; returns cudaError_t
 int frame_strips_init();
 

@@ -348,6 +348,9 @@ int validate(const nes_gpu_session *s, const nes_frame_in *in, const nes_frame_o
   if (in->mem != NES_MEM_HOST && in->mem != NES_MEM_DEVICE) return NES_ERR_INVALID_ARG;
   if (out->mem != NES_MEM_HOST && out->mem != NES_MEM_DEVICE) return NES_ERR_INVALID_ARG;
   const bool want_depth = out->depth[0] != nullptr;
+  if (in->depth_fmt != NES_DEPTH_GRAY8 && in->depth_fmt != NES_DEPTH_GRAY16LE) return NES_ERR_INVALID_ARG;
+  if (in->depth_fmt == NES_DEPTH_GRAY16LE && in->n_sources > 1) return NES_ERR_INVALID_ARG;  // no 16-bit depth composite
+  const int dbs = in->depth_fmt == NES_DEPTH_GRAY16LE ? 2 : 1;  // bytes per depth sample
   for (int k = 0; k < in->n_sources; k++) {
     const nes_source &sr = in->src[k];
     if (!sr.rgb) return NES_ERR_INVALID_ARG;
@@ -356,9 +359,9 @@ int validate(const nes_gpu_session *s, const nes_frame_in *in, const nes_frame_o
     if (sr.rgb_bytes < (uint64_t)(rs * (H - 1) + (int64_t)W * bpp)) return NES_ERR_SHORT_BUFFER;
     if (want_depth || in->n_sources > 1) {
       if (!sr.depth) return NES_ERR_INVALID_ARG;
-      const int64_t ds = sr.depth_stride ? sr.depth_stride : W;
-      if (ds < W) return NES_ERR_INVALID_ARG;
-      if (sr.depth_bytes < (uint64_t)(ds * (H - 1) + W)) return NES_ERR_SHORT_BUFFER;
+      const int64_t ds = sr.depth_stride ? sr.depth_stride : (int64_t)W * dbs;
+      if (ds < (int64_t)W * dbs || (dbs == 2 && (ds & 1))) return NES_ERR_INVALID_ARG;
+      if (sr.depth_bytes < (uint64_t)(ds * (H - 1) + (int64_t)W * dbs)) return NES_ERR_SHORT_BUFFER;
     }
   }
   // the kernels index planes with 32-bit offsets
@@ -450,6 +453,15 @@ void job_tiles(DevJob *jb, int tile_base) {
     jb->tiles_y = (jb->Hd + jb->rs_th - 1) / jb->rs_th;
   }
   jb->tile_base = tile_base;
+}
+
+// 16-bit depth: the scene kernels run without a depth stream, k_depth16_* (depth16.cu) writes the depth image.
+void job_depth16(DevJob *jb) {
+  jb->d16_src = jb->src[0].depth; jb->d16_stride = jb->src[0].depth_stride;
+  jb->d16_y = jb->dy; jb->d16_u = jb->du; jb->d16_v = jb->dv;
+  jb->d16_ys = jb->dys; jb->d16_us = jb->dus; jb->d16_vs = jb->dvs;
+  jb->dy = jb->du = jb->dv = nullptr;
+  jb->src[0].depth = nullptr;
 }
 
 void job_alignment(DevJob *jb) {
@@ -612,6 +624,8 @@ int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, 
   if (r1 > 0) l += r1;
   const int r = launch_resize_tiles(d_jobs, h_jobs, n, st);
   if (r > 0) l += r;
+  const int r2 = launch_depth16(h_jobs, n, st);
+  if (r2 > 0) l += r2;
   s->launches += (uint64_t)l;
   return l;
 }
@@ -877,6 +891,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   const bool want_depth = out->depth[0] != nullptr;
   const bool need_depth_in = want_depth || in->n_sources > 1;
   const bool resize = (W != Wd) || (H != Hd) || H < MIN_FUSED_H;
+  const size_t dbs = in->depth_fmt == NES_DEPTH_GRAY16LE ? 2 : 1;  // bytes per depth sample
 
   // text -> placed glyphs (pinned)
   const int n_gl = place_text(s, W, H, runs, n_runs, sl.h_glyphs, s->cfg.max_glyphs);
@@ -899,10 +914,10 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
       jb->src[k].rgb = in->src[k].rgb;
       jb->src[k].rgb_stride = in->src[k].rgb_stride ? in->src[k].rgb_stride : W * bpp;
       jb->src[k].depth = need_depth_in ? in->src[k].depth : nullptr;
-      jb->src[k].depth_stride = in->src[k].depth_stride ? in->src[k].depth_stride : W;
+      jb->src[k].depth_stride = in->src[k].depth_stride ? in->src[k].depth_stride : (int)(W * dbs);
     }
   } else {
-    const size_t rs_dev = align_up((size_t)W * bpp, 16), ds_dev = align_up((size_t)W, 16);
+    const size_t rs_dev = align_up((size_t)W * bpp, 16), ds_dev = align_up((size_t)W * dbs, 16);
     const size_t rgb_sz = align_up(rs_dev * H, 256), dep_sz = need_depth_in ? align_up(ds_dev * H, 256) : 0;
     const size_t need = (rgb_sz + dep_sz) * in->n_sources;
     if ((st = ensure_dev(s, &sl.d_in, &sl.d_in_cap, need))) return st;
@@ -919,7 +934,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
       const nes_source &sr = in->src[k];
       const size_t o_rgb = (rgb_sz + dep_sz) * k, o_dep = o_rgb + rgb_sz;
       const size_t rs = sr.rgb_stride ? sr.rgb_stride : (size_t)W * bpp;
-      const size_t ds = sr.depth_stride ? sr.depth_stride : (size_t)W;
+      const size_t ds = sr.depth_stride ? sr.depth_stride : (size_t)W * dbs;
       jb->src[k].rgb = sl.d_in + o_rgb;
       jb->src[k].rgb_stride = (int)rs_dev;
       jb->src[k].depth = need_depth_in ? sl.d_in + o_dep : nullptr;
@@ -933,8 +948,8 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
         if (rs == rs_dev) std::memcpy(sl.h_in + o_rgb, sr.rgb, rs * (H - 1) + (size_t)W * bpp);
         else for (int y = 0; y < H; y++) std::memcpy(sl.h_in + o_rgb + y * rs_dev, sr.rgb + y * rs, (size_t)W * bpp);
         if (need_depth_in) {
-          if (ds == ds_dev) std::memcpy(sl.h_in + o_dep, sr.depth, ds * (H - 1) + W);
-          else for (int y = 0; y < H; y++) std::memcpy(sl.h_in + o_dep + y * ds_dev, sr.depth + y * ds, W);
+          if (ds == ds_dev) std::memcpy(sl.h_in + o_dep, sr.depth, ds * (H - 1) + W * dbs);
+          else for (int y = 0; y < H; y++) std::memcpy(sl.h_in + o_dep + y * ds_dev, sr.depth + y * ds, W * dbs);
         }
       }
     }
@@ -957,6 +972,9 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   jb->sys = out->scene_linesize[0]; jb->sus = out->scene_linesize[1]; jb->svs = out->scene_linesize[2];
   jb->dys = out->depth_linesize[0]; jb->dus = out->depth_linesize[1]; jb->dvs = out->depth_linesize[2];
   jb->nv12 = out->pix_fmt == NES_OUT_NV12;
+  if (in->depth_fmt == NES_DEPTH_GRAY16LE && want_depth) job_depth16(jb);
+  // (a banded submit launches unit ranges of one kernel: a 16-bit depth frame goes through whole)
+  if (jb->d16_src) banded = false;
 
   jb->general = resize;
   if (n_gl > 0) band_glyphs(jb, sl.h_glyphs, n_gl, &s->scratch_banded);
@@ -980,7 +998,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   CU_TRY(s, cudaMemcpyAsync(sl.d_job, sl.h_job, sizeof(DevJob), cudaMemcpyHostToDevice, s->st_in));
 
   // rows [y0, y1) of every (pinned) source -> the device copy
-  const size_t rs_dev_ = align_up((size_t)W * bpp, 16), ds_dev_ = align_up((size_t)W, 16);
+  const size_t rs_dev_ = align_up((size_t)W * bpp, 16), ds_dev_ = align_up((size_t)W * dbs, 16);
   auto upload_rows = [&](int y0, int y1) -> int {
     if (y1 <= y0) return NES_OK;
     for (int k = 0; k < in->n_sources; k++) {
@@ -989,8 +1007,8 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
       if (u.rs == rs_dev_) CU_TRY(s, cudaMemcpyAsync(u.d_rgb + y0 * rs_dev_, u.rgb + y0 * u.rs, y1 == H ? (rows - 1) * u.rs + (size_t)W * bpp : rows * u.rs, cudaMemcpyHostToDevice, s->st_in));
       else CU_TRY(s, cudaMemcpy2DAsync(u.d_rgb + y0 * rs_dev_, rs_dev_, u.rgb + y0 * u.rs, u.rs, (size_t)W * bpp, rows, cudaMemcpyHostToDevice, s->st_in));
       if (u.depth) {
-        if (u.ds == ds_dev_) CU_TRY(s, cudaMemcpyAsync(u.d_depth + y0 * ds_dev_, u.depth + y0 * u.ds, y1 == H ? (rows - 1) * u.ds + (size_t)W : rows * u.ds, cudaMemcpyHostToDevice, s->st_in));
-        else CU_TRY(s, cudaMemcpy2DAsync(u.d_depth + y0 * ds_dev_, ds_dev_, u.depth + y0 * u.ds, u.ds, (size_t)W, rows, cudaMemcpyHostToDevice, s->st_in));
+        if (u.ds == ds_dev_) CU_TRY(s, cudaMemcpyAsync(u.d_depth + y0 * ds_dev_, u.depth + y0 * u.ds, y1 == H ? (rows - 1) * u.ds + (size_t)W * dbs : rows * u.ds, cudaMemcpyHostToDevice, s->st_in));
+        else CU_TRY(s, cudaMemcpy2DAsync(u.d_depth + y0 * ds_dev_, ds_dev_, u.depth + y0 * u.ds, u.ds, (size_t)W * dbs, rows, cudaMemcpyHostToDevice, s->st_in));
       }
     }
     return NES_OK;
@@ -1159,7 +1177,7 @@ static int build_batch(nes_gpu_session *s, BatchTables &bt, int n_frames, const 
       jb->src[k].rgb = in[f].src[k].rgb;
       jb->src[k].rgb_stride = in[f].src[k].rgb_stride ? in[f].src[k].rgb_stride : W * bpp;
       jb->src[k].depth = (want_depth || in[f].n_sources > 1) ? in[f].src[k].depth : nullptr;
-      jb->src[k].depth_stride = in[f].src[k].depth_stride ? in[f].src[k].depth_stride : W;
+      jb->src[k].depth_stride = in[f].src[k].depth_stride ? in[f].src[k].depth_stride : W * (in[f].depth_fmt == NES_DEPTH_GRAY16LE ? 2 : 1);
     }
     jb->sy = out[f].scene[0]; jb->su = out[f].scene[1]; jb->sv = out[f].scene[2];
     jb->sys = out[f].scene_linesize[0]; jb->sus = out[f].scene_linesize[1]; jb->svs = out[f].scene_linesize[2];
@@ -1168,6 +1186,7 @@ static int build_batch(nes_gpu_session *s, BatchTables &bt, int n_frames, const 
       jb->dys = out[f].depth_linesize[0]; jb->dus = out[f].depth_linesize[1]; jb->dvs = out[f].depth_linesize[2];
     }
     jb->nv12 = out[f].pix_fmt == NES_OUT_NV12;
+    if (in[f].depth_fmt == NES_DEPTH_GRAY16LE && want_depth) job_depth16(jb);
     jb->general = general;
     if (n_gl > 0) band_glyphs(jb, bt.h_glyphs + gl_used - n_gl, n_gl, &s->scratch_banded);
     if (general) {
@@ -1336,8 +1355,9 @@ static void mux_dispatch(nes_gpu_mux *m, std::vector<std::pair<nes_gpu_session *
     const int r0 = launch_frame_strips(bt.d_jobs, bt.h_jobs, n, m->d_counters, &m->strips_seq, m->st_k);
     const int r1 = launch_resize_strips(bt.d_jobs, bt.h_jobs, n, m->d_counters, &m->strips_seq, m->st_k);
     const int r2 = launch_resize_tiles(bt.d_jobs, bt.h_jobs, n, m->st_k);
-    if (r0 < 0 || r1 < 0 || r2 < 0) { status = NES_ERR_CUDA; m->err = "kernel launch failed"; }
-    l = std::max(r0, 0) + std::max(r1, 0) + std::max(r2, 0);
+    const int r3 = launch_depth16(bt.h_jobs, n, m->st_k);
+    if (r0 < 0 || r1 < 0 || r2 < 0 || r3 < 0) { status = NES_ERR_CUDA; m->err = "kernel launch failed"; }
+    l = std::max(r0, 0) + std::max(r1, 0) + std::max(r2, 0) + std::max(r3, 0);
     cu(cudaGetLastError(), "launch");
   }
   cu(cudaEventRecord(bt.done, m->st_k), "cudaEventRecord(done)");

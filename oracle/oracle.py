@@ -143,6 +143,8 @@ class Port:
         L.nes_oracle_rgb_to_yuv420p.restype = C.c_int
         L.nes_oracle_gray_to_yuv420p.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_uint8), C.c_int] * 3
         L.nes_oracle_gray_to_yuv420p.restype = C.c_int
+        L.nes_oracle_gray16_to_yuv420p.argtypes = [C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_uint8), C.c_int] * 3
+        L.nes_oracle_gray16_to_yuv420p.restype = C.c_int
         L.nes_oracle_render_string.argtypes = [C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.POINTER(_Glyph)]
         L.nes_oracle_render_string.restype = C.c_long
         L.nes_oracle_render_string4.argtypes = [C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.c_int, C.POINTER(_Glyph), C.c_int]
@@ -180,6 +182,17 @@ class Port:
         r = self.L.nes_oracle_gray_to_yuv420p(_u8p(img), img.strides[0], w, h, wd, hd, _u8p(out.y), out.ys, _u8p(out.u), out.cs, _u8p(out.v), out.cs)
         if r:
             raise ValueError("nes_oracle_gray_to_yuv420p: bad arguments")
+        return out
+
+    def gray16_to_yuv420p(self, img: np.ndarray, wd: int | None = None, hd: int | None = None) -> Yuv:
+        """img: uint16 [H, W] (GRAY16LE)"""
+        h, w = img.shape
+        assert img.dtype == np.uint16
+        wd, hd = wd or w, hd or h
+        out = Yuv(wd, hd)
+        r = self.L.nes_oracle_gray16_to_yuv420p(img.ctypes.data_as(C.POINTER(C.c_uint16)), img.strides[0], w, h, wd, hd, _u8p(out.y), out.ys, _u8p(out.u), out.cs, _u8p(out.v), out.cs)
+        if r:
+            raise ValueError("nes_oracle_gray16_to_yuv420p: bad arguments")
         return out
 
     def render_string(self, surface: np.ndarray, position: int, text: bytes, glyphs: GlyphTable) -> int:
@@ -276,7 +289,7 @@ class Ref:
         h, w = img.shape[:2]
         wd, hd = wd or w, hd or h
         out = Yuv(wd, hd)
-        r = self.L.nes_ref_sws_convert(_u8p(img), img.strides[0], fmt.encode(), w, h, wd, hd, flags, _u8p(out.y), out.ys, _u8p(out.u), out.cs, _u8p(out.v), out.cs)
+        r = self.L.nes_ref_sws_convert(img.ctypes.data_as(C.POINTER(C.c_uint8)), img.strides[0], fmt.encode(), w, h, wd, hd, flags, _u8p(out.y), out.ys, _u8p(out.u), out.cs, _u8p(out.v), out.cs)
         if r:
             raise RuntimeError(f"nes_ref_sws_convert failed: {r}")
         return out

@@ -320,3 +320,70 @@ NES_ORACLE_API int nes_oracle_gray_to_yuv420p(const uint8_t *src, int src_stride
   (void)xinc_is_unscaled;
   return 0;
 }
+
+/* Ordered dither libswscale applies in the vertical scaler when the source has more than 8 bits per sample and the
+ * destination 8 (swscale.c: should_dither = is16BPS(srcFormat) -> lumDither8 = ff_dither_8x8_128[dstY & 7]; output.c
+ * yuv2plane1_8_c / yuv2planeX_8_c add dither[(x + offset) & 7], <<12 for the filtered case).  The table is
+ * libswscale/output.c ff_dither_8x8_128; tests/test_oracle.py re-derives every entry from the live library. */
+static const uint8_t kDither8x8_128[8][8] = {
+    {36, 68, 60, 92, 34, 66, 58, 90},  {100, 4, 124, 28, 98, 2, 122, 26}, {52, 84, 44, 76, 50, 82, 42, 74}, {116, 20, 108, 12, 114, 18, 106, 10},
+    {32, 64, 56, 88, 38, 70, 62, 94},  {96, 0, 120, 24, 102, 6, 126, 30}, {48, 80, 40, 72, 54, 86, 46, 78}, {112, 16, 104, 8, 118, 22, 110, 14}};
+NES_ORACLE_API const uint8_t *nes_oracle_dither8x8_128(void) { return &kDither8x8_128[0][0]; }
+
+static void vscale_plane_dither(uint8_t *dst, int dst_stride, int dst_w, int dst_h, const int16_t *plane15, int plane_w, const int16_t *vf,
+                                const int32_t *vpos, int vsize) {
+  for (int i = 0; i < dst_h; i++) {
+    uint8_t *d = dst + (size_t)i * dst_stride;
+    const uint8_t *dith = kDither8x8_128[i & 7];
+    if (vsize == 1) {
+      const int16_t *p = plane15 + (size_t)vpos[i] * plane_w;
+      for (int x = 0; x < dst_w; x++) d[x] = (uint8_t)clip8((p[x] + dith[x & 7]) >> 7);
+    } else {
+      for (int x = 0; x < dst_w; x++) {
+        int val = dith[x & 7] << 12;
+        for (int j = 0; j < vsize; j++) val += (int)plane15[(size_t)(vpos[i] + j) * plane_w + x] * vf[(size_t)i * vsize + j];
+        d[x] = (uint8_t)clip8(val >> 19);
+      }
+    }
+  }
+}
+
+/* horizontal polyphase, 16-bit gray input: hScale16To15_c with sh = depth - 1 = 15 (libswscale swscale.c; the
+ * RGB-derived planes above use sh = 13) */
+static void hscale_gray16to15(int16_t *dst, int dst_w, const uint16_t *src, const int16_t *filter, const int32_t *pos, int size) {
+  for (int i = 0; i < dst_w; i++) {
+    int val = 0;
+    for (int j = 0; j < size; j++) val += (int)src[pos[i] + j] * filter[size * i + j];
+    dst[i] = (int16_t)imin(val >> 15, (1 << 15) - 1);
+  }
+}
+
+/*
+ * GRAY16LE -> YUV420P: the 16-bit depth variant of the reference's depth stream (server.cpp:193-194 fixes GRAY8 today;
+ * SURVEY.md §8 f rank 4).  Same chain as GRAY8 with the 16-bit horizontal scaler: hScale16To15 (>>15) ->
+ * lumRangeFromJpeg (14071 / 33561472) -> vertical WITH libswscale's 8x8 ordered dither (a 16-bit source going to 8 bits);
+ * U = V = 128.  Pinned against the real libswscale in
+ * tests/test_oracle.py.
+ */
+NES_ORACLE_API int nes_oracle_gray16_to_yuv420p(const uint16_t *src, int src_stride_bytes, int W, int H, int Wd, int Hd, uint8_t *dy, int ys,
+                                                uint8_t *du, int us, uint8_t *dv, int vs) {
+  if (W < 4 || H < 4 || Wd < 2 || Hd < 2 || (W | H | Wd | Hd) & 1) return -1;
+  const int cdW = (Wd + 1) >> 1, cdH = (Hd + 1) >> 1;
+  int16_t *hf_l, *vf_l;
+  int32_t *hp_l, *vp_l;
+  const int hs_l = nes_oracle_init_filter(W, Wd, 1 << 14, &hf_l, &hp_l);
+  const int vs_l = nes_oracle_init_filter(H, Hd, 1 << 12, &vf_l, &vp_l);
+  int16_t *py = (int16_t *)malloc(sizeof(int16_t) * (size_t)Wd * H);
+  for (int y = 0; y < H; y++) {
+    int16_t *p = py + (size_t)y * Wd;
+    hscale_gray16to15(p, Wd, (const uint16_t *)((const uint8_t *)src + (size_t)y * src_stride_bytes), hf_l, hp_l, hs_l);
+    for (int x = 0; x < Wd; x++) p[x] = (int16_t)((p[x] * 14071 + 33561472) >> 14);
+  }
+  vscale_plane_dither(dy, ys, Wd, Hd, py, Wd, vf_l, vp_l, vs_l);
+  for (int i = 0; i < cdH; i++) {
+    memset(du + (size_t)i * us, 128, (size_t)cdW);
+    memset(dv + (size_t)i * vs, 128, (size_t)cdW);
+  }
+  free(py); free(hf_l); free(vf_l); free(hp_l); free(vp_l);
+  return 0;
+}

@@ -468,6 +468,41 @@ def test_cpp_shim_process_frame(N, O, port, glyphs, tmp_path):
     assert (tmp_path / "o.zero.yuv").read_bytes() == want_s   # zero-copy constructor (wire bytes borrowed)
 
 
+@pytest.mark.parametrize("w,h,wd,hd,pinned", [(640, 360, 640, 360, True), (322, 94, 322, 94, False), (1920, 1080, 1920, 1080, True), (384, 216, 256, 144, True),
+                                              (256, 144, 384, 216, False), (1920, 1080, 1280, 720, True), (64, 8, 64, 8, False)])
+def test_depth16(N, O, port, glyphs, session, w, h, wd, hd, pinned):
+    """16-bit depth input (GRAY16LE, nes_frame_in.depth_fmt): the depth image equals libswscale's (16-bit scaler + ordered
+    dither, pinned in test_oracle.py); the scene of the same frame (with its overlays) is unaffected."""
+    rng = np.random.default_rng(w + h)
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    dep = rng.integers(0, 65536, (h, w), dtype=np.uint16)
+    dep[0, :8] = [0, 1, 255, 256, 32767, 32768, 65534, 65535]
+    runs = O.reference_strings(index=16)
+    want_s, _ = O.expected_frame([(rgb, np.zeros((h, w), np.uint8))], "rgb24", runs, wd, hd, port, glyphs)
+    want_d = port.gray16_to_yuv420p(dep, wd, hd)
+    scene = N.FrameManager(N.FrameContext(wd, hd, "yuv420p"), session=session if pinned else None)
+    depth = N.FrameManager(N.FrameContext(wd, hd, "yuv420p"), session=session if pinned else None)
+    if pinned:
+        hr, hd_ = session.host_array(rgb.nbytes), session.host_array(dep.nbytes)
+        hr[:] = rgb.reshape(-1); hd_[:] = dep.reshape(-1).view(np.uint8)
+    else:
+        hr, hd_ = np.ascontiguousarray(rgb).reshape(-1), np.ascontiguousarray(dep).reshape(-1).view(np.uint8)
+    fin = N.Session.frame_in("rgb24", w, h, [(hr, hd_, 0, 0)], depth_fmt="gray16le")
+    session.convert(fin, runs, N.api._frame_out(scene, depth))
+    assert depth.cropped() == want_d.cropped(), first_diff(depth.cropped(), want_d.cropped())
+    assert scene.cropped() == want_s.cropped(), first_diff(scene.cropped(), want_s.cropped())
+
+
+def test_depth16_rejects_composites(N, O, session):
+    w, h = 64, 32
+    srcs = [(O.to_fmt(O.synth_rgb(w, h, k), "rgba").reshape(-1), np.zeros(w * h * 2, np.uint8), 0, 0) for k in range(2)]
+    fin = N.Session.frame_in("rgba", w, h, srcs, depth_fmt="gray16le")
+    sc, dp = N.FrameManager(N.FrameContext(w, h, "yuv420p")), N.FrameManager(N.FrameContext(w, h, "yuv420p"))
+    with pytest.raises(N.NesGpuError) as e:
+        session.convert(fin, None, N.api._frame_out(sc, dp))
+    assert e.value.status == N.NES_ERR_INVALID_ARG
+
+
 def test_mux_many_sessions(N, O, port, glyphs):
     """nes_gpu_mux: 12 client sessions (two pixel formats, with and without text, one of them resizing) driven by 4 host
     threads; every frame equals the oracle, and the dispatcher coalesced frames of several sessions into shared launches."""

@@ -259,6 +259,30 @@ def test_port_matches_config_size_goldens(N, O, port, glyphs, golden):
         assert sha16(dp.cropped()) == c["depth"], name
 
 
+def test_port_gray16_vs_real_libswscale(O, port, ref):
+    """GRAY16LE -> YUV420P (16-bit depth input, SURVEY.md §8 f rank 4): the port equals the real libswscale, same size
+    and resized; and the 8x8 ordered dither libswscale applies to a >8-bit source is re-derived entry by entry from the
+    live library (same-size output = (p + d[y&7][x&7]) >> 7 with p the range-compressed 15-bit sample)."""
+    import ctypes as C
+    rng = np.random.default_rng(16)
+    for (w, h, wd, hd) in [(64, 32, 64, 32), (320, 180, 320, 180), (384, 216, 256, 144), (256, 144, 384, 216), (200, 100, 120, 90), (96, 54, 64, 54)]:
+        img = rng.integers(0, 65536, (h, w), dtype=np.uint16)
+        assert port.gray16_to_yuv420p(img, wd, hd).cropped() == ref.sws_convert(img, "gray16le", wd, hd).cropped(), (w, h, wd, hd)
+    full = np.arange(65536, dtype=np.uint16).reshape(16, 4096)
+    assert port.gray16_to_yuv420p(full).cropped() == ref.sws_convert(full, "gray16le").cropped()
+    img = rng.integers(0, 65536, (64, 4096), dtype=np.uint16)
+    out = ref.sws_convert(img, "gray16le").y[:64, :4096].astype(np.int64)
+    p = ((np.minimum(img.astype(np.int64) >> 1, 32767)) * 14071 + 33561472) >> 14
+    port.L.nes_oracle_dither8x8_128.restype = C.POINTER(C.c_uint8)
+    table = np.ctypeslib.as_array(port.L.nes_oracle_dither8x8_128(), shape=(8, 8))
+    for yy in range(8):
+        for xx in range(8):
+            pp, oo = p[yy::8, xx::8].ravel(), out[yy::8, xx::8].ravel()
+            m = (oo > 0) & (oo < 255)
+            lo, hi = (128 * oo - pp)[m].max(), (128 * oo - pp + 127)[m].min()
+            assert lo == hi == table[yy, xx], (yy, xx, lo, hi, table[yy, xx])
+
+
 def test_format_camera_matrix(N, O):
     assert N.format_camera_matrix(O.KINITIAL_CAMERA_MATRIX) == O.format_matrix_text(O.KINITIAL_CAMERA_MATRIX)
     assert N.format_camera_matrix(O.KINITIAL_CAMERA_MATRIX).startswith(b"+1.00000 +0.00000 +0.00000 +0.50000 \n+0.00000 -1.00000")

@@ -64,6 +64,10 @@ def main():
     s = n.Session(device=0, max_width=max(wl["w"], wl["wd"]), max_height=max(wl["h"], wl["hd"]), max_sources=wl["n_src"])
     m, b = n.synth.load_glyph_table()
     s.atlas_set(m, b)
+    if args.frames <= 0:  # the ring bench.py uses: distinct frames > 3x L2
+        bpp = n.PIX_BPP[wl["fmt"]]
+        per = wl["n_src"] * (bpp + 1) * wl["w"] * wl["h"] + 2 * (n.align32(wl["wd"]) * wl["hd"] + 2 * n.align32(wl["wd"] // 2) * (wl["hd"] // 2))
+        args.frames = max(2, min(64, int(np.ceil((400 << 20) / per))))
     fins, runs, fouts = device_batch(n, s, wl, args.frames)
     import time
     prep = s.prepare_batch(fins, runs, fouts)
