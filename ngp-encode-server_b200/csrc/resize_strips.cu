@@ -216,6 +216,67 @@ __device__ __forceinline__ int mask_chunk(const DevJob &jb, uint32_t *s_mask, in
   return pass;
 }
 
+// Horizontal pass of one source row for NL slots of 32 luma columns (+ the depth plane, same filter): all chains
+// advance together, tap by tap.
+template <int NL, int T>
+__device__ __forceinline__ void h_luma(uint32_t rowbuf, const int (&pos_l)[4], const int (&cf_l)[4][T], bool want_depth, int dw, int lane, uint32_t oy, uint32_t od) {
+  int v[NL], d[NL];
+  uint32_t a[NL], ad[NL];
+#pragma unroll
+  for (int cc = 0; cc < NL; cc++) { v[cc] = 0; d[cc] = 0; a[cc] = rowbuf + RZ_RB_Y + pos_l[cc] * 2; ad[cc] = rowbuf + RZ_RB_D + pos_l[cc]; }
+  if (want_depth) {
+#pragma unroll
+    for (int jj = 0; jj < T; jj++) {
+#pragma unroll
+      for (int cc = 0; cc < NL; cc++) {
+        const int yv = lds_u16(a[cc] + 2 * jj), dv = lds_u8(ad[cc] + jj);
+        v[cc] += yv * cf_l[cc][jj];
+        d[cc] += dv * cf_l[cc][jj];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int jj = 0; jj < T; jj++) {
+#pragma unroll
+      for (int cc = 0; cc < NL; cc++) v[cc] += lds_u16(a[cc] + 2 * jj) * cf_l[cc][jj];
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < NL; cc++) {
+    const bool on = lane + 32 * cc < dw;
+    const int y15 = min(v[cc] >> 13, 32767);
+    if (on) sts32(oy + 128 * cc, (uint32_t)y15);
+    if (want_depth) {
+      int g = min(d[cc] >> 7, 32767);
+      g = (g * 14071 + 33561472) >> 14;
+      if (on) sts32(od + 128 * cc, (uint32_t)g);
+    }
+  }
+}
+template <int NC, int T>
+__device__ __forceinline__ void h_chroma(uint32_t rowbuf, const int (&pos_c)[2], const int (&cf_c)[2][T], int dcw, int lane, uint32_t ou, uint32_t ov) {
+  int u[NC], v[NC];
+  uint32_t au[NC], av[NC];
+#pragma unroll
+  for (int cc = 0; cc < NC; cc++) { u[cc] = 0; v[cc] = 0; au[cc] = rowbuf + RZ_RB_U + pos_c[cc] * 2; av[cc] = rowbuf + RZ_RB_V + pos_c[cc] * 2; }
+#pragma unroll
+  for (int jj = 0; jj < T; jj++) {
+#pragma unroll
+    for (int cc = 0; cc < NC; cc++) {
+      const int uu = lds_u16(au[cc] + 2 * jj), vv = lds_u16(av[cc] + 2 * jj);
+      u[cc] += uu * cf_c[cc][jj];
+      v[cc] += vv * cf_c[cc][jj];
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < NC; cc++) {
+    if (lane + 32 * cc < dcw) {
+      sts32(ou + 128 * cc, (uint32_t)min(u[cc] >> 13, 32767));
+      sts32(ov + 128 * cc, (uint32_t)min(v[cc] >> 13, 32767));
+    }
+  }
+}
+
 }  // namespace
 
 // T: horizontal taps held in registers (>= the longest horizontal filter of the launch; shorter filters are
@@ -519,44 +580,21 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
             int slot = rbase_y + r, slot_c = rbase_c + r;
             if (slot >= nry) slot -= nry;
             if (slot_c >= nrc) slot_c -= nrc;
-            // ---- horizontal pass of this row: hScale16To15 (>>13, clamp) / hScale8To15 (>>7) + range compression
+            // ---- horizontal pass of this row: hScale16To15 (>>13, clamp) / hScale8To15 (>>7) + range compression.
+            // The slots of a plane (32 destination columns each) and the luma / depth pair run as independent
+            // accumulation chains inside one tap loop (the chains hide each other's multiply latency).
             if (need_l) {
-#pragma unroll
-              for (int cc = 0; cc < 4; cc++) {
-                const int col = lane + 32 * cc;
-                if (32 * cc < dw) {  // warp-uniform
-                  const uint32_t a = rowbuf + RZ_RB_Y + pos_l[cc] * 2;
-                  int v = 0;
-#pragma unroll
-                  for (int jj = 0; jj < T; jj++) v += lds_u16(a + 2 * jj) * cf_l[cc][jj];
-                  v = min(v >> 13, 32767);
-                  if (col < dw) sts32(ringY + slot * rowbY + col * 4, (uint32_t)v);
-                  if (want_depth) {
-                    const uint32_t ad = rowbuf + RZ_RB_D + pos_l[cc];
-                    int d = 0;
-#pragma unroll
-                    for (int jj = 0; jj < T; jj++) d += lds_u8(ad + jj) * cf_l[cc][jj];
-                    d = min(d >> 7, 32767);
-                    d = (d * 14071 + 33561472) >> 14;
-                    if (col < dw) sts32(ringD + slot * rowbY + col * 4, (uint32_t)d);
-                  }
-                }
-              }
+              const uint32_t oy = ringY + slot * rowbY + lane * 4, od = ringD + slot * rowbY + lane * 4;
+              const int nl = (dw + 31) >> 5;  // warp-uniform
+              if (nl == 1) h_luma<1, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
+              else if (nl == 2) h_luma<2, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
+              else if (nl == 3) h_luma<3, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
+              else h_luma<4, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
             }
             if (need_c) {
-#pragma unroll
-              for (int cc = 0; cc < 2; cc++) {
-                const int col = lane + 32 * cc;
-                if (32 * cc < dcw) {
-                  const uint32_t au = rowbuf + RZ_RB_U + pos_c[cc] * 2, av = rowbuf + RZ_RB_V + pos_c[cc] * 2;
-                  int u = 0, v = 0;
-#pragma unroll
-                  for (int jj = 0; jj < T; jj++) { u += lds_u16(au + 2 * jj) * cf_c[cc][jj]; v += lds_u16(av + 2 * jj) * cf_c[cc][jj]; }
-                  u = min(u >> 13, 32767);
-                  v = min(v >> 13, 32767);
-                  if (col < dcw) { sts32(ringU + slot_c * rowbC + col * 4, (uint32_t)u); sts32(ringV + slot_c * rowbC + col * 4, (uint32_t)v); }
-                }
-              }
+              const uint32_t ou = ringU + slot_c * rowbC + lane * 4, ov = ringV + slot_c * rowbC + lane * 4;
+              if (dcw <= 32) h_chroma<1, T>(rowbuf, pos_c, cf_c, dcw, lane, ou, ov);
+              else h_chroma<2, T>(rowbuf, pos_c, cf_c, dcw, lane, ou, ov);
             }
           }
           __syncwarp();  // the row buffer is rewritten by this warp's next row
@@ -595,8 +633,10 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
               const int16_t *cf = c.vl_coef + (size_t)dyy * vls;
               a[0] = a[1] = a[2] = a[3] = 64 << 12;
               d[0] = d[1] = d[2] = d[3] = 64 << 12;
+              int kn = (int)__ldg(cf);
               for (int jj = 0; jj < vls; jj++) {
-                const int k = (int)__ldg(cf + jj);
+                const int k = kn;
+                if (jj + 1 < vls) kn = (int)__ldg(cf + jj + 1);  // the next tap's coefficient is in flight while this tap is applied
                 const int4 w = lds_v4s(ringY + slot * rowbY + g * 16);
                 a[0] += w.x * k; a[1] += w.y * k; a[2] += w.z * k; a[3] += w.w * k;
                 if (want_depth) {
@@ -629,7 +669,9 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           const int total = (cb - ca) * gc;
           const uint32_t rcp = (65536u + gc - 1) / gc;
           const bool nv12 = c.nv12 != 0;
-          for (int idx = tid; idx < total; idx += 32 * NW) {
+          // (the luma items went to the low threads: the chroma items are dealt from the other end, so that the warps
+          // the luma pass left idle take them)
+          for (int idx = 32 * NW - 1 - tid; idx < total; idx += 32 * NW) {
             const int ry = (int)(((uint32_t)idx * rcp) >> 16), g = idx - ry * gc;
             const int cyy = ca + ry;
             const int pos = __ldg(c.vc_pos + cyy);
@@ -645,8 +687,10 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
               const int16_t *cf = c.vc_coef + (size_t)cyy * vcs;
               u[0] = u[1] = u[2] = u[3] = 64 << 12;
               v[0] = v[1] = v[2] = v[3] = 64 << 12;
+              int kn = (int)__ldg(cf);
               for (int jj = 0; jj < vcs; jj++) {
-                const int k = (int)__ldg(cf + jj);
+                const int k = kn;
+                if (jj + 1 < vcs) kn = (int)__ldg(cf + jj + 1);
                 const int4 w = lds_v4s(ringU + slot * rowbC + g * 16), e = lds_v4s(ringV + slot * rowbC + g * 16);
                 u[0] += w.x * k; u[1] += w.y * k; u[2] += w.z * k; u[3] += w.w * k;
                 v[0] += e.x * k; v[1] += e.y * k; v[2] += e.z * k; v[3] += e.w * k;
