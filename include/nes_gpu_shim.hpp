@@ -101,6 +101,26 @@ inline int &thread_device() {
 }
 inline void set_thread_device(int d) { thread_device() = d; }
 
+// Process-wide multiplexer (nes_gpu_mux), one per GPU: with nes_shim::enable_mux() (or NES_GPU_MUX=1) the sessions of all
+// converting threads -- both eyes, every client session of the process -- hand their frames to one dispatcher per GPU,
+// which launches whatever is ready together (BASELINE config 4).  Off by default: one session per thread, one launch per frame.
+inline bool &mux_enabled() {
+  static bool on = std::getenv("NES_GPU_MUX") != nullptr && std::atoi(std::getenv("NES_GPU_MUX")) != 0;
+  return on;
+}
+inline void enable_mux(bool on = true) { mux_enabled() = on; }
+inline nes_gpu_mux *device_mux(int device) {
+  static std::mutex mu;
+  static std::vector<std::pair<int, nes_gpu_mux *>> muxes;  // live for the process (sessions must go first)
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto &m : muxes)
+    if (m.first == device) return m.second;
+  nes_gpu_mux *m = nullptr;
+  check(nes_gpu_mux_create(device, 0, &m), "nes_gpu_mux_create");
+  muxes.emplace_back(device, m);
+  return m;
+}
+
 // One session per converting thread (the reference runs one process_frame_thread per eye).
 class ThreadSession {
  public:
@@ -112,6 +132,7 @@ class ThreadSession {
     if (!m_s) {
       nes_gpu_cfg cfg{thread_device(), limits().max_width, limits().max_height, limits().max_sources, limits().ring_depth, 0};
       check(nes_gpu_session_create(&cfg, &m_s), "nes_gpu_session_create");
+      if (mux_enabled()) check(nes_gpu_mux_attach(device_mux(cfg.device), m_s), "nes_gpu_mux_attach");
     }
     return m_s;
   }

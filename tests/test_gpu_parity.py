@@ -466,6 +466,12 @@ def test_cpp_shim_process_frame(N, O, port, glyphs, tmp_path):
     assert (tmp_path / "o.depth.yuv").read_bytes() == want_d
     assert (tmp_path / "o.sws.yuv").read_bytes() == want_s
     assert (tmp_path / "o.zero.yuv").read_bytes() == want_s   # zero-copy constructor (wire bytes borrowed)
+    # the same flow with the process-wide multiplexer (nes_shim::enable_mux / NES_GPU_MUX=1): the thread's session hands
+    # its frames to the per-GPU dispatcher
+    r = subprocess.run([exe, str(tmp_path / "m.bin"), FONT, N.find_freetype(), str(w), str(h), "12:34:56.789", str(tmp_path / "m")], capture_output=True, text=True,
+                       env=dict(os.environ, NES_AVUTIL_SO=avutil, NES_GPU_MUX="1"))
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "m.scene.yuv").read_bytes() == want_s and (tmp_path / "m.depth.yuv").read_bytes() == want_d
 
 
 @pytest.mark.parametrize("w,h,wd,hd,pinned", [(640, 360, 640, 360, True), (322, 94, 322, 94, False), (1920, 1080, 1920, 1080, True), (384, 216, 256, 144, True),
