@@ -49,6 +49,7 @@ struct Api {
   int (*buffer_get_ref_count)(const AvBufferRef *) = nullptr;
   Layout L{};
   int status = NES_ERR_UNSUPPORTED;
+  bool tried = false;
   std::string why;
 };
 
@@ -75,8 +76,13 @@ T &at(void *frame, int off) { return *reinterpret_cast<T *>(static_cast<uint8_t 
 
 Api &api(const char *so) {
   static Api a;
-  static std::once_flag once;
-  std::call_once(once, [&] {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  // bound once; a failed attempt is retried when the caller names a library (a later call may know the path)
+  if (a.status == NES_OK || (a.tried && !(so && *so))) return a;
+  a.tried = true;
+  a.why.clear();
+  [&] {
     const char *cands[] = {so, getenv("NES_AVUTIL_SO"), "libavutil.so.60", "libavutil.so"};
     for (const char *c : cands) {
       if (!c || !*c) continue;
@@ -114,7 +120,7 @@ Api &api(const char *so) {
     a.frame_free(&f);
     if (!ok) { a.why = "AVFrame layout check failed against the loaded libavutil"; return; }
     a.status = NES_OK;
-  });
+  }();
   return a;
 }
 

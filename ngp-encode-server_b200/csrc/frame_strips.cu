@@ -38,6 +38,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "device_common.cuh"
 #include "nes_internal.h"
@@ -192,9 +193,12 @@ __device__ __forceinline__ unsigned smid() {
 }
 #endif
 
+// The kernel body.  `jobs` is either the launch's descriptor table in global memory or (single-frame launches) the
+// descriptor inside the kernel's own parameter block; `inline_glyphs` is that block's placed-glyph list (else null: the
+// job's own device list is used).
 template <int BPP>
-__global__ void __launch_bounds__(CTA_THREADS, 3)
-k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int total_units, int text_units, uint32_t *__restrict__ counters, int ns, int slot_bytes) {
+__device__ __forceinline__ void frame_strips_body(const DevJob *__restrict__ jobs, const DevPlaced *__restrict__ inline_glyphs, int n_jobs, int unit_begin, int total_units,
+                                                  int text_units, uint32_t *__restrict__ counters, int ns, int slot_bytes) {
   // programmatic dependent launch: the next launch on this stream (other frames: nothing of ours is its input)
   // may fill the SMs as our CTAs drain instead of waiting for the whole grid
   asm volatile("griddepcontrol.launch_dependents;");
@@ -442,7 +446,7 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
         }
         __syncwarp();
         // ---- text overlay, stamped into the staged rows of source 0 ----------------------------
-        if (c.stamp) stamp_chunk<BPP, STRIP_W>(jobs[c.job], smem + L::OFF_STAGE, qc, ns, slot_bytes, x0, x0 + tw, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
+        if (c.stamp) stamp_chunk<BPP, STRIP_W>(jobs[c.job], inline_glyphs, smem + L::OFF_STAGE, qc, ns, slot_bytes, x0, x0 + tw, yc0, ra, rb, c.rgb_base, s_hits, s_nhits);
         fence_proxy_async();  // our generic-proxy writes to the stage come before the TMA refill
       }
 
@@ -681,6 +685,21 @@ k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int 
   }
 }
 
+template <int BPP>
+__global__ void __launch_bounds__(CTA_THREADS, 3)
+k_frame_strips(const DevJob *__restrict__ jobs, int n_jobs, int unit_begin, int total_units, int text_units, uint32_t *__restrict__ counters, int ns, int slot_bytes) {
+  frame_strips_body<BPP>(jobs, nullptr, n_jobs, unit_begin, total_units, text_units, counters, ns, slot_bytes);
+}
+
+// Single-frame launches: the descriptor, its tensor maps and its placed glyphs travel in the kernel's parameter block
+// (__grid_constant__: the producer warp and the TMA unit read them in place), so a frame costs no descriptor upload,
+// no event and no wait on the host -- and consecutive frames of a stream are adjacent launches that overlap on the device.
+template <int BPP>
+__global__ void __launch_bounds__(CTA_THREADS, 3)
+k_frame_strips_1(const __grid_constant__ JobPack pack, int unit_begin, int total_units, int text_units, uint32_t *__restrict__ counters, int ns, int slot_bytes) {
+  frame_strips_body<BPP>(&pack.job, pack.glyphs, 1, unit_begin, total_units, text_units, counters, ns, slot_bytes);
+}
+
 #ifdef NES_TRACE
 extern "C" __attribute__((visibility("default"))) int nes_debug_read_trace(unsigned long long *out, int n) {
   return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * (size_t)n);
@@ -715,6 +734,10 @@ int frame_strips_init() {
   e = cudaFuncSetAttribute(k_frame_strips<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, two);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(k_frame_strips<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, two);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_frame_strips_1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, two);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(k_frame_strips_1<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, two);
   if (e != cudaSuccess) return (int)e;
   if (const char *v = getenv("NES_STRIPS_CTAS")) g_force_ctas = atoi(v);
   return 0;
@@ -831,7 +854,32 @@ static cudaError_t launch_one(int grid, int smem, cudaStream_t st, const DevJob 
   return cudaLaunchKernelEx(&cfg, k_frame_strips<BPP>, jobs, n_jobs, u0, u1, text_units, counters, ns, slot);
 }
 
-int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream, int unit_begin, int unit_end) {
+static bool g_inline = true;  // NES_NO_INLINE=1: single-frame launches read their descriptor from the table like batches do
+
+template <int BPP>
+static cudaError_t launch_one_inline(int grid, int smem, cudaStream_t st, const JobPack &pack, int u0, int u1, int text_units, uint32_t *counters, int ns, int slot) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(CTA_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_frame_strips_1<BPP>, pack, u0, u1, text_units, counters, ns, slot);
+}
+
+// A single same-size frame whose placed glyphs fit the parameter block can be launched without a device-resident descriptor.
+bool frame_strips_inline_ok(const DevJob *jobs_host, int n_jobs) {
+  static const bool once = [] { if (const char *v = getenv("NES_NO_INLINE")) g_inline = atoi(v) == 0; return true; }();
+  (void)once;
+  return g_inline && n_jobs == 1 && !jobs_host[0].general && jobs_host[0].n_glyphs <= INLINE_GLYPHS;
+}
+
+int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream, int unit_begin, int unit_end,
+                        const DevPlaced *glyphs_host) {
   int total[2] = {0, 0}, text[2] = {0, 0}, staged[2];
   launch_staged(jobs_host, n_jobs, staged);
   for (int j = 0; j < n_jobs; j++) {
@@ -851,8 +899,17 @@ int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_j
     const int grid = std::min(u1 - u0, g_num_sms * c.ctas);
     // every launch gets its own self re-arming counter pair: consecutive launches overlap (see the kernel's first line)
     uint32_t *ctr = counters + 2 * ((*seq)++ % COUNTER_SLOTS);
-    const cudaError_t e = cls == 0 ? launch_one<3>(grid, c.smem, (cudaStream_t)stream, jobs_dev, n_jobs, u0, u1, text[cls], ctr, c.ns, c.slot)
-                                   : launch_one<4>(grid, c.smem, (cudaStream_t)stream, jobs_dev, n_jobs, u0, u1, text[cls], ctr, c.ns, c.slot);
+    cudaError_t e;
+    if (glyphs_host != nullptr && frame_strips_inline_ok(jobs_host, n_jobs)) {
+      static thread_local JobPack pack;  // ~9 KB: copied into the launch's parameter block by cudaLaunchKernelEx
+      pack.job = jobs_host[0];
+      if (jobs_host[0].n_glyphs > 0) std::memcpy(pack.glyphs, glyphs_host, sizeof(DevPlaced) * (size_t)jobs_host[0].n_glyphs);
+      e = cls == 0 ? launch_one_inline<3>(grid, c.smem, (cudaStream_t)stream, pack, u0, u1, text[cls], ctr, c.ns, c.slot)
+                   : launch_one_inline<4>(grid, c.smem, (cudaStream_t)stream, pack, u0, u1, text[cls], ctr, c.ns, c.slot);
+    } else {
+      e = cls == 0 ? launch_one<3>(grid, c.smem, (cudaStream_t)stream, jobs_dev, n_jobs, u0, u1, text[cls], ctr, c.ns, c.slot)
+                   : launch_one<4>(grid, c.smem, (cudaStream_t)stream, jobs_dev, n_jobs, u0, u1, text[cls], ctr, c.ns, c.slot);
+    }
     if (e != cudaSuccess) return -1;
     launches++;
   }

@@ -185,10 +185,21 @@ struct alignas(64) DevJob {
   int32_t rz_unit_base[2], rz_units;     // [bpp-3]: units of the rz jobs of that pixel class ahead of this job in the launch
 };
 
+// Parameter block of a single-frame launch of k_frame_strips (k_frame_strips_1): descriptor + placed glyphs by value.
+constexpr int INLINE_GLYPHS = 192;
+struct alignas(64) JobPack {
+  DevJob job;
+  DevPlaced glyphs[INLINE_GLYPHS];
+};
+
 // Launchers (frame_strips.cu, resize_tiles.cu).  jobs: device pointer to n_jobs descriptors.
 // unit_end > 0 (single-job launches only): process only the units [unit_begin, unit_end) of the job
 // counters: COUNTER_SLOTS pairs; *seq: the session's launch sequence number (picks the pair)
-int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream, int unit_begin = 0, int unit_end = 0);
+// glyphs_host != null: the caller has the job's placed glyphs on the host and did NOT upload descriptor / glyphs when
+// frame_strips_inline_ok() said so -- a single same-size frame then travels in the kernel's parameter block.
+int launch_frame_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream, int unit_begin = 0, int unit_end = 0,
+                        const DevPlaced *glyphs_host = nullptr);
+bool frame_strips_inline_ok(const DevJob *jobs_host, int n_jobs);
 // Assigns seg_rows / seg_order / unit_base of the same-size jobs of a launch (host).  text_first = false keeps the
 // segments in frame order (banded submits launch unit ranges that must be row bands).
 void plan_frame_strips(DevJob *jobs_host, int n_jobs, bool text_first = true);

@@ -103,6 +103,7 @@ struct BatchTables {
   cudaEvent_t done = nullptr, up = nullptr;
   bool used = false;
   int n = 0;  // frames described
+  bool inline_job = false;  // a single frame launched from its kernel's parameter block (nothing was uploaded)
 };
 
 }  // namespace
@@ -616,9 +617,9 @@ int enqueue_download(nes_gpu_session *s, Slot &sl) {
   return NES_OK;
 }
 
-int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, int n, cudaStream_t st) {
+int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, int n, cudaStream_t st, const DevPlaced *glyphs_host = nullptr) {
   int l = 0;
-  const int r0 = launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, &s->strips_seq, st);
+  const int r0 = launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, &s->strips_seq, st, 0, 0, glyphs_host);
   if (r0 > 0) l += r0;
   const int r1 = launch_resize_strips(d_jobs, h_jobs, n, s->d_counters, &s->strips_seq, st);
   if (r1 > 0) l += r1;
@@ -994,8 +995,13 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
   plan_frame_strips(jb, 1, /*text_first=*/!banded);
   plan_resize_strips(jb, 1);
 
-  if (n_gl > 0) CU_TRY(s, cudaMemcpyAsync(sl.d_glyphs, sl.h_glyphs, (size_t)n_gl * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
-  CU_TRY(s, cudaMemcpyAsync(sl.d_job, sl.h_job, sizeof(DevJob), cudaMemcpyHostToDevice, s->st_in));
+  // a single same-size frame travels in its kernel's parameter block (k_frame_strips_1): no descriptor / glyph upload.
+  // (a multiplexed session's frame is launched from the mux's table, which points at the slot's device glyph list)
+  const bool inline_job = !s->mux && frame_strips_inline_ok(jb, 1);
+  if (!inline_job) {
+    if (n_gl > 0) CU_TRY(s, cudaMemcpyAsync(sl.d_glyphs, sl.h_glyphs, (size_t)n_gl * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
+    if (!s->mux) CU_TRY(s, cudaMemcpyAsync(sl.d_job, sl.h_job, sizeof(DevJob), cudaMemcpyHostToDevice, s->st_in));
+  }
 
   // rows [y0, y1) of every (pinned) source -> the device copy
   const size_t rs_dev_ = align_up((size_t)W * bpp, 16), ds_dev_ = align_up((size_t)W * dbs, 16);
@@ -1054,7 +1060,8 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
       CU_TRY(s, cudaEventRecord(sl.e_band_in[b], s->st_in));
       CU_TRY(s, cudaStreamWaitEvent(s->st_k, sl.e_band_in[b], 0));
       if (b == 0) CU_TRY(s, cudaEventRecord(sl.e_k0, s->st_k));
-      const int l = launch_frame_strips(sl.d_job, sl.h_job, 1, s->d_counters, &s->strips_seq, s->st_k, seg_lo * jb->strips_x, seg_hi * jb->strips_x);
+      const int l = launch_frame_strips(sl.d_job, sl.h_job, 1, s->d_counters, &s->strips_seq, s->st_k, seg_lo * jb->strips_x, seg_hi * jb->strips_x,
+                                        inline_job ? sl.h_glyphs : nullptr);
       if (l < 0) { s->err = "launch_frame_strips failed"; return NES_ERR_CUDA; }
       sl.n_launches += l;
       s->launches += (uint64_t)l;
@@ -1080,7 +1087,7 @@ int nes_gpu_submit(nes_gpu_session *s, const nes_frame_in *in, const nes_text_ru
     // ---- kernels ----
     CU_TRY(s, cudaStreamWaitEvent(s->st_k, sl.e_in, 0));
     CU_TRY(s, cudaEventRecord(sl.e_k0, s->st_k));
-    sl.n_launches = run_kernels(s, sl.d_job, sl.h_job, 1, s->st_k);
+    sl.n_launches = run_kernels(s, sl.d_job, sl.h_job, 1, s->st_k, inline_job ? sl.h_glyphs : nullptr);
     CU_TRY(s, cudaGetLastError());
     CU_TRY(s, cudaEventRecord(sl.e_k1, s->st_k));
 
@@ -1143,7 +1150,7 @@ int nes_gpu_last_timing(nes_gpu_session *s, nes_timing *t) {
 // Descriptor table of a batch of device-resident frames -> bt (pinned + device copies, uploaded on the copy
 // stream; bt.up is recorded behind the upload).
 static int build_batch(nes_gpu_session *s, BatchTables &bt, int n_frames, const nes_frame_in *in, const nes_text_run *const *runs, const int *n_runs,
-                       const nes_frame_out *out) {
+                       const nes_frame_out *out, bool allow_inline = false) {
   const int gl_cap = s->cfg.max_glyphs * kBatchGlyphFactor;
   const size_t gl_bytes = (size_t)gl_cap * sizeof(DevPlaced);
   if (!bt.h_jobs) {
@@ -1205,11 +1212,13 @@ static int build_batch(nes_gpu_session *s, BatchTables &bt, int n_frames, const 
   }
   plan_frame_strips(bt.h_jobs, n_frames);
   plan_resize_strips(bt.h_jobs, n_frames);
+  bt.n = n_frames;
+  bt.inline_job = allow_inline && frame_strips_inline_ok(bt.h_jobs, n_frames);
+  if (bt.inline_job) return NES_OK;  // the one frame travels in its kernel's parameter block: nothing to upload
   // descriptor upload on the copy stream, so that it overlaps the kernels of the previous batch
   if (gl_used > 0) CU_TRY(s, cudaMemcpyAsync(bt.d_glyphs, bt.h_glyphs, (size_t)gl_used * sizeof(DevPlaced), cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaMemcpyAsync(bt.d_jobs, bt.h_jobs, sizeof(DevJob) * n_frames, cudaMemcpyHostToDevice, s->st_in));
   CU_TRY(s, cudaEventRecord(bt.up, s->st_in));
-  bt.n = n_frames;
   return NES_OK;
 }
 
@@ -1220,10 +1229,10 @@ int nes_gpu_convert_batch_device(nes_gpu_session *s, int n_frames, const nes_fra
   if (s->sticky) return s->sticky;
   CU_TRY(s, cudaSetDevice(s->cfg.device));
   BatchTables &bt = s->batch[s->batch_seq++ % kBatchRing];
-  const int st = build_batch(s, bt, n_frames, in, runs, n_runs, out);
+  const int st = build_batch(s, bt, n_frames, in, runs, n_runs, out, /*allow_inline=*/true);
   if (st) return st;
-  CU_TRY(s, cudaStreamWaitEvent(s->st_k, bt.up, 0));
-  run_kernels(s, bt.d_jobs, bt.h_jobs, n_frames, s->st_k);
+  if (!bt.inline_job) CU_TRY(s, cudaStreamWaitEvent(s->st_k, bt.up, 0));
+  run_kernels(s, bt.d_jobs, bt.h_jobs, n_frames, s->st_k, bt.inline_job ? bt.h_glyphs : nullptr);
   CU_TRY(s, cudaGetLastError());
   CU_TRY(s, cudaEventRecord(bt.done, s->st_k));
   bt.used = true;

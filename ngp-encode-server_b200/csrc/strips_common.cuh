@@ -170,8 +170,8 @@ __device__ __forceinline__ void stg64(uint8_t *p, uint32_t w0, uint32_t w1) { *(
 // (one thread each); the descriptors that hit are staged in shared memory; then a warp takes a glyph and a
 // lane one of its rows: ONE load of the row's bit mask (1 bit per pixel, DevPlaced) and a loop over its set bits.
 template <int BPP, int SW, int HITS = STRIP_HITS>
-__device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *stage0, int qc, int ns, int slot_bytes, int x0, int x1, int yc0, int ra, int rb,
-                                            int rgb_base, DevPlaced *s_hits, int *s_nhits) {
+__device__ __forceinline__ void stamp_chunk(const DevJob &jb, const DevPlaced *glyph_list, uint8_t *stage0, int qc, int ns, int slot_bytes, int x0, int x1, int yc0, int ra,
+                                            int rb, int rgb_base, DevPlaced *s_hits, int *s_nhits) {
   constexpr int ROWB = SW * BPP;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int g_begin = 0, g_end = jb.n_glyphs;
@@ -179,7 +179,7 @@ __device__ __forceinline__ void stamp_chunk(const DevJob &jb, uint8_t *stage0, i
     const int b0 = max(ra - jb.glyph_max_h, 0) >> jb.glyph_band_shift, b1 = (rb - 1) >> jb.glyph_band_shift;
     g_begin = jb.glyph_band[b0]; g_end = jb.glyph_band[b1 + 1];
   }
-  const DevPlaced *__restrict__ glyphs = jb.glyphs;
+  const DevPlaced *__restrict__ glyphs = glyph_list ? glyph_list : jb.glyphs;  // (the list may travel in the kernel's parameter block)
   const uint32_t *__restrict__ atlas = jb.atlas;
   for (int base = g_begin; base < g_end; base += HITS) {
     if (tid == 0) *s_nhits = 0;
