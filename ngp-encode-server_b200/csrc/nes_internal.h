@@ -41,13 +41,16 @@ constexpr int GLYPH_BANDS = 256;          // placed glyphs of a resize job are b
 // Strip-organised resize kernel (resize_strips.cu, k_resize_strips): a work unit is one segment (rz_seg_rows
 // destination rows) of one column strip (rz_dw destination columns) of one frame; its source window is at most
 // RZ_BOXW pixels wide (one 4-pixel group per lane) and is walked top to bottom in chunks of RZ_CH source rows through
-// the same TMA sub-stage ring as k_frame_strips; a warp takes a source row from packed pixels to horizontally
-// filtered 15-bit samples in RZ_NR-row rings, the vertical pass runs once per chunk.
+// the same TMA sub-stage ring as k_frame_strips.  One persistent CTA per SM with three warp roles: RZ_H_WARPS take
+// source rows from packed pixels to horizontally filtered 15-bit samples in rings, RZ_V_WARPS run the vertical pass
+// one chunk behind them, one producer warp issues the TMA copies; the roles meet only at mbarriers.
 constexpr int RZ_BOXW = 128;
 constexpr int RZ_DEPB = RZ_BOXW + 16;  // bytes of a staged depth row: its box starts on the 16-pixel boundary at or below the window origin
-constexpr int RZ_SUB = 8;        // source rows per TMA sub-stage (one per consumer warp)
-constexpr int RZ_CH = 16;        // source rows per chunk
-constexpr int RZ_MAX_DW = 128;   // destination columns per strip (4 per lane)
+constexpr int RZ_SUB = 8;        // source rows per TMA sub-stage
+constexpr int RZ_CH = 32;        // source rows per chunk (two rows per horizontal-pass warp)
+constexpr int RZ_H_WARPS = 16, RZ_V_WARPS = 6;  // 23 warps with the producer: 6 per scheduler, 80 registers each
+constexpr int RZ_THREADS = 32 * (RZ_H_WARPS + RZ_V_WARPS + 1);
+constexpr int RZ_MAX_DW = 96;    // destination columns per strip (three 32-column slots per lane)
 constexpr int RZ_MAX_TH = 8;     // horizontal taps kept in registers
 constexpr int RZ_MAX_TV = 16;    // vertical taps
 constexpr int RZ_MIN_WD = 64, RZ_MIN_HD = 32;  // smaller destinations go to k_resize_tiles
@@ -183,6 +186,10 @@ struct alignas(64) DevJob {
   int32_t rz_dw;                         // destination columns per strip (multiple of 16, <= RZ_MAX_DW; 0: the size pair does not fit)
   int32_t rz_strips_x, rz_seg_rows, rz_segs_y;
   int32_t rz_unit_base[2], rz_units;     // [bpp-3]: units of the rz jobs of that pixel class ahead of this job in the launch
+  // overlay bitmap of the frame (k_overlay_bits, resize_strips.cu): one bit per source pixel, rz_ovl_pitch words per row, at word
+  // rz_ovl_off of the launch's overlay scratch (< 0: the job has no text)
+  int64_t rz_ovl_off;
+  int32_t rz_ovl_pitch;
 };
 
 // Parameter block of a single-frame launch of k_frame_strips (k_frame_strips_1): descriptor + placed glyphs by value.
@@ -207,7 +214,14 @@ constexpr int COUNTER_SLOTS = 64;  // work counters of k_frame_strips: one self 
 int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
 // Assigns rz_seg_rows / rz_unit_base of the jobs k_resize_strips takes (host), then the launch itself.
 void plan_resize_strips(DevJob *jobs_host, int n_jobs);
-int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream);
+// scratch: the caller's (session's / mux's) overlay bitmap storage, grown on demand; a launch whose jobs carry text
+// clears it and rebuilds the bitmaps (k_overlay_bits) ahead of the resize kernel, on the same stream
+struct RzScratch {
+  uint32_t *ovl = nullptr;
+  size_t cap = 0;  // bytes
+};
+int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream, RzScratch *scratch);
+void resize_strips_free_scratch(RzScratch *scratch);
 int resize_strips_init();
 // GRAY16LE depth images of the jobs that carry one (depth16.cu); returns launches or -1
 int launch_depth16(const DevJob *jobs_host, int n_jobs, void *stream);

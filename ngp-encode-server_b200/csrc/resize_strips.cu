@@ -9,20 +9,23 @@
 //   depth : GRAY8 -> horizontal polyphase (>>7) -> range compression -> vertical; U = V = 128
 //
 // Shape (HBM-bound in principle; what bounds it in practice is instruction issue, so the organisation is about
-// touching every source pixel once and keeping per-pixel instruction counts low):
+// touching every source pixel once, keeping per-pixel instruction counts low and never making one warp wait for another):
 //   * work unit = one SEGMENT (rz_seg_rows destination rows) of one column STRIP (rz_dw destination columns)
-//     of one frame; persistent CTAs take units from a global counter.  The strip's source window is at most
+//     of one frame; ONE persistent CTA per SM takes units from a global counter.  The strip's source window is at most
 //     RZ_BOXW = 128 pixels wide: one 4-pixel group per lane;
-//   * the source window is walked top to bottom in CHUNKS of 16 source rows; rows travel through a ring of 8-row
-//     SUB-STAGES filled by the producer warp with 2D tensor-map TMA copies (packed pixels and GRAY8 depth of every
+//   * the source window is walked top to bottom in CHUNKS of 32 source rows; rows travel through a ring of 8-row
+//     SUB-STAGES filled by the PRODUCER warp with 2D tensor-map TMA copies (packed pixels and GRAY8 depth of every
 //     staged source; SASS UTMALDG), exactly like k_frame_strips;
-//   * a consumer warp owns one source row of a sub-stage END TO END: composite select among the staged sources in
-//     registers -> 14-bit Y / U / V and depth bytes into a 1 KB per-warp row buffer -> horizontal pass of that row
-//     (lane = destination column, its taps live in registers for the whole unit) -> 15-bit samples into four
-//     48-row rings (Y, depth, U, V); the sub-stage is released at once;
-//   * one consumer barrier per chunk, then the vertical pass emits every destination row whose taps are now all in
-//     the rings (4 adjacent columns per thread, 16-byte ring loads, 4-byte stores).  The vertical halo is paid once
-//     per segment, not per tile, and nothing is staged twice.
+//   * 16 HORIZONTAL warps: a warp owns one source row of a sub-stage END TO END: composite select among the staged
+//     sources in registers -> overlay bits (one word of the frame's overlay bitmap) -> 14-bit Y / U / V and depth bytes
+//     into a 1 KB per-warp row buffer -> horizontal pass of that row (lane = destination column, its taps live in
+//     registers for the whole unit) -> 15-bit samples into four rings (Y, depth, U, V); the sub-stage is released at once;
+//   * 6 VERTICAL warps run one chunk behind: every destination row whose taps are all in the rings (4 adjacent columns
+//     per thread, 16-byte ring loads, 4-byte stores).  The vertical halo is paid once per segment, nothing is staged twice;
+//   * the roles meet only at mbarriers (sub-stage full / empty, chunk horizontally done, chunk vertically done): there is
+//     no CTA-wide barrier anywhere in the loop;
+//   * the text overlay is ONE BIT PER SOURCE PIXEL in a per-frame bitmap that a small kernel ahead of this one
+//     (k_overlay_bits, same stream) builds from the placed glyphs and the 1-bit atlas.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,31 +41,36 @@ namespace nes {
 
 namespace {
 
-enum { RM_ROWS = 0, RM_SELECT = 1, RM_MATERIALIZED = 2 };
+enum { RM_ROWS = 0, RM_SELECT = 1 };
 
 constexpr int RZ_ROWBUF = 1024;        // per-warp row buffer: y14 | u14 | v14 (u16, 144 each) | depth bytes (144)
 constexpr int RZ_RB_Y = 0, RZ_RB_U = 288, RZ_RB_V = 576, RZ_RB_D = 864;
 constexpr int RZ_NS_MAX = 8;
-constexpr int RZ_NCTX = 8;
-constexpr int RZ_HITS = 64;            // glyph rect tests per pass of an overlay chunk
+constexpr int RZ_NCTX = 8;             // chunk contexts in flight: the producer runs <= 2 chunks ahead of the horizontal warps, the vertical warps <= 2 behind
+constexpr int RZ_NL = RZ_MAX_DW / 32;  // 32-column slots of a destination strip
+constexpr int RZ_SUBS = RZ_CH / RZ_SUB;
+constexpr int RZ_HG = RZ_H_WARPS / RZ_SUB;  // groups of horizontal warps (group g takes sub-stages g, g + RZ_HG, ... of a chunk)
+static_assert(RZ_H_WARPS % RZ_SUB == 0 && RZ_SUBS % RZ_HG == 0, "a horizontal warp takes whole sub-stage rows");
+constexpr int RZ_ROWS_PER_WARP = RZ_SUBS / RZ_HG;
 
-// Everything the consumer warps need to know about one chunk (written by lane 0 of the producer warp).
+// Everything the horizontal and vertical warps need to know about one chunk (written by lane 0 of the producer warp).
 struct RzCtx {
   int32_t last;       // last chunk this CTA processes
   int32_t first;      // first chunk of a unit: (re)load the horizontal filter registers
-  int32_t unit_end;   // last chunk of a unit: the rings are reused from slot 0 by the next one
-  int32_t mode, stamp, n_src, job, n_staged;
+  int32_t mode, n_src, n_staged;
   int32_t wx0;        // source column of window column 0 (4-byte pixels: multiple of 4; 3-byte pixels: of 16 -- TMA box rows start on 16-byte boundaries)
   int32_t dshift;     // window column 0 inside the staged depth rows (their box starts at wx0 & ~15)
   int32_t yc0, ra, rb;          // source row of chunk-local row 0; rows of this chunk that are needed [ra, rb)
   int32_t lr0, lr1, cr0, cr1;   // source rows the luma / chroma vertical filters of this unit read
   int32_t ya, yb, ca, cb;       // destination rows to emit after this chunk (luma, chroma)
-  int32_t rbase_y, rbase_c;     // luma / chroma ring slot of chunk-local row 0
+  int32_t rbase_y, rbase_c;     // luma / chroma ring slot of chunk-local row 0 (the rings run on across units)
   int32_t dx0, dw, cx0, dcw;    // destination strip: luma / chroma columns
   int32_t half, dep_staged, nv12, rgb_base;
   int32_t hls, hcs, vls, vcs;   // filter sizes
+  int32_t ovl_pitch;            // words per row of the overlay bitmap
   uint32_t a_mask;
   uint32_t ky[2], ku[2], kv[2];
+  const uint32_t *ovl;          // overlay bitmap of the frame, or null: no glyph touches this chunk
   const int16_t *hl_coef, *hc_coef, *vl_coef, *vc_coef;
   const int32_t *hl_pos, *hc_pos, *vl_pos, *vc_pos;
   int32_t sys, sus, svs, dys, dus, dvs;
@@ -70,12 +78,13 @@ struct RzCtx {
 };
 
 struct RzSmem {
-  int ringY, ringD, ringU, ringV, rowbuf, ctx, bar, hits, mask, stage;
+  int ringY, ringD, ringU, ringV, rowbuf, ctx, bar, stage;
 };
 constexpr int RZ_CTX_BYTES = ((int)sizeof(RzCtx) + 15) & ~15;
-// nry / nrc: rows of the luma (+ depth) and chroma rings: a ring must hold 31 + (vertical filter size) rows so that
-// the rows one chunk's vertical pass still reads are never overwritten by the next chunk's horizontal pass
-__host__ __device__ inline int rz_ring_rows(int vsize) { return (31 + vsize + 7) & ~7; }
+// nry / nrc: rows of the luma (+ depth) and chroma rings.  The vertical pass of chunk j reads back to RZ_CH + (filter
+// size) - 1 rows before the end of chunk j while the horizontal warps may already be writing chunk j + 1 (they wait for
+// the vertical pass of chunk j - 1 before that): 2 * RZ_CH - 1 + (filter size) rows.
+__host__ __device__ inline int rz_ring_rows(int vsize) { return (2 * RZ_CH - 1 + vsize + 7) & ~7; }
 __host__ __device__ inline RzSmem rz_smem(int dwp, int nry, int nrc) {
   RzSmem L;
   int o = 0;
@@ -83,11 +92,9 @@ __host__ __device__ inline RzSmem rz_smem(int dwp, int nry, int nrc) {
   L.ringD = o; o += nry * dwp * 4;
   L.ringU = o; o += nrc * (dwp / 2) * 4;
   L.ringV = o; o += nrc * (dwp / 2) * 4;
-  L.rowbuf = o; o += CONSUMER_WARPS * RZ_ROWBUF;
+  L.rowbuf = o; o += RZ_H_WARPS * RZ_ROWBUF;
   L.ctx = o; o += RZ_NCTX * RZ_CTX_BYTES;
-  L.bar = o; o += 2 * RZ_NS_MAX * 8;
-  L.hits = o; o += RZ_HITS * (int)sizeof(DevPlaced) + 16;
-  L.mask = o; o += RZ_CH * (RZ_BOXW / 32) * 4;  // overlay bits of one chunk of the window
+  L.bar = o; o += (2 * RZ_NS_MAX + 4) * 8;  // full[], empty[], hdone[2], vdone[2]
   L.stage = (o + 1023) & ~1023;
   return L;
 }
@@ -158,68 +165,10 @@ __device__ __forceinline__ void select4(uint32_t px, uint32_t dep, int n_src, ui
   d4 = __byte_perm(lo, hi, 0x5410);
 }
 
-// Overlay bits of one chunk: s_mask[RZ_CH][RZ_BOXW / 32] (zero on entry; window column x of chunk row r is bit x & 31
-// of word r * 4 + (x >> 5)).  The glyph list is bucketed by row band on the host; one thread tests one glyph, the hits
-// are staged as whole descriptors, then a warp takes a glyph and a lane one word of one of its rows (the atlas holds
-// one bit per glyph pixel) and ORs it in, shifted to the window's column grid.  Rows outside [ra, rb) are never set.
-// pass: running count of passes (selects one of the two hit counters; the other one is re-armed in the meantime).
-__device__ __forceinline__ int mask_chunk(const DevJob &jb, uint32_t *s_mask, int x0, int yc0, int ra, int rb, DevPlaced *s_hits, int *s_nhits, int pass) {
-  constexpr int NT = 32 * CONSUMER_WARPS;
-  constexpr int MW = RZ_BOXW / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int x1 = x0 + RZ_BOXW;
-  int g_begin = 0, g_end = jb.n_glyphs;
-  if (jb.glyph_band_shift >= 0) {
-    const int b0 = max(ra - jb.glyph_max_h, 0) >> jb.glyph_band_shift, b1 = (rb - 1) >> jb.glyph_band_shift;
-    g_begin = jb.glyph_band[b0]; g_end = jb.glyph_band[b1 + 1];
-  }
-  const DevPlaced *__restrict__ glyphs = jb.glyphs;
-  const uint32_t *__restrict__ atlas = jb.atlas;
-  auto or_rows = [&](const DevPlaced &pg, int first, int step) {
-    const int q0 = max(0, ra - pg.y), q1 = min(pg.h, rb - pg.y);
-    const int p0 = max(0, x0 - pg.x), p1 = min(pg.w, x1 - pg.x);
-    const int bit_lo = pg.bit0 + p0, bit_hi = pg.bit0 + p1;
-    const int w_lo = bit_lo >> 5, w_hi = (bit_hi - 1) >> 5, nw = w_hi - w_lo + 1;
-    for (int i = first; i < (q1 - q0) * nw; i += step) {
-      const int qq = i / nw, wi = w_lo + (i - qq * nw), q = q0 + qq;
-      uint32_t m = __ldg(atlas + pg.mask_off + (uint32_t)(q * pg.wpr + wi));
-      const int lo = max(bit_lo - 32 * wi, 0), hi = min(bit_hi - 32 * wi, 32);
-      m &= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (32 - hi));
-      if (m == 0) continue;
-      const int xb = pg.x - pg.bit0 + 32 * wi - x0;  // window column of bit 0 of this word (negative only for masked-off bits)
-      const int wd = xb >> 5, sh = xb & 31;
-      uint32_t *mrow = s_mask + (pg.y + q - yc0) * MW;
-      const uint32_t lo_part = m << sh;
-      if (lo_part && wd >= 0) atomicOr(&mrow[wd], lo_part);
-      if (sh) {
-        const uint32_t hi_part = m >> (32 - sh);
-        if (hi_part) atomicOr(&mrow[wd + 1], hi_part);
-      }
-    }
-  };
-  for (int base = g_begin; base < g_end; base += NT, pass++) {
-    int *cnt = s_nhits + (pass & 1);
-    if (base + tid < g_end) {
-      const DevPlaced pg = glyphs[base + tid];
-      if (pg.x < x1 && pg.x + pg.w > x0 && pg.y < rb && pg.y + pg.h > ra) {
-        const int i = atomicAdd(cnt, 1);
-        if (i < RZ_HITS) s_hits[i] = pg;
-        else or_rows(pg, 0, 1);  // more hits than staging slots (tiny glyphs): this thread does the whole glyph
-      }
-    }
-    consumer_sync();
-    const int nh = min(*cnt, RZ_HITS);
-    if (tid == 0) s_nhits[(pass + 1) & 1] = 0;
-    for (int h = warp; h < nh; h += CONSUMER_WARPS) or_rows(s_hits[h], lane, 32);
-    consumer_sync();
-  }
-  return pass;
-}
-
 // Horizontal pass of one source row for NL slots of 32 luma columns (+ the depth plane, same filter): all chains
 // advance together, tap by tap.
 template <int NL, int T>
-__device__ __forceinline__ void h_luma(uint32_t rowbuf, const int (&pos_l)[4], const int (&cf_l)[4][T], bool want_depth, int dw, int lane, uint32_t oy, uint32_t od) {
+__device__ __forceinline__ void h_luma(uint32_t rowbuf, const int (&pos_l)[RZ_NL], const int (&cf_l)[RZ_NL][T], bool want_depth, int dw, int lane, uint32_t oy, uint32_t od) {
   int v[NL], d[NL];
   uint32_t a[NL], ad[NL];
 #pragma unroll
@@ -279,39 +228,78 @@ __device__ __forceinline__ void h_chroma(uint32_t rowbuf, const int (&pos_c)[2],
 
 }  // namespace
 
+// Overlay bitmaps of the jobs of a launch: bit (x & 31) of word rz_ovl_off + y * rz_ovl_pitch + (x >> 5) of the
+// scratch is set when a glyph pixel with coverage != 0 covers source pixel (x, y) (render_text.cc:94-106: such a
+// pixel becomes white).  The launcher clears the storage; a warp takes a placed glyph, a lane one mask word of one
+// of its rows (the atlas holds one bit per glyph pixel) and ORs it in, shifted to the frame's column grid.
+__global__ void __launch_bounds__(256) k_overlay_bits(const DevJob *__restrict__ jobs, int n_jobs, uint32_t *__restrict__ ovl_base) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = blockIdx.y; j < n_jobs; j += gridDim.y) {
+    const DevJob &jb = jobs[j];
+    if (!jb.rz_ok || jb.rz_ovl_off < 0 || jb.n_glyphs <= 0) continue;
+    uint32_t *bits = ovl_base + jb.rz_ovl_off;
+    const int pitch = jb.rz_ovl_pitch, W = jb.W, H = jb.H;
+    const DevPlaced *__restrict__ glyphs = jb.glyphs;
+    const uint32_t *__restrict__ atlas = jb.atlas;
+    for (int g = blockIdx.x * 8 + warp; g < jb.n_glyphs; g += gridDim.x * 8) {
+      const DevPlaced pg = glyphs[g];
+      const int q0 = max(0, -pg.y), q1 = min(pg.h, H - pg.y);
+      const int p0 = max(0, -pg.x), p1 = min(pg.w, W - pg.x);
+      if (q1 <= q0 || p1 <= p0) continue;
+      const int bit_lo = pg.bit0 + p0, bit_hi = pg.bit0 + p1;
+      const int w_lo = bit_lo >> 5, w_hi = (bit_hi - 1) >> 5, nw = w_hi - w_lo + 1;
+      for (int i = lane; i < (q1 - q0) * nw; i += 32) {
+        const int qq = i / nw, wi = w_lo + (i - qq * nw), q = q0 + qq;
+        uint32_t m = __ldg(atlas + pg.mask_off + (uint32_t)(q * pg.wpr + wi));
+        const int lo = max(bit_lo - 32 * wi, 0), hi = min(bit_hi - 32 * wi, 32);
+        m &= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (32 - hi));
+        if (m == 0) continue;
+        const int xb = pg.x - pg.bit0 + 32 * wi;  // frame column of bit 0 of this word (negative only for masked-off bits)
+        const int wd = xb >> 5, sh = xb & 31;
+        uint32_t *row = bits + (size_t)(pg.y + q) * pitch;
+        const uint32_t lo_part = m << sh;
+        if (lo_part && wd >= 0) atomicOr(&row[wd], lo_part);
+        if (sh) {
+          const uint32_t hi_part = m >> (32 - sh);
+          if (hi_part) atomicOr(&row[wd + 1], hi_part);
+        }
+      }
+    }
+  }
+}
+
 // T: horizontal taps held in registers (>= the longest horizontal filter of the launch; shorter filters are
 // padded with zero coefficients).
 template <int BPP, int T>
-__global__ void __launch_bounds__(CTA_THREADS, 2)
-k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters, int ns, int slot_bytes, int dwp, int nry, int nrc) {
+__global__ void __launch_bounds__(RZ_THREADS, 1)
+k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters, const uint32_t *__restrict__ ovl_base, int ns, int slot_bytes,
+                int dwp, int nry, int nrc) {
   asm volatile("griddepcontrol.launch_dependents;");  // see k_frame_strips: consecutive launches overlap
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int ROWB = RZ_BOXW * BPP;
-  constexpr int NW = CONSUMER_WARPS;
   const RzSmem L = rz_smem(dwp, nry, nrc);
   uint64_t *s_full = (uint64_t *)(smem + L.bar);
   uint64_t *s_empty = s_full + RZ_NS_MAX;
-  DevPlaced *s_hits = (DevPlaced *)(smem + L.hits);
-  int *s_nhits = (int *)(s_hits + RZ_HITS);  // [2]: alternate from pass to pass (the idle one is re-armed meanwhile)
-  uint32_t *s_mask = (uint32_t *)(smem + L.mask);
+  uint64_t *s_hdone = s_empty + RZ_NS_MAX;  // [2]: the horizontal warps have written chunk j's rows into the rings (j & 1)
+  uint64_t *s_vdone = s_hdone + 2;          // [2]: the vertical warps have emitted chunk j's destination rows
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t smem_base = smem_u32(smem);
 
   if (tid == 0) {
-    for (int i = 0; i < RZ_NS_MAX; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], NW); }
+    for (int i = 0; i < RZ_NS_MAX; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], RZ_SUB); }
+    for (int i = 0; i < 2; i++) { mbar_init(&s_hdone[i], RZ_H_WARPS); mbar_init(&s_vdone[i], RZ_V_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    s_nhits[0] = s_nhits[1] = 0;
   }
-  if (tid < RZ_CH * (RZ_BOXW / 32)) s_mask[tid] = 0;
   __syncthreads();
 
-  if (warp == NW) {
+  if (warp == RZ_H_WARPS + RZ_V_WARPS) {
     // =========================== producer warp ===========================================
     int cur_u = (int)blockIdx.x, next_u = 0;
     if (lane == 0) next_u = (int)gridDim.x + (int)atomicAdd(&counters[0], 1u);
     next_u = __shfl_sync(0xffffffffu, next_u, 0);
     int q = 0, par = 0, round0 = 1;
     int chunk_it = 0;
+    int rbase_y = 0, rbase_c = 0;  // the rings run on from unit to unit
     while (cur_u < total_units) {
       const int j = job_of_rz_unit(jobs, n_jobs, BPP - 3, cur_u);
       const DevJob *jp = jobs + j;
@@ -348,8 +336,8 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
       }
       const int strips256 = (jp->W + STRIP_W - 1) / STRIP_W;
       const int nbands = (jp->H + (1 << MASK_BAND_SHIFT) - 1) >> MASK_BAND_SHIFT;
+      const bool has_text = jp->n_glyphs > 0 && jp->rz_ovl_off >= 0 && ovl_base != nullptr;
       int ly = dy0, cy = cy0;  // emission cursors
-      int rbase_y = 0, rbase_c = 0;
       for (int k = 0; k < nchunks; k++, chunk_it++) {
         const int yc0 = r0 + k * RZ_CH;
         const int ra = yc0, rb = min(yc0 + RZ_CH, r1);
@@ -375,7 +363,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
         if (lane == 0) {
           RzCtx &c = *(RzCtx *)(smem + L.ctx + (chunk_it & (RZ_NCTX - 1)) * RZ_CTX_BYTES);
           int stamp = 0;
-          if (jp->n_glyphs > 0) {
+          if (has_text) {
             stamp = 1;
             if (jp->use_mask) {
               stamp = 0;
@@ -389,10 +377,8 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           }
           c.last = last_k && next_u >= total_units;
           c.first = (k == 0);
-          c.unit_end = last_k;
-          c.stamp = stamp;
           c.mode = n_src > 1 ? RM_SELECT : RM_ROWS;
-          c.n_src = n_src; c.job = j; c.n_staged = n_staged;
+          c.n_src = n_src; c.n_staged = n_staged;
           c.wx0 = wx0; c.dshift = wx0 - wxd; c.yc0 = yc0; c.ra = ra; c.rb = rb;
           c.lr0 = lr0; c.lr1 = lr1; c.cr0 = cr0; c.cr1 = cr1;
           c.ya = ya; c.yb = ly; c.ca = ca; c.cb = cy;
@@ -400,6 +386,8 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           c.dx0 = dx0; c.dw = dw; c.cx0 = cx0; c.dcw = dcw;
           c.half = half; c.dep_staged = dep_staged; c.nv12 = jp->nv12; c.rgb_base = jp->rgb_base;
           c.hls = jp->hl.size; c.hcs = jp->hc.size; c.vls = vls; c.vcs = vcs;
+          c.ovl = stamp ? ovl_base + jp->rz_ovl_off : nullptr;
+          c.ovl_pitch = jp->rz_ovl_pitch;
           c.a_mask = jp->a_off >= 0 ? (0xFFu << (8 * jp->a_off)) : 0xFFFFFFFFu;
           c.ky[0] = jp->ky[0]; c.ky[1] = jp->ky[1]; c.ku[0] = jp->ku[0]; c.ku[1] = jp->ku[1]; c.kv[0] = jp->kv[0]; c.kv[1] = jp->kv[1];
           c.hl_coef = jp->hl.coef; c.hc_coef = jp->hc.coef; c.vl_coef = jp->vl.coef; c.vc_coef = jp->vc.coef;
@@ -408,12 +396,9 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           c.sy = jp->sy; c.su = jp->su; c.sv = jp->sv; c.dy = jp->dy; c.du = jp->du; c.dv = jp->dv;
         }
         __syncwarp();
-#ifdef NES_RZ_DEBUG
-        if (lane < 2 && cur_u < 3) printf("cta %d u %d j %d strip %d seg %d wx0 %d r0 %d r1 %d k %d yc0 %d rb %d ya..yb %d..%d lane %d map %p off %u x %d tx %u ns %d slot %d stage %d dwp %d\n", (int)blockIdx.x, cur_u, j, strip, seg, wx0, r0, r1, k, yc0, rb, ya, ly, lane, (const void *)my_map, my_off, my_x, tx_bytes, ns, slot_bytes, L.stage, dwp);
-#endif
 #pragma unroll 1
-        for (int sub = 0; sub < RZ_CH / RZ_SUB; sub++) {
-          if (!round0) mbar_wait_hint_a(smem_u32(&s_empty[q]), (uint32_t)(par ^ 1), 2000u);
+        for (int sub = 0; sub < RZ_SUBS; sub++) {
+          if (!round0) mbar_wait_sleep_a(smem_u32(&s_empty[q]), (uint32_t)(par ^ 1), 256u);
           const int ys = yc0 + sub * RZ_SUB;
           const bool wanted = ys < rb;
           if (wanted) {
@@ -441,16 +426,159 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
     return;
   }
 
-  // ============================= consumer warps ===========================================
-  const uint32_t full0 = smem_base + L.bar, empty0 = full0 + RZ_NS_MAX * 8;
-  const uint32_t rowbuf = smem_base + L.rowbuf + warp * RZ_ROWBUF;
   const uint32_t ringY = smem_base + L.ringY, ringD = smem_base + L.ringD, ringU = smem_base + L.ringU, ringV = smem_base + L.ringV;
   const int rowbY = dwp * 4, rowbC = (dwp / 2) * 4;
-  // horizontal filters of the current unit: lane = destination column (+32 per slot)
-  int pos_l[4], pos_c[2];
-  int cf_l[4][T], cf_c[2][T];
+  const uint32_t hdone0 = smem_u32(s_hdone), vdone0 = smem_u32(s_vdone);
+
+  if (warp >= RZ_H_WARPS) {
+    // ============================= vertical warps ===========================================
+    // chunk j: wait until every horizontal warp has written its rows of chunk j, emit the destination rows the
+    // producer listed for it, then tell the horizontal warps (they wait for chunk j before writing chunk j + 2)
+    const int vtid = tid - 32 * RZ_H_WARPS;
+    constexpr int VT = 32 * RZ_V_WARPS;
+    for (int j = 0;; j++) {
+      mbar_wait_sleep_a(hdone0 + (j & 1) * 8, (uint32_t)((j >> 1) & 1), 512u);
+      const RzCtx &c = *(const RzCtx *)(smem + L.ctx + (j & (RZ_NCTX - 1)) * RZ_CTX_BYTES);
+      const int last = c.last;
+      const int yc0 = c.yc0, dw = c.dw, dcw = c.dcw;
+      const bool want_depth = c.dy != nullptr;
+      const int rbase_y = c.rbase_y, rbase_c = c.rbase_c;
+      // (the launch only takes jobs with 16-byte aligned destination planes: whole groups go out as words)
+      const int ya = c.ya, yb = c.yb, vls = c.vls;
+      const int gl = (dw + 3) >> 2;
+      const int total_l = (yb - ya) * gl;
+      const uint32_t rcp_l = gl > 1 ? 0xFFFFFFFFu / (uint32_t)gl + 1u : 0u;  // idx / gl == umulhi(idx, rcp) for every idx here
+      const int ca = c.ca, cb = c.cb, vcs = c.vcs;
+      const int gc = (dcw + 3) >> 2;
+      const int total_c = (cb - ca) * gc;
+      const uint32_t rcp_c = gc > 1 ? 0xFFFFFFFFu / (uint32_t)gc + 1u : 0u;
+      const bool nv12 = c.nv12 != 0;
+      uint8_t *const sy = c.sy + c.dx0, *const dyp = want_depth ? c.dy + c.dx0 : nullptr;
+      for (int it = vtid; it < total_l + total_c; it += VT) {
+        if (it < total_l) {
+          // luma (+ depth luma, same filter)
+          const int idx = it;
+          const int ry = gl > 1 ? (int)__umulhi((uint32_t)idx, rcp_l) : idx, g = idx - ry * gl;
+          const int dyy = ya + ry;
+          const int pos = __ldg(c.vl_pos + dyy);
+          int slot = rbase_y + pos - yc0;
+          if (slot < 0) slot += nry;
+          if (slot >= nry) slot -= nry;
+          int a[4], d[4];
+          if (vls == 1) {
+            const int4 w = lds_v4s(ringY + slot * rowbY + g * 16);
+            a[0] = (w.x + 64) >> 7; a[1] = (w.y + 64) >> 7; a[2] = (w.z + 64) >> 7; a[3] = (w.w + 64) >> 7;
+            if (want_depth) {
+              const int4 e = lds_v4s(ringD + slot * rowbY + g * 16);
+              d[0] = (e.x + 64) >> 7; d[1] = (e.y + 64) >> 7; d[2] = (e.z + 64) >> 7; d[3] = (e.w + 64) >> 7;
+            }
+          } else {
+            const int16_t *cf = c.vl_coef + (size_t)dyy * vls;
+            a[0] = a[1] = a[2] = a[3] = 64 << 12;
+            d[0] = d[1] = d[2] = d[3] = 64 << 12;
+            int kn = (int)__ldg(cf);
+            for (int jj = 0; jj < vls; jj++) {
+              const int k = kn;
+              if (jj + 1 < vls) kn = (int)__ldg(cf + jj + 1);  // the next tap's coefficient is in flight while this tap is applied
+              const int4 w = lds_v4s(ringY + slot * rowbY + g * 16);
+              a[0] += w.x * k; a[1] += w.y * k; a[2] += w.z * k; a[3] += w.w * k;
+              if (want_depth) {
+                const int4 e = lds_v4s(ringD + slot * rowbY + g * 16);
+                d[0] += e.x * k; d[1] += e.y * k; d[2] += e.z * k; d[3] += e.w * k;
+              }
+              if (++slot == nry) slot = 0;
+            }
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
+            for (int k = 0; k < 4; k++) { a[k] >>= 19; d[k] >>= 19; }
+          }
+          const uint32_t yw = clip8_relu(a[0]) | (clip8_relu(a[1]) << 8) | (clip8_relu(a[2]) << 16) | (clip8_relu(a[3]) << 24);
+          uint8_t *o = sy + (size_t)dyy * c.sys + 4 * g;
+          if (4 * g + 4 <= dw) stg32(o, yw);
+          else
+            for (int k = 0; 4 * g + k < dw; k++) o[k] = (uint8_t)(yw >> (8 * k));
+          if (want_depth) {
+            const uint32_t gw = clip8_relu(d[0]) | (clip8_relu(d[1]) << 8) | (clip8_relu(d[2]) << 16) | (clip8_relu(d[3]) << 24);
+            uint8_t *od = dyp + (size_t)dyy * c.dys + 4 * g;
+            if (4 * g + 4 <= dw) stg32(od, gw);
+            else
+              for (int k = 0; 4 * g + k < dw; k++) od[k] = (uint8_t)(gw >> (8 * k));
+          }
+        } else {
+          // chroma (U and V share the filter); depth chroma is constant 128
+          const int idx = it - total_l;
+          const int ry = gc > 1 ? (int)__umulhi((uint32_t)idx, rcp_c) : idx, g = idx - ry * gc;
+          const int cyy = ca + ry;
+          const int pos = __ldg(c.vc_pos + cyy);
+          int slot = rbase_c + pos - yc0;
+          if (slot < 0) slot += nrc;
+          if (slot >= nrc) slot -= nrc;
+          int u[4], v[4];
+          if (vcs == 1) {
+            const int4 w = lds_v4s(ringU + slot * rowbC + g * 16), e = lds_v4s(ringV + slot * rowbC + g * 16);
+            u[0] = (w.x + 64) >> 7; u[1] = (w.y + 64) >> 7; u[2] = (w.z + 64) >> 7; u[3] = (w.w + 64) >> 7;
+            v[0] = (e.x + 64) >> 7; v[1] = (e.y + 64) >> 7; v[2] = (e.z + 64) >> 7; v[3] = (e.w + 64) >> 7;
+          } else {
+            const int16_t *cf = c.vc_coef + (size_t)cyy * vcs;
+            u[0] = u[1] = u[2] = u[3] = 64 << 12;
+            v[0] = v[1] = v[2] = v[3] = 64 << 12;
+            int kn = (int)__ldg(cf);
+            for (int jj = 0; jj < vcs; jj++) {
+              const int k = kn;
+              if (jj + 1 < vcs) kn = (int)__ldg(cf + jj + 1);
+              const int4 w = lds_v4s(ringU + slot * rowbC + g * 16), e = lds_v4s(ringV + slot * rowbC + g * 16);
+              u[0] += w.x * k; u[1] += w.y * k; u[2] += w.z * k; u[3] += w.w * k;
+              v[0] += e.x * k; v[1] += e.y * k; v[2] += e.z * k; v[3] += e.w * k;
+              if (++slot == nrc) slot = 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { u[k] >>= 19; v[k] >>= 19; }
+          }
+          const uint32_t ub = clip8_relu(u[0]) | (clip8_relu(u[1]) << 8) | (clip8_relu(u[2]) << 16) | (clip8_relu(u[3]) << 24);
+          const uint32_t vb = clip8_relu(v[0]) | (clip8_relu(v[1]) << 8) | (clip8_relu(v[2]) << 16) | (clip8_relu(v[3]) << 24);
+          const bool full = 4 * g + 4 <= dcw;
+          if (nv12) {
+            // U0 V0 U1 V1 | U2 V2 U3 V3: chroma column x sits at byte 2x of the UV row
+            const uint32_t w0 = __byte_perm(ub, vb, 0x5140), w1 = __byte_perm(ub, vb, 0x7362);
+            uint8_t *o = c.su + (size_t)cyy * c.sus + 2 * c.cx0 + 8 * g;
+            if (full) stg64(o, w0, w1);
+            else
+              for (int k = 0; 4 * g + (k >> 1) < dcw; k++) o[k] = (uint8_t)((k < 4 ? w0 : w1) >> (8 * (k & 3)));
+            if (want_depth) {
+              uint8_t *od = c.du + (size_t)cyy * c.dus + 2 * c.cx0 + 8 * g;
+              if (full) stg64(od, 0x80808080u, 0x80808080u);
+              else
+                for (int k = 0; 4 * g + (k >> 1) < dcw; k++) od[k] = 128;
+            }
+          } else {
+            uint8_t *ou = c.su + (size_t)cyy * c.sus + c.cx0 + 4 * g, *ov = c.sv + (size_t)cyy * c.svs + c.cx0 + 4 * g;
+            if (full) { stg32(ou, ub); stg32(ov, vb); }
+            else
+              for (int k = 0; 4 * g + k < dcw; k++) { ou[k] = (uint8_t)(ub >> (8 * k)); ov[k] = (uint8_t)(vb >> (8 * k)); }
+            if (want_depth) {
+              uint8_t *du_ = c.du + (size_t)cyy * c.dus + c.cx0 + 4 * g, *dv_ = c.dv + (size_t)cyy * c.dvs + c.cx0 + 4 * g;
+              if (full) { stg32(du_, 0x80808080u); stg32(dv_, 0x80808080u); }
+              else
+                for (int k = 0; 4 * g + k < dcw; k++) { du_[k] = 128; dv_[k] = 128; }
+            }
+          }
+        }
+      }
+      __syncwarp();  // every lane is done with the rings and the context of chunk j
+      if (lane == 0) mbar_arrive_a(vdone0 + (j & 1) * 8);
+      if (last) break;
+    }
+    return;
+  }
+
+  // ============================= horizontal warps ===========================================
+  const uint32_t full0 = smem_base + L.bar, empty0 = full0 + RZ_NS_MAX * 8;
+  const uint32_t rowbuf = smem_base + L.rowbuf + warp * RZ_ROWBUF;
+  const int hgrp = warp / RZ_SUB, wrow = warp % RZ_SUB;  // this warp takes row wrow of the sub-stages hgrp, hgrp + RZ_HG, ... of every chunk
+  // horizontal filters of the current unit: lane = destination column (+32 per slot)
+  int pos_l[RZ_NL], pos_c[2];
+  int cf_l[RZ_NL][T], cf_c[2][T];
+#pragma unroll
+  for (int c = 0; c < RZ_NL; c++) {
     pos_l[c] = 0;
 #pragma unroll
     for (int jj = 0; jj < T; jj++) cf_l[c][jj] = 0;
@@ -461,30 +589,31 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
 #pragma unroll
     for (int jj = 0; jj < T; jj++) cf_c[c][jj] = 0;
   }
-  int qc = 0, parc = 0;
-  int mask_pass = 0;  // overlay passes so far (selects the hit counter; the same in every consumer thread)
-  for (int chunk_it = 0;; chunk_it++) {
-    int q[2], par[2];
-    q[0] = qc; par[0] = parc;
-    q[1] = qc + 1; par[1] = parc;
-    if (q[1] == ns) { q[1] = 0; par[1] ^= 1; }
+  int qc = 0, parc = 0;  // ring slot and parity of the chunk's first sub-stage
+  for (int j = 0;; j++) {
+    int q[RZ_ROWS_PER_WARP], par[RZ_ROWS_PER_WARP];
+#pragma unroll
+    for (int i = 0; i < RZ_ROWS_PER_WARP; i++) {
+      int a = qc + hgrp + i * RZ_HG, p = parc;
+      while (a >= ns) { a -= ns; p ^= 1; }
+      q[i] = a; par[i] = p;
+    }
     mbar_wait_hint_a(full0 + q[0] * 8, (uint32_t)par[0], 2000u);
-    const RzCtx &c = *(const RzCtx *)(smem + L.ctx + (chunk_it & (RZ_NCTX - 1)) * RZ_CTX_BYTES);
-    const int last = c.last, unit_end = c.unit_end;
+    const RzCtx &c = *(const RzCtx *)(smem + L.ctx + (j & (RZ_NCTX - 1)) * RZ_CTX_BYTES);
+    const int last = c.last;
     {
-      const uint32_t sb[2] = {smem_base + L.stage + (uint32_t)(q[0] * slot_bytes), smem_base + L.stage + (uint32_t)(q[1] * slot_bytes)};
       const uint32_t dep_off = (uint32_t)(c.n_staged * RZ_SUB) * ROWB + (uint32_t)c.dshift;
       const int wx0 = c.wx0, yc0 = c.yc0, ra = c.ra, rb = c.rb;
       const int dw = c.dw, dcw = c.dcw;
       const bool half = c.half != 0, dep_staged = c.dep_staged != 0;
       const bool want_depth = c.dy != nullptr;
-      int mode = c.mode;
+      const int mode = c.mode;
 
       if (c.first) {
         const int hls = c.hls, hcs = c.hcs;
         const int corg = half ? (wx0 >> 1) : wx0;
 #pragma unroll
-        for (int cc = 0; cc < 4; cc++) {
+        for (int cc = 0; cc < RZ_NL; cc++) {
           const int col = lane + 32 * cc;
           const bool on = col < dw;
           pos_l[cc] = on ? __ldg(c.hl_pos + c.dx0 + col) - wx0 : 0;
@@ -502,246 +631,117 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           for (int jj = 0; jj < T; jj++) cf_c[cc][jj] = (on && jj < hcs) ? (int)__ldg(cf + jj) : 0;
         }
       }
+      // the ring rows this chunk overwrites were last read by the vertical pass of chunk j - 2
+      if (j >= 2) mbar_wait_sleep_a(vdone0 + (j & 1) * 8, (uint32_t)(((j - 2) >> 1) & 1), 128u);
 
-      // ---- text overlay: the chunk's glyph pixels as a bit mask of the window (render_text.cc:94-106: coverage != 0
-      // -> white); the rows apply it in registers after the composite, nothing is written back to the staged rows
-      const bool stamped = c.stamp != 0;
-      if (stamped) mask_pass = mask_chunk(jobs[c.job], s_mask, wx0, yc0, ra, rb, s_hits, s_nhits, mask_pass);
-
-      // ---- per source row: composite -> 14-bit planes (row buffer) -> horizontal pass -> rings ----------
-      {
-        const uint32_t ky0 = c.ky[0], ky1 = c.ky[1], ku0 = c.ku[0], ku1 = c.ku[1], kv0 = c.kv[0], kv1 = c.kv[1];
-        const int rbase_y = c.rbase_y, rbase_c = c.rbase_c;
+      // ---- per source row: composite -> overlay bits -> 14-bit planes (row buffer) -> horizontal pass -> rings ----------
+      const uint32_t ky0 = c.ky[0], ky1 = c.ky[1], ku0 = c.ku[0], ku1 = c.ku[1], kv0 = c.kv[0], kv1 = c.kv[1];
+      const int rbase_y = c.rbase_y, rbase_c = c.rbase_c;
+      const uint32_t *ovl = c.ovl;
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-          const int r = warp + i * RZ_SUB;
-          const int y = yc0 + r;
-          if (i == 1) mbar_wait_hint_a(full0 + q[1] * 8, (uint32_t)par[1], 2000u);
-          if (y >= ra && y < rb) {
-            const uint32_t row = sb[i] + warp * ROWB;
-            const uint32_t drow = sb[i] + dep_off + warp * RZ_DEPB;
-            uint32_t p[4], d4 = 0;
-            if (BPP == 4) {
-              if (mode == RM_SELECT) {
-                select4<ROWB>(row, drow, c.n_src, c.a_mask, lane, p, d4);
-              } else {
-                const uint4 a = lds128(row + lane * 16);
-                p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w;
-                if (dep_staged) d4 = lds32(drow + lane * 4);
-              }
+      for (int i = 0; i < RZ_ROWS_PER_WARP; i++) {
+        const int r = (hgrp + i * RZ_HG) * RZ_SUB + wrow;
+        const int y = yc0 + r;
+        if (i > 0) mbar_wait_hint_a(full0 + q[i] * 8, (uint32_t)par[i], 2000u);
+        if (y >= ra && y < rb) {
+          const uint32_t sb = smem_base + L.stage + (uint32_t)(q[i] * slot_bytes);
+          const uint32_t row = sb + wrow * ROWB;
+          const uint32_t drow = sb + dep_off + wrow * RZ_DEPB;
+          // text overlay (render_text.cc:94-106: coverage != 0 -> white): the 4 bits of this lane's pixels; the word is
+          // in flight while the composite runs
+          uint32_t obits = 0;
+          if (ovl) {
+            const int xx = wx0 + 4 * lane;
+            obits = __ldg(ovl + (size_t)y * c.ovl_pitch + (xx >> 5)) >> (xx & 31);
+          }
+          uint32_t p[4], d4 = 0;
+          if (BPP == 4) {
+            if (mode == RM_SELECT) {
+              select4<ROWB>(row, drow, c.n_src, c.a_mask, lane, p, d4);
             } else {
-              // 4 packed 3-byte pixels = 3 words -> pixel words r | g<<8 | b<<16 | junk<<24 (the junk byte has coefficient 0)
-              const uint32_t w0 = lds32(row + lane * 12), w1 = lds32(row + lane * 12 + 4), w2 = lds32(row + lane * 12 + 8);
-              p[0] = w0;
-              p[1] = __funnelshift_r(w0, w1, 24);
-              p[2] = __funnelshift_r(w1, w2, 16);
-              p[3] = w2 >> 8;
+              const uint4 a = lds128(row + lane * 16);
+              p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w;
               if (dep_staged) d4 = lds32(drow + lane * 4);
             }
-            if (stamped) {
-              const uint32_t m = (s_mask[r * (RZ_BOXW / 32) + (lane >> 3)] >> ((lane & 7) * 4)) & 15u;
-              const uint32_t white = BPP == 4 ? (0x00FFFFFFu << (8 * c.rgb_base)) : 0x00FFFFFFu;
+          } else {
+            // 4 packed 3-byte pixels = 3 words -> pixel words r | g<<8 | b<<16 | junk<<24 (the junk byte has coefficient 0)
+            const uint32_t w0 = lds32(row + lane * 12), w1 = lds32(row + lane * 12 + 4), w2 = lds32(row + lane * 12 + 8);
+            p[0] = w0;
+            p[1] = __funnelshift_r(w0, w1, 24);
+            p[2] = __funnelshift_r(w1, w2, 16);
+            p[3] = w2 >> 8;
+            if (dep_staged) d4 = lds32(drow + lane * 4);
+          }
+          if (ovl) {
+            const uint32_t white = BPP == 4 ? (0x00FFFFFFu << (8 * c.rgb_base)) : 0x00FFFFFFu;
 #pragma unroll
-              for (int k = 0; k < 4; k++)
-                if ((m >> k) & 1u) p[k] |= white;
-              __syncwarp();
-              if (lane < RZ_BOXW / 32) s_mask[r * (RZ_BOXW / 32) + lane] = 0;  // this warp owns the row: leave it clean for the next chunk
-            }
-            const bool need_l = y >= c.lr0 && y < c.lr1, need_c = y >= c.cr0 && y < c.cr1;
-            if (need_l) {
-              int yv[4];
+            for (int k = 0; k < 4; k++)
+              if ((obits >> k) & 1u) p[k] |= white;
+          }
+          const bool need_l = y >= c.lr0 && y < c.lr1, need_c = y >= c.cr0 && y < c.cr1;
+          if (need_l) {
+            int yv[4];
 #pragma unroll
-              for (int k = 0; k < 4; k++) yv[k] = dot_px(ky0, ky1, p[k], (32 << 14) + (1 << 8)) >> 9;
-              sts64(rowbuf + RZ_RB_Y + lane * 8, pack16(yv[0], yv[1]), pack16(yv[2], yv[3]));
-              if (want_depth) sts32(rowbuf + RZ_RB_D + lane * 4, d4);
-            }
-            if (need_c) {
-              if (half) {
-                int u[2], v[2];
+            for (int k = 0; k < 4; k++) yv[k] = dot_px(ky0, ky1, p[k], (32 << 14) + (1 << 8)) >> 9;
+            sts64(rowbuf + RZ_RB_Y + lane * 8, pack16(yv[0], yv[1]), pack16(yv[2], yv[3]));
+            if (want_depth) sts32(rowbuf + RZ_RB_D + lane * 4, d4);
+          }
+          if (need_c) {
+            if (half) {
+              int u[2], v[2];
 #pragma unroll
-                for (int k = 0; k < 2; k++) {
-                  u[k] = dot_px(ku0, ku1, p[2 * k + 1], dot_px(ku0, ku1, p[2 * k], C_BIAS)) >> 10;
-                  v[k] = dot_px(kv0, kv1, p[2 * k + 1], dot_px(kv0, kv1, p[2 * k], C_BIAS)) >> 10;
-                }
-                sts32(rowbuf + RZ_RB_U + lane * 4, pack16(u[0], u[1]));
-                sts32(rowbuf + RZ_RB_V + lane * 4, pack16(v[0], v[1]));
-              } else {
-                int u[4], v[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                  u[k] = dot_px(ku0, ku1, p[k], C1_BIAS) >> 9;
-                  v[k] = dot_px(kv0, kv1, p[k], C1_BIAS) >> 9;
-                }
-                sts64(rowbuf + RZ_RB_U + lane * 8, pack16(u[0], u[1]), pack16(u[2], u[3]));
-                sts64(rowbuf + RZ_RB_V + lane * 8, pack16(v[0], v[1]), pack16(v[2], v[3]));
+              for (int k = 0; k < 2; k++) {
+                u[k] = dot_px(ku0, ku1, p[2 * k + 1], dot_px(ku0, ku1, p[2 * k], C_BIAS)) >> 10;
+                v[k] = dot_px(kv0, kv1, p[2 * k + 1], dot_px(kv0, kv1, p[2 * k], C_BIAS)) >> 10;
               }
-            }
-            __syncwarp();
-            int slot = rbase_y + r, slot_c = rbase_c + r;
-            if (slot >= nry) slot -= nry;
-            if (slot_c >= nrc) slot_c -= nrc;
-            // ---- horizontal pass of this row: hScale16To15 (>>13, clamp) / hScale8To15 (>>7) + range compression.
-            // The slots of a plane (32 destination columns each) and the luma / depth pair run as independent
-            // accumulation chains inside one tap loop (the chains hide each other's multiply latency).
-            if (need_l) {
-              const uint32_t oy = ringY + slot * rowbY + lane * 4, od = ringD + slot * rowbY + lane * 4;
-              const int nl = (dw + 31) >> 5;  // warp-uniform
-              if (nl == 1) h_luma<1, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
-              else if (nl == 2) h_luma<2, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
-              else if (nl == 3) h_luma<3, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
-              else h_luma<4, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
-            }
-            if (need_c) {
-              const uint32_t ou = ringU + slot_c * rowbC + lane * 4, ov = ringV + slot_c * rowbC + lane * 4;
-              if (dcw <= 32) h_chroma<1, T>(rowbuf, pos_c, cf_c, dcw, lane, ou, ov);
-              else h_chroma<2, T>(rowbuf, pos_c, cf_c, dcw, lane, ou, ov);
+              sts32(rowbuf + RZ_RB_U + lane * 4, pack16(u[0], u[1]));
+              sts32(rowbuf + RZ_RB_V + lane * 4, pack16(v[0], v[1]));
+            } else {
+              int u[4], v[4];
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                u[k] = dot_px(ku0, ku1, p[k], C1_BIAS) >> 9;
+                v[k] = dot_px(kv0, kv1, p[k], C1_BIAS) >> 9;
+              }
+              sts64(rowbuf + RZ_RB_U + lane * 8, pack16(u[0], u[1]), pack16(u[2], u[3]));
+              sts64(rowbuf + RZ_RB_V + lane * 8, pack16(v[0], v[1]), pack16(v[2], v[3]));
             }
           }
-          __syncwarp();  // the row buffer is rewritten by this warp's next row
-          if (lane == 0) mbar_arrive_a(empty0 + q[i] * 8);
-        }
-      }
-      consumer_sync();
-
-      // ---- vertical pass: every destination row whose taps are all in the rings ---------------------
-      {
-        const int rbase_y = c.rbase_y, rbase_c = c.rbase_c;
-        // (the launch only takes jobs with 16-byte aligned destination planes: whole groups go out as words)
-        // luma (+ depth luma, same filter)
-        {
-          const int ya = c.ya, yb = c.yb, vls = c.vls;
-          const int gl = (dw + 3) >> 2;
-          const int total = (yb - ya) * gl;
-          const uint32_t rcp = (65536u + gl - 1) / gl;
-          uint8_t *const sy = c.sy + c.dx0, *const dyp = want_depth ? c.dy + c.dx0 : nullptr;
-          for (int idx = tid; idx < total; idx += 32 * NW) {
-            const int ry = (int)(((uint32_t)idx * rcp) >> 16), g = idx - ry * gl;
-            const int dyy = ya + ry;
-            const int pos = __ldg(c.vl_pos + dyy);
-            int slot = rbase_y + pos - yc0;
-            if (slot < 0) slot += nry;
-            if (slot >= nry) slot -= nry;
-            int a[4], d[4];
-            if (vls == 1) {
-              const int4 w = lds_v4s(ringY + slot * rowbY + g * 16);
-              a[0] = (w.x + 64) >> 7; a[1] = (w.y + 64) >> 7; a[2] = (w.z + 64) >> 7; a[3] = (w.w + 64) >> 7;
-              if (want_depth) {
-                const int4 e = lds_v4s(ringD + slot * rowbY + g * 16);
-                d[0] = (e.x + 64) >> 7; d[1] = (e.y + 64) >> 7; d[2] = (e.z + 64) >> 7; d[3] = (e.w + 64) >> 7;
-              }
-            } else {
-              const int16_t *cf = c.vl_coef + (size_t)dyy * vls;
-              a[0] = a[1] = a[2] = a[3] = 64 << 12;
-              d[0] = d[1] = d[2] = d[3] = 64 << 12;
-              int kn = (int)__ldg(cf);
-              for (int jj = 0; jj < vls; jj++) {
-                const int k = kn;
-                if (jj + 1 < vls) kn = (int)__ldg(cf + jj + 1);  // the next tap's coefficient is in flight while this tap is applied
-                const int4 w = lds_v4s(ringY + slot * rowbY + g * 16);
-                a[0] += w.x * k; a[1] += w.y * k; a[2] += w.z * k; a[3] += w.w * k;
-                if (want_depth) {
-                  const int4 e = lds_v4s(ringD + slot * rowbY + g * 16);
-                  d[0] += e.x * k; d[1] += e.y * k; d[2] += e.z * k; d[3] += e.w * k;
-                }
-                if (++slot == nry) slot = 0;
-              }
-#pragma unroll
-              for (int k = 0; k < 4; k++) { a[k] >>= 19; d[k] >>= 19; }
-            }
-            const uint32_t yw = clip8_relu(a[0]) | (clip8_relu(a[1]) << 8) | (clip8_relu(a[2]) << 16) | (clip8_relu(a[3]) << 24);
-            uint8_t *o = sy + (size_t)dyy * c.sys + 4 * g;
-            if (4 * g + 4 <= dw) stg32(o, yw);
-            else
-              for (int k = 0; 4 * g + k < dw; k++) o[k] = (uint8_t)(yw >> (8 * k));
-            if (want_depth) {
-              const uint32_t gw = clip8_relu(d[0]) | (clip8_relu(d[1]) << 8) | (clip8_relu(d[2]) << 16) | (clip8_relu(d[3]) << 24);
-              uint8_t *od = dyp + (size_t)dyy * c.dys + 4 * g;
-              if (4 * g + 4 <= dw) stg32(od, gw);
-              else
-                for (int k = 0; 4 * g + k < dw; k++) od[k] = (uint8_t)(gw >> (8 * k));
-            }
+          __syncwarp();
+          int slot = rbase_y + r, slot_c = rbase_c + r;
+          if (slot >= nry) slot -= nry;
+          if (slot_c >= nrc) slot_c -= nrc;
+          // ---- horizontal pass of this row: hScale16To15 (>>13, clamp) / hScale8To15 (>>7) + range compression.
+          // The slots of a plane (32 destination columns each) and the luma / depth pair run as independent
+          // accumulation chains inside one tap loop (the chains hide each other's multiply latency).
+          if (need_l) {
+            const uint32_t oy = ringY + slot * rowbY + lane * 4, od = ringD + slot * rowbY + lane * 4;
+            const int nl = (dw + 31) >> 5;  // warp-uniform
+            if (nl == 1) h_luma<1, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
+            else if (nl == 2) h_luma<2, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
+            else h_luma<3, T>(rowbuf, pos_l, cf_l, want_depth, dw, lane, oy, od);
+          }
+          if (need_c) {
+            const uint32_t ou = ringU + slot_c * rowbC + lane * 4, ov = ringV + slot_c * rowbC + lane * 4;
+            if (dcw <= 32) h_chroma<1, T>(rowbuf, pos_c, cf_c, dcw, lane, ou, ov);
+            else h_chroma<2, T>(rowbuf, pos_c, cf_c, dcw, lane, ou, ov);
           }
         }
-        // chroma (U and V share the filter); depth chroma is constant 128
-        {
-          const int ca = c.ca, cb = c.cb, vcs = c.vcs;
-          const int gc = (dcw + 3) >> 2;
-          const int total = (cb - ca) * gc;
-          const uint32_t rcp = (65536u + gc - 1) / gc;
-          const bool nv12 = c.nv12 != 0;
-          // (the luma items went to the low threads: the chroma items are dealt from the other end, so that the warps
-          // the luma pass left idle take them)
-          for (int idx = 32 * NW - 1 - tid; idx < total; idx += 32 * NW) {
-            const int ry = (int)(((uint32_t)idx * rcp) >> 16), g = idx - ry * gc;
-            const int cyy = ca + ry;
-            const int pos = __ldg(c.vc_pos + cyy);
-            int slot = rbase_c + pos - yc0;
-            if (slot < 0) slot += nrc;
-            if (slot >= nrc) slot -= nrc;
-            int u[4], v[4];
-            if (vcs == 1) {
-              const int4 w = lds_v4s(ringU + slot * rowbC + g * 16), e = lds_v4s(ringV + slot * rowbC + g * 16);
-              u[0] = (w.x + 64) >> 7; u[1] = (w.y + 64) >> 7; u[2] = (w.z + 64) >> 7; u[3] = (w.w + 64) >> 7;
-              v[0] = (e.x + 64) >> 7; v[1] = (e.y + 64) >> 7; v[2] = (e.z + 64) >> 7; v[3] = (e.w + 64) >> 7;
-            } else {
-              const int16_t *cf = c.vc_coef + (size_t)cyy * vcs;
-              u[0] = u[1] = u[2] = u[3] = 64 << 12;
-              v[0] = v[1] = v[2] = v[3] = 64 << 12;
-              int kn = (int)__ldg(cf);
-              for (int jj = 0; jj < vcs; jj++) {
-                const int k = kn;
-                if (jj + 1 < vcs) kn = (int)__ldg(cf + jj + 1);
-                const int4 w = lds_v4s(ringU + slot * rowbC + g * 16), e = lds_v4s(ringV + slot * rowbC + g * 16);
-                u[0] += w.x * k; u[1] += w.y * k; u[2] += w.z * k; u[3] += w.w * k;
-                v[0] += e.x * k; v[1] += e.y * k; v[2] += e.z * k; v[3] += e.w * k;
-                if (++slot == nrc) slot = 0;
-              }
-#pragma unroll
-              for (int k = 0; k < 4; k++) { u[k] >>= 19; v[k] >>= 19; }
-            }
-            const uint32_t ub = clip8_relu(u[0]) | (clip8_relu(u[1]) << 8) | (clip8_relu(u[2]) << 16) | (clip8_relu(u[3]) << 24);
-            const uint32_t vb = clip8_relu(v[0]) | (clip8_relu(v[1]) << 8) | (clip8_relu(v[2]) << 16) | (clip8_relu(v[3]) << 24);
-            const bool full = 4 * g + 4 <= dcw;
-            if (nv12) {
-              // U0 V0 U1 V1 | U2 V2 U3 V3: chroma column x sits at byte 2x of the UV row
-              const uint32_t w0 = __byte_perm(ub, vb, 0x5140), w1 = __byte_perm(ub, vb, 0x7362);
-              uint8_t *o = c.su + (size_t)cyy * c.sus + 2 * c.cx0 + 8 * g;
-              if (full) stg64(o, w0, w1);
-              else
-                for (int k = 0; 4 * g + (k >> 1) < dcw; k++) o[k] = (uint8_t)((k < 4 ? w0 : w1) >> (8 * (k & 3)));
-              if (want_depth) {
-                uint8_t *od = c.du + (size_t)cyy * c.dus + 2 * c.cx0 + 8 * g;
-                if (full) stg64(od, 0x80808080u, 0x80808080u);
-                else
-                  for (int k = 0; 4 * g + (k >> 1) < dcw; k++) od[k] = 128;
-              }
-            } else {
-              uint8_t *ou = c.su + (size_t)cyy * c.sus + c.cx0 + 4 * g, *ov = c.sv + (size_t)cyy * c.svs + c.cx0 + 4 * g;
-              if (full) { stg32(ou, ub); stg32(ov, vb); }
-              else
-                for (int k = 0; 4 * g + k < dcw; k++) { ou[k] = (uint8_t)(ub >> (8 * k)); ov[k] = (uint8_t)(vb >> (8 * k)); }
-              if (want_depth) {
-                uint8_t *du_ = c.du + (size_t)cyy * c.dus + c.cx0 + 4 * g, *dv_ = c.dv + (size_t)cyy * c.dvs + c.cx0 + 4 * g;
-                if (full) { stg32(du_, 0x80808080u); stg32(dv_, 0x80808080u); }
-                else
-                  for (int k = 0; 4 * g + k < dcw; k++) { du_[k] = 128; dv_[k] = 128; }
-              }
-            }
-          }
-        }
+        __syncwarp();  // the row buffer is rewritten by this warp's next row; every lane is done with the sub-stage
+        if (lane == 0) mbar_arrive_a(empty0 + q[i] * 8);
       }
     }
+    if (lane == 0) mbar_arrive_a(hdone0 + (j & 1) * 8);  // (after the __syncwarp above: this warp's ring rows of chunk j are written)
     if (last) break;
-    if (unit_end) consumer_sync();  // the next unit's first rows reuse ring slots this vertical pass was reading
-    qc = q[1] + 1; parc = par[1];
-    if (qc == ns) { qc = 0; parc ^= 1; }
+    qc += RZ_SUBS;
+    while (qc >= ns) { qc -= ns; parc ^= 1; }
   }
 }
 
 // ---------------------------------------------------------------------------
 // host side: planning and launch
 // ---------------------------------------------------------------------------
-static int g_rz_sms = 0, g_rz_smem_sm = 0, g_rz_reserved = 1024, g_rz_optin = 0;
+static int g_rz_sms = 0, g_rz_optin = 0;
 static bool g_rz_pdl = true;
 
 template <int BPP, int T>
@@ -754,9 +754,6 @@ int resize_strips_init() {
   cudaGetDevice(&dev);
   cudaError_t e = cudaDeviceGetAttribute(&g_rz_sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return (int)e;
-  e = cudaDeviceGetAttribute(&g_rz_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-  if (e != cudaSuccess) return (int)e;
-  cudaDeviceGetAttribute(&g_rz_reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev);
   e = cudaDeviceGetAttribute(&g_rz_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (e != cudaSuccess) return (int)e;
   if ((e = rz_set_attr<3, 4>()) != cudaSuccess || (e = rz_set_attr<3, 6>()) != cudaSuccess || (e = rz_set_attr<3, 8>()) != cudaSuccess ||
@@ -767,11 +764,10 @@ int resize_strips_init() {
 }
 
 struct RzConfig {
-  int ns, slot, smem, ctas, dwp, taps, nry, nrc;
+  int ns, slot, smem, dwp, taps, nry, nrc;
 };
 // Launch shape of one pixel class: rings sized for the widest destination strip and the longest vertical filters of
-// the launch, sub-stage slots for the most sources; two CTAs per SM when two sub-stages (one chunk) fit half an SM,
-// else one CTA with a deeper ring.
+// the launch, sub-stage slots for the most sources; one CTA per SM, the rest of its shared memory is the sub-stage ring.
 static RzConfig rz_config(const DevJob *jobs, int n_jobs, int bpp) {
   int dwp = 16, staged = 1, taps = 1, vl = 1, vc = 1;
   for (int j = 0; j < n_jobs; j++) {
@@ -786,19 +782,17 @@ static RzConfig rz_config(const DevJob *jobs, int n_jobs, int bpp) {
   const int nry = rz_ring_rows(vl), nrc = rz_ring_rows(vc);
   const RzSmem L = rz_smem(dwp, nry, nrc);
   const int slot = staged * RZ_SUB * (RZ_BOXW * bpp + RZ_DEPB);
-  const int smem_sm = g_rz_smem_sm > 0 ? g_rz_smem_sm : 233472;
-  RzConfig c{0, slot, 0, 0, dwp, taps <= 4 ? 4 : taps <= 6 ? 6 : 8, nry, nrc};
-  for (int ctas = 2; ctas >= 1; ctas--) {
-    const int budget = std::min(smem_sm / ctas - g_rz_reserved, g_rz_optin > 0 ? g_rz_optin : 232448) - L.stage;
-    const int ns = std::min(RZ_NS_MAX, budget / slot);
-    if (ns >= 2) { c.ns = ns; c.ctas = ctas; c.smem = L.stage + ns * slot; break; }
-  }
+  RzConfig c{0, slot, 0, dwp, taps <= 4 ? 4 : taps <= 6 ? 6 : 8, nry, nrc};
+  const int budget = (g_rz_optin > 0 ? g_rz_optin : 232448) - L.stage;
+  const int ns = std::min(RZ_NS_MAX, budget / slot);
+  if (ns >= 2) { c.ns = ns; c.smem = L.stage + ns * slot; }
   return c;
 }
 
 // One segment height (destination rows) per pixel class: the vertical halo (about the longest vertical filter, in
 // source rows, per segment) against the one-unit tail of the persistent grid.  Unit numbering: a prefix sum over the
-// launch in which the jobs of the other class (and the jobs k_resize_tiles keeps) take no units.
+// launch in which the jobs of the other class (and the jobs k_resize_tiles keeps) take no units.  Also lays the
+// overlay bitmaps of the jobs that carry text out in the launch's scratch.
 void plan_resize_strips(DevJob *jobs, int n_jobs) {
   const int sms = g_rz_sms > 0 ? g_rz_sms : 148;
   for (int cls = 0; cls < 2; cls++) {
@@ -807,8 +801,7 @@ void plan_resize_strips(DevJob *jobs, int n_jobs) {
     for (int j = 0; j < n_jobs; j++) any = any || (jobs[j].rz_ok && jobs[j].bpp == bpp);
     int best_s = 32;
     if (any) {
-      const RzConfig cfg = rz_config(jobs, n_jobs, bpp);
-      const int grid = sms * std::max(cfg.ctas, 1);
+      const int grid = sms;
       double best_cost = 1e30;
       for (int S = 16; S <= 512; S *= 2) {
         double work = 0, unit_max = 0;
@@ -818,7 +811,7 @@ void plan_resize_strips(DevJob *jobs, int n_jobs) {
           if (!jb.rz_ok || jb.bpp != bpp) continue;
           const int strips = (jb.Wd + jb.rz_dw - 1) / jb.rz_dw, segs = (jb.Hd + S - 1) / S;
           const double ratio = (double)jb.H / jb.Hd;
-          const double halo = std::max(jb.vl.size, jb.vc.size);
+          const double halo = std::max(jb.vl.size, jb.vc.size) + RZ_CH / 2;  // + the ragged last chunk
           units += (long)strips * segs;
           work += (double)strips * (jb.H + segs * halo);
           unit_max = std::max(unit_max, S * ratio + halo);
@@ -839,25 +832,77 @@ void plan_resize_strips(DevJob *jobs, int n_jobs) {
       base += jb.rz_units;
     }
   }
+  int64_t off = 0;
+  for (int j = 0; j < n_jobs; j++) {
+    DevJob &jb = jobs[j];
+    jb.rz_ovl_off = -1;
+    jb.rz_ovl_pitch = 0;
+    if (!jb.rz_ok || jb.n_glyphs <= 0) continue;
+    // a window reads up to RZ_BOXW - 1 columns past the frame's last one: the pitch covers them (they stay 0)
+    jb.rz_ovl_pitch = ((jb.W + RZ_BOXW + 31) >> 5) + 1;
+    jb.rz_ovl_off = off;
+    off += (int64_t)jb.rz_ovl_pitch * jb.H;
+    off = (off + 31) & ~(int64_t)31;
+  }
+}
+
+static size_t rz_overlay_bytes(const DevJob *jobs, int n_jobs) {
+  size_t words = 0;
+  for (int j = 0; j < n_jobs; j++)
+    if (jobs[j].rz_ok && jobs[j].rz_ovl_off >= 0) words = std::max(words, (size_t)jobs[j].rz_ovl_off + (size_t)jobs[j].rz_ovl_pitch * jobs[j].H);
+  return words * 4;
+}
+
+void resize_strips_free_scratch(RzScratch *scratch) {
+  if (scratch && scratch->ovl) cudaFree(scratch->ovl);
+  if (scratch) { scratch->ovl = nullptr; scratch->cap = 0; }
 }
 
 template <int BPP, int T>
-static cudaError_t rz_launch_one(int grid, const RzConfig &c, cudaStream_t st, const DevJob *jobs, int n_jobs, int total, uint32_t *ctr) {
+static cudaError_t rz_launch_one(int grid, const RzConfig &c, cudaStream_t st, const DevJob *jobs, int n_jobs, int total, uint32_t *ctr, const uint32_t *ovl, bool pdl) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(CTA_THREADS);
+  cfg.blockDim = dim3(RZ_THREADS);
   cfg.dynamicSmemBytes = (size_t)c.smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = g_rz_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k_resize_strips<BPP, T>, jobs, n_jobs, total, ctr, c.ns, c.slot, c.dwp, c.nry, c.nrc);
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_resize_strips<BPP, T>, jobs, n_jobs, total, ctr, ovl, c.ns, c.slot, c.dwp, c.nry, c.nrc);
 }
 
-int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream) {
+int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream, RzScratch *scratch) {
   int launches = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int total_all = 0;
+  for (int j = 0; j < n_jobs; j++)
+    if (jobs_host[j].rz_ok) total_all += jobs_host[j].rz_units;
+  if (total_all == 0) return 0;
+  // text: the frames' overlay bitmaps are rebuilt ahead of the resize kernel (ordinary stream order: the kernel that
+  // reads them is then launched without the programmatic-overlap attribute)
+  const size_t ovl_bytes = rz_overlay_bytes(jobs_host, n_jobs);
+  const uint32_t *ovl = nullptr;
+  if (ovl_bytes > 0) {
+    if (!scratch) return -1;
+    if (scratch->cap < ovl_bytes) {
+      if (scratch->ovl) cudaFree(scratch->ovl);  // (synchronises: nothing in flight still reads it)
+      scratch->ovl = nullptr; scratch->cap = 0;
+      const size_t want = (ovl_bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+      if (cudaMalloc((void **)&scratch->ovl, want) != cudaSuccess) { cudaGetLastError(); scratch->ovl = nullptr; return -1; }
+      scratch->cap = want;
+    }
+    if (cudaMemsetAsync(scratch->ovl, 0, ovl_bytes, st) != cudaSuccess) return -1;
+    int max_gl = 0;
+    for (int j = 0; j < n_jobs; j++)
+      if (jobs_host[j].rz_ok && jobs_host[j].rz_ovl_off >= 0) max_gl = std::max(max_gl, jobs_host[j].n_glyphs);
+    const dim3 grid((unsigned)std::min(std::max((max_gl + 7) / 8, 1), 4096), (unsigned)std::min(n_jobs, 1024));  // one glyph per warp
+    k_overlay_bits<<<grid, 256, 0, st>>>(jobs_dev, n_jobs, scratch->ovl);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    launches++;
+    ovl = scratch->ovl;
+  }
   for (int bpp = 3; bpp <= 4; bpp++) {
     int total = 0;
     for (int j = 0; j < n_jobs; j++)
@@ -865,12 +910,12 @@ int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_
     if (total == 0) continue;
     const RzConfig c = rz_config(jobs_host, n_jobs, bpp);
     if (c.ns < 2) return -1;
-    const int grid = std::min(total, g_rz_sms * c.ctas);
+    const int grid = std::min(total, g_rz_sms);
     uint32_t *ctr = counters + 2 * ((*seq)++ % COUNTER_SLOTS);
-    cudaStream_t st = (cudaStream_t)stream;
+    const bool pdl = g_rz_pdl && ovl == nullptr;
     cudaError_t e;
-    if (bpp == 3) e = c.taps == 4 ? rz_launch_one<3, 4>(grid, c, st, jobs_dev, n_jobs, total, ctr) : c.taps == 6 ? rz_launch_one<3, 6>(grid, c, st, jobs_dev, n_jobs, total, ctr) : rz_launch_one<3, 8>(grid, c, st, jobs_dev, n_jobs, total, ctr);
-    else e = c.taps == 4 ? rz_launch_one<4, 4>(grid, c, st, jobs_dev, n_jobs, total, ctr) : c.taps == 6 ? rz_launch_one<4, 6>(grid, c, st, jobs_dev, n_jobs, total, ctr) : rz_launch_one<4, 8>(grid, c, st, jobs_dev, n_jobs, total, ctr);
+    if (bpp == 3) e = c.taps == 4 ? rz_launch_one<3, 4>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl) : c.taps == 6 ? rz_launch_one<3, 6>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl) : rz_launch_one<3, 8>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl);
+    else e = c.taps == 4 ? rz_launch_one<4, 4>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl) : c.taps == 6 ? rz_launch_one<4, 6>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl) : rz_launch_one<4, 8>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl);
     if (e != cudaSuccess) return -1;
     launches++;
   }
