@@ -186,10 +186,6 @@ struct alignas(64) DevJob {
   int32_t rz_dw;                         // destination columns per strip (multiple of 16, <= RZ_MAX_DW; 0: the size pair does not fit)
   int32_t rz_strips_x, rz_seg_rows, rz_segs_y;
   int32_t rz_unit_base[2], rz_units;     // [bpp-3]: units of the rz jobs of that pixel class ahead of this job in the launch
-  // overlay bitmap of the frame (k_overlay_bits, resize_strips.cu): one bit per source pixel, rz_ovl_pitch words per row, at word
-  // rz_ovl_off of the launch's overlay scratch (< 0: the job has no text)
-  int64_t rz_ovl_off;
-  int32_t rz_ovl_pitch;
 };
 
 // Parameter block of a single-frame launch of k_frame_strips (k_frame_strips_1): descriptor + placed glyphs by value.
@@ -214,14 +210,7 @@ constexpr int COUNTER_SLOTS = 64;  // work counters of k_frame_strips: one self 
 int launch_resize_tiles(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, void *stream);
 // Assigns rz_seg_rows / rz_unit_base of the jobs k_resize_strips takes (host), then the launch itself.
 void plan_resize_strips(DevJob *jobs_host, int n_jobs);
-// scratch: the caller's (session's / mux's) overlay bitmap storage, grown on demand; a launch whose jobs carry text
-// clears it and rebuilds the bitmaps (k_overlay_bits) ahead of the resize kernel, on the same stream
-struct RzScratch {
-  uint32_t *ovl = nullptr;
-  size_t cap = 0;  // bytes
-};
-int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream, RzScratch *scratch);
-void resize_strips_free_scratch(RzScratch *scratch);
+int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream);
 int resize_strips_init();
 // GRAY16LE depth images of the jobs that carry one (depth16.cu); returns launches or -1
 int launch_depth16(const DevJob *jobs_host, int n_jobs, void *stream);

@@ -17,19 +17,21 @@
 //     SUB-STAGES filled by the PRODUCER warp with 2D tensor-map TMA copies (packed pixels and GRAY8 depth of every
 //     staged source; SASS UTMALDG), exactly like k_frame_strips;
 //   * 16 HORIZONTAL warps: a warp owns one source row of a sub-stage END TO END: composite select among the staged
-//     sources in registers -> overlay bits (one word of the frame's overlay bitmap) -> 14-bit Y / U / V and depth bytes
+//     sources in registers -> overlay bits (one shared-memory word) -> 14-bit Y / U / V and depth bytes
 //     into a 1 KB per-warp row buffer -> horizontal pass of that row (lane = destination column, its taps live in
 //     registers for the whole unit) -> 15-bit samples into four rings (Y, depth, U, V); the sub-stage is released at once;
 //   * 6 VERTICAL warps run one chunk behind: every destination row whose taps are all in the rings (4 adjacent columns
 //     per thread, 16-byte ring loads, 4-byte stores).  The vertical halo is paid once per segment, nothing is staged twice;
 //   * the roles meet only at mbarriers (sub-stage full / empty, chunk horizontally done, chunk vertically done): there is
 //     no CTA-wide barrier anywhere in the loop;
-//   * the text overlay is ONE BIT PER SOURCE PIXEL in a per-frame bitmap that a small kernel ahead of this one
-//     (k_overlay_bits, same stream) builds from the placed glyphs and the 1-bit atlas.
+//   * the text overlay of a unit is ONE BIT PER PIXEL of its source window, built in shared memory by the horizontal
+//     warps when the unit starts (one thread tests a placed glyph, the hits are staged as descriptors, a lane ORs one
+//     word of one glyph row of the 1-bit atlas); the rows apply it in registers after the composite.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -47,6 +49,7 @@ constexpr int RZ_ROWBUF = 1024;        // per-warp row buffer: y14 | u14 | v14 (
 constexpr int RZ_RB_Y = 0, RZ_RB_U = 288, RZ_RB_V = 576, RZ_RB_D = 864;
 constexpr int RZ_NS_MAX = 8;
 constexpr int RZ_NCTX = 8;             // chunk contexts in flight: the producer runs <= 2 chunks ahead of the horizontal warps, the vertical warps <= 2 behind
+constexpr int RZ_HITS = 96;            // glyph descriptors staged per pass of a unit's overlay build
 constexpr int RZ_NL = RZ_MAX_DW / 32;  // 32-column slots of a destination strip
 constexpr int RZ_SUBS = RZ_CH / RZ_SUB;
 constexpr int RZ_HG = RZ_H_WARPS / RZ_SUB;  // groups of horizontal warps (group g takes sub-stages g, g + RZ_HG, ... of a chunk)
@@ -57,7 +60,9 @@ constexpr int RZ_ROWS_PER_WARP = RZ_SUBS / RZ_HG;
 struct RzCtx {
   int32_t last;       // last chunk this CTA processes
   int32_t first;      // first chunk of a unit: (re)load the horizontal filter registers
-  int32_t mode, n_src, n_staged;
+  int32_t mode, n_src, n_staged, job;
+  int32_t unit_text;  // (first chunk) some placed glyph may touch the unit's window: build its overlay bits
+  int32_t stamp;      // the overlay bits of this chunk's rows are not all zero
   int32_t wx0;        // source column of window column 0 (4-byte pixels: multiple of 4; 3-byte pixels: of 16 -- TMA box rows start on 16-byte boundaries)
   int32_t dshift;     // window column 0 inside the staged depth rows (their box starts at wx0 & ~15)
   int32_t yc0, ra, rb;          // source row of chunk-local row 0; rows of this chunk that are needed [ra, rb)
@@ -67,10 +72,8 @@ struct RzCtx {
   int32_t dx0, dw, cx0, dcw;    // destination strip: luma / chroma columns
   int32_t half, dep_staged, nv12, rgb_base;
   int32_t hls, hcs, vls, vcs;   // filter sizes
-  int32_t ovl_pitch;            // words per row of the overlay bitmap
   uint32_t a_mask;
   uint32_t ky[2], ku[2], kv[2];
-  const uint32_t *ovl;          // overlay bitmap of the frame, or null: no glyph touches this chunk
   const int16_t *hl_coef, *hc_coef, *vl_coef, *vc_coef;
   const int32_t *hl_pos, *hc_pos, *vl_pos, *vc_pos;
   int32_t sys, sus, svs, dys, dus, dvs;
@@ -78,14 +81,15 @@ struct RzCtx {
 };
 
 struct RzSmem {
-  int ringY, ringD, ringU, ringV, rowbuf, ctx, bar, stage;
+  int ringY, ringD, ringU, ringV, rowbuf, ctx, bar, hits, ovl, stage;
 };
 constexpr int RZ_CTX_BYTES = ((int)sizeof(RzCtx) + 15) & ~15;
 // nry / nrc: rows of the luma (+ depth) and chroma rings.  The vertical pass of chunk j reads back to RZ_CH + (filter
 // size) - 1 rows before the end of chunk j while the horizontal warps may already be writing chunk j + 1 (they wait for
 // the vertical pass of chunk j - 1 before that): 2 * RZ_CH - 1 + (filter size) rows.
 __host__ __device__ inline int rz_ring_rows(int vsize) { return (2 * RZ_CH - 1 + vsize + 7) & ~7; }
-__host__ __device__ inline RzSmem rz_smem(int dwp, int nry, int nrc) {
+// ovl_rows: source rows of the tallest unit of the launch that carries text (0: none does)
+__host__ __device__ inline RzSmem rz_smem(int dwp, int nry, int nrc, int ovl_rows) {
   RzSmem L;
   int o = 0;
   L.ringY = o; o += nry * dwp * 4;
@@ -95,6 +99,8 @@ __host__ __device__ inline RzSmem rz_smem(int dwp, int nry, int nrc) {
   L.rowbuf = o; o += RZ_H_WARPS * RZ_ROWBUF;
   L.ctx = o; o += RZ_NCTX * RZ_CTX_BYTES;
   L.bar = o; o += (2 * RZ_NS_MAX + 4) * 8;  // full[], empty[], hdone[2], vdone[2]
+  L.hits = o; o += ovl_rows > 0 ? RZ_HITS * (int)sizeof(DevPlaced) + 16 : 0;
+  L.ovl = o; o += ovl_rows * (RZ_BOXW / 8);  // one bit per pixel of the unit's source window
   L.stage = (o + 1023) & ~1023;
   return L;
 }
@@ -226,62 +232,90 @@ __device__ __forceinline__ void h_chroma(uint32_t rowbuf, const int (&pos_c)[2],
   }
 }
 
-}  // namespace
+// barrier among the horizontal warps only
+__device__ __forceinline__ void h_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * RZ_H_WARPS) : "memory"); }
 
-// Overlay bitmaps of the jobs of a launch: bit (x & 31) of word rz_ovl_off + y * rz_ovl_pitch + (x >> 5) of the
-// scratch is set when a glyph pixel with coverage != 0 covers source pixel (x, y) (render_text.cc:94-106: such a
-// pixel becomes white).  The launcher clears the storage; a warp takes a placed glyph, a lane one mask word of one
-// of its rows (the atlas holds one bit per glyph pixel) and ORs it in, shifted to the frame's column grid.
-__global__ void __launch_bounds__(256) k_overlay_bits(const DevJob *__restrict__ jobs, int n_jobs, uint32_t *__restrict__ ovl_base) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = blockIdx.y; j < n_jobs; j += gridDim.y) {
-    const DevJob &jb = jobs[j];
-    if (!jb.rz_ok || jb.rz_ovl_off < 0 || jb.n_glyphs <= 0) continue;
-    uint32_t *bits = ovl_base + jb.rz_ovl_off;
-    const int pitch = jb.rz_ovl_pitch, W = jb.W, H = jb.H;
-    const DevPlaced *__restrict__ glyphs = jb.glyphs;
-    const uint32_t *__restrict__ atlas = jb.atlas;
-    for (int g = blockIdx.x * 8 + warp; g < jb.n_glyphs; g += gridDim.x * 8) {
-      const DevPlaced pg = glyphs[g];
-      const int q0 = max(0, -pg.y), q1 = min(pg.h, H - pg.y);
-      const int p0 = max(0, -pg.x), p1 = min(pg.w, W - pg.x);
-      if (q1 <= q0 || p1 <= p0) continue;
-      const int bit_lo = pg.bit0 + p0, bit_hi = pg.bit0 + p1;
-      const int w_lo = bit_lo >> 5, w_hi = (bit_hi - 1) >> 5, nw = w_hi - w_lo + 1;
-      for (int i = lane; i < (q1 - q0) * nw; i += 32) {
-        const int qq = i / nw, wi = w_lo + (i - qq * nw), q = q0 + qq;
-        uint32_t m = __ldg(atlas + pg.mask_off + (uint32_t)(q * pg.wpr + wi));
-        const int lo = max(bit_lo - 32 * wi, 0), hi = min(bit_hi - 32 * wi, 32);
-        m &= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (32 - hi));
-        if (m == 0) continue;
-        const int xb = pg.x - pg.bit0 + 32 * wi;  // frame column of bit 0 of this word (negative only for masked-off bits)
-        const int wd = xb >> 5, sh = xb & 31;
-        uint32_t *row = bits + (size_t)(pg.y + q) * pitch;
-        const uint32_t lo_part = m << sh;
-        if (lo_part && wd >= 0) atomicOr(&row[wd], lo_part);
-        if (sh) {
-          const uint32_t hi_part = m >> (32 - sh);
-          if (hi_part) atomicOr(&row[wd + 1], hi_part);
-        }
+// Overlay bits of one unit's source window (all horizontal warps; called when the unit starts): s_ovl[r1 - r0][RZ_BOXW / 32],
+// window column x of source row y is bit x & 31 of word (y - r0) * 4 + (x >> 5).  The glyph list is bucketed by row band on
+// the host; one thread tests one glyph, the hits are staged as whole descriptors, then a warp takes a glyph and a lane one
+// word of one of its rows (the atlas holds one bit per glyph pixel) and ORs it in, shifted to the window's column grid.
+// (render_text.cc:94-106: a bitmap pixel with coverage != 0 turns the frame pixel white.)
+__device__ __forceinline__ void unit_overlay(const DevJob &jb, uint32_t *s_ovl, int x0, int r0, int r1, DevPlaced *s_hits, int *s_nhits) {
+  constexpr int NT = 32 * RZ_H_WARPS;
+  constexpr int MW = RZ_BOXW / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x1 = x0 + RZ_BOXW;
+  h_sync();  // every horizontal warp is done with the previous unit's bits
+  for (int i = tid; i < (r1 - r0) * MW; i += NT) s_ovl[i] = 0;
+  if (tid == 0) { s_nhits[0] = 0; s_nhits[1] = 0; }
+  h_sync();
+  int g_begin = 0, g_end = jb.n_glyphs;
+  if (jb.glyph_band_shift >= 0) {
+    const int b0 = max(r0 - jb.glyph_max_h, 0) >> jb.glyph_band_shift, b1 = (r1 - 1) >> jb.glyph_band_shift;
+    g_begin = jb.glyph_band[b0]; g_end = jb.glyph_band[b1 + 1];
+  }
+  const DevPlaced *__restrict__ glyphs = jb.glyphs;
+  const uint32_t *__restrict__ atlas = jb.atlas;
+  auto or_rows = [&](const DevPlaced &pg, int first, int step) {
+    const int q0 = max(0, r0 - pg.y), q1 = min(pg.h, r1 - pg.y);
+    const int p0 = max(0, x0 - pg.x), p1 = min(pg.w, x1 - pg.x);
+    const int bit_lo = pg.bit0 + p0, bit_hi = pg.bit0 + p1;
+    const int w_lo = bit_lo >> 5, w_hi = (bit_hi - 1) >> 5, nw = w_hi - w_lo + 1;
+    for (int i = first; i < (q1 - q0) * nw; i += step) {
+      const int qq = i / nw, wi = w_lo + (i - qq * nw), q = q0 + qq;
+      uint32_t m = __ldg(atlas + pg.mask_off + (uint32_t)(q * pg.wpr + wi));
+      const int lo = max(bit_lo - 32 * wi, 0), hi = min(bit_hi - 32 * wi, 32);
+      m &= (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (32 - hi));
+      if (m == 0) continue;
+      const int xb = pg.x - pg.bit0 + 32 * wi - x0;  // window column of bit 0 of this word (negative only for masked-off bits)
+      const int wd = xb >> 5, sh = xb & 31;
+      uint32_t *mrow = s_ovl + (pg.y + q - r0) * MW;
+      const uint32_t lo_part = m << sh;
+      if (lo_part && wd >= 0) atomicOr(&mrow[wd], lo_part);
+      if (sh) {
+        const uint32_t hi_part = m >> (32 - sh);
+        if (hi_part) atomicOr(&mrow[wd + 1], hi_part);
       }
     }
+  };
+  int pass = 0;
+  for (int base = g_begin; base < g_end; base += NT, pass++) {
+    int *cnt = s_nhits + (pass & 1);
+    if (base + tid < g_end) {
+      const DevPlaced pg = glyphs[base + tid];
+      if (pg.x < x1 && pg.x + pg.w > x0 && pg.y < r1 && pg.y + pg.h > r0) {
+        const int i = atomicAdd(cnt, 1);
+        if (i < RZ_HITS) s_hits[i] = pg;
+        else or_rows(pg, 0, 1);  // more hits than staging slots (tiny glyphs): this thread does the whole glyph
+      }
+    }
+    h_sync();
+    const int nh = min(*cnt, RZ_HITS);
+    if (tid == 0) s_nhits[(pass + 1) & 1] = 0;  // (the other counter: last read before the previous pass's second barrier)
+    for (int h = warp; h < nh; h += RZ_H_WARPS) or_rows(s_hits[h], lane, 32);
+    h_sync();
   }
 }
+
+}  // namespace
 
 // T: horizontal taps held in registers (>= the longest horizontal filter of the launch; shorter filters are
 // padded with zero coefficients).
 template <int BPP, int T>
 __global__ void __launch_bounds__(RZ_THREADS, 1)
-k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters, const uint32_t *__restrict__ ovl_base, int ns, int slot_bytes,
-                int dwp, int nry, int nrc) {
+k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, uint32_t *__restrict__ counters, int ns, int slot_bytes, int dwp, int nry, int nrc,
+                int ovl_rows) {
   asm volatile("griddepcontrol.launch_dependents;");  // see k_frame_strips: consecutive launches overlap
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int ROWB = RZ_BOXW * BPP;
-  const RzSmem L = rz_smem(dwp, nry, nrc);
+  const RzSmem L = rz_smem(dwp, nry, nrc, ovl_rows);
   uint64_t *s_full = (uint64_t *)(smem + L.bar);
   uint64_t *s_empty = s_full + RZ_NS_MAX;
   uint64_t *s_hdone = s_empty + RZ_NS_MAX;  // [2]: the horizontal warps have written chunk j's rows into the rings (j & 1)
   uint64_t *s_vdone = s_hdone + 2;          // [2]: the vertical warps have emitted chunk j's destination rows
+  DevPlaced *s_hits = (DevPlaced *)(smem + L.hits);
+  int *s_nhits = (int *)(s_hits + RZ_HITS);  // [2]: alternate from pass to pass (the idle one is re-armed meanwhile)
+  uint32_t *s_ovl = (uint32_t *)(smem + L.ovl);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t smem_base = smem_u32(smem);
 
@@ -336,7 +370,22 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
       }
       const int strips256 = (jp->W + STRIP_W - 1) / STRIP_W;
       const int nbands = (jp->H + (1 << MASK_BAND_SHIFT) - 1) >> MASK_BAND_SHIFT;
-      const bool has_text = jp->n_glyphs > 0 && jp->rz_ovl_off >= 0 && ovl_base != nullptr;
+      // text: does any placed glyph touch a (32-row band, 256-pixel strip) cell of this unit's source window?
+      int unit_text = 0;
+      if (jp->n_glyphs > 0) {
+        unit_text = 1;
+        if (jp->use_mask) {
+          const int s0 = wx0 / STRIP_W, s1 = min((wx0 + RZ_BOXW - 1) / STRIP_W, strips256 - 1);
+          unsigned any = 0;
+          for (int band = (r0 >> MASK_BAND_SHIFT) + lane; band <= (r1 - 1) >> MASK_BAND_SHIFT && band < nbands; band += 32)
+            for (int st = s0; st <= s1; st++) {
+              const int bit = band * strips256 + st;
+              any |= (jp->tile_mask[bit >> 5] >> (bit & 31)) & 1u;
+            }
+          unit_text = __any_sync(0xffffffffu, any != 0);
+        }
+        if (unit_text && r1 - r0 > ovl_rows) __trap();  // the host sized the overlay rows from the same filters: cannot happen
+      }
       int ly = dy0, cy = cy0;  // emission cursors
       for (int k = 0; k < nchunks; k++, chunk_it++) {
         const int yc0 = r0 + k * RZ_CH;
@@ -363,7 +412,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
         if (lane == 0) {
           RzCtx &c = *(RzCtx *)(smem + L.ctx + (chunk_it & (RZ_NCTX - 1)) * RZ_CTX_BYTES);
           int stamp = 0;
-          if (has_text) {
+          if (unit_text) {
             stamp = 1;
             if (jp->use_mask) {
               stamp = 0;
@@ -378,7 +427,8 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           c.last = last_k && next_u >= total_units;
           c.first = (k == 0);
           c.mode = n_src > 1 ? RM_SELECT : RM_ROWS;
-          c.n_src = n_src; c.n_staged = n_staged;
+          c.n_src = n_src; c.n_staged = n_staged; c.job = j;
+          c.unit_text = unit_text; c.stamp = stamp;
           c.wx0 = wx0; c.dshift = wx0 - wxd; c.yc0 = yc0; c.ra = ra; c.rb = rb;
           c.lr0 = lr0; c.lr1 = lr1; c.cr0 = cr0; c.cr1 = cr1;
           c.ya = ya; c.yb = ly; c.ca = ca; c.cb = cy;
@@ -386,8 +436,6 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           c.dx0 = dx0; c.dw = dw; c.cx0 = cx0; c.dcw = dcw;
           c.half = half; c.dep_staged = dep_staged; c.nv12 = jp->nv12; c.rgb_base = jp->rgb_base;
           c.hls = jp->hl.size; c.hcs = jp->hc.size; c.vls = vls; c.vcs = vcs;
-          c.ovl = stamp ? ovl_base + jp->rz_ovl_off : nullptr;
-          c.ovl_pitch = jp->rz_ovl_pitch;
           c.a_mask = jp->a_off >= 0 ? (0xFFu << (8 * jp->a_off)) : 0xFFFFFFFFu;
           c.ky[0] = jp->ky[0]; c.ky[1] = jp->ky[1]; c.ku[0] = jp->ku[0]; c.ku[1] = jp->ku[1]; c.kv[0] = jp->kv[0]; c.kv[1] = jp->kv[1];
           c.hl_coef = jp->hl.coef; c.hc_coef = jp->hc.coef; c.vl_coef = jp->vl.coef; c.vc_coef = jp->vc.coef;
@@ -631,13 +679,16 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           for (int jj = 0; jj < T; jj++) cf_c[cc][jj] = (on && jj < hcs) ? (int)__ldg(cf + jj) : 0;
         }
       }
+      // ---- text overlay of the unit: one bit per pixel of its source window (nothing is written to the staged rows)
+      if (c.first && c.unit_text) unit_overlay(jobs[c.job], s_ovl, wx0, min(c.lr0, c.cr0), max(c.lr1, c.cr1), s_hits, s_nhits);
       // the ring rows this chunk overwrites were last read by the vertical pass of chunk j - 2
       if (j >= 2) mbar_wait_sleep_a(vdone0 + (j & 1) * 8, (uint32_t)(((j - 2) >> 1) & 1), 128u);
 
       // ---- per source row: composite -> overlay bits -> 14-bit planes (row buffer) -> horizontal pass -> rings ----------
       const uint32_t ky0 = c.ky[0], ky1 = c.ky[1], ku0 = c.ku[0], ku1 = c.ku[1], kv0 = c.kv[0], kv1 = c.kv[1];
       const int rbase_y = c.rbase_y, rbase_c = c.rbase_c;
-      const uint32_t *ovl = c.ovl;
+      const bool stamped = c.stamp != 0;
+      const int ovl_r0 = min(c.lr0, c.cr0);
 #pragma unroll
       for (int i = 0; i < RZ_ROWS_PER_WARP; i++) {
         const int r = (hgrp + i * RZ_HG) * RZ_SUB + wrow;
@@ -647,13 +698,9 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           const uint32_t sb = smem_base + L.stage + (uint32_t)(q[i] * slot_bytes);
           const uint32_t row = sb + wrow * ROWB;
           const uint32_t drow = sb + dep_off + wrow * RZ_DEPB;
-          // text overlay (render_text.cc:94-106: coverage != 0 -> white): the 4 bits of this lane's pixels; the word is
-          // in flight while the composite runs
+          // text overlay (render_text.cc:94-106: coverage != 0 -> white): the 4 bits of this lane's pixels
           uint32_t obits = 0;
-          if (ovl) {
-            const int xx = wx0 + 4 * lane;
-            obits = __ldg(ovl + (size_t)y * c.ovl_pitch + (xx >> 5)) >> (xx & 31);
-          }
+          if (stamped) obits = s_ovl[(y - ovl_r0) * (RZ_BOXW / 32) + (lane >> 3)] >> ((lane & 7) * 4);
           uint32_t p[4], d4 = 0;
           if (BPP == 4) {
             if (mode == RM_SELECT) {
@@ -672,7 +719,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
             p[3] = w2 >> 8;
             if (dep_staged) d4 = lds32(drow + lane * 4);
           }
-          if (ovl) {
+          if (stamped) {
             const uint32_t white = BPP == 4 ? (0x00FFFFFFu << (8 * c.rgb_base)) : 0x00FFFFFFu;
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -764,7 +811,7 @@ int resize_strips_init() {
 }
 
 struct RzConfig {
-  int ns, slot, smem, dwp, taps, nry, nrc;
+  int ns, slot, smem, dwp, taps, nry, nrc, ovl_rows;
 };
 // Launch shape of one pixel class: rings sized for the widest destination strip and the longest vertical filters of
 // the launch, sub-stage slots for the most sources; one CTA per SM, the rest of its shared memory is the sub-stage ring.
@@ -779,10 +826,20 @@ static RzConfig rz_config(const DevJob *jobs, int n_jobs, int bpp) {
     vl = std::max(vl, jb.vl.size);
     vc = std::max(vc, jb.vc.size);
   }
+  // overlay bits: one row of RZ_BOXW bits per source row of the tallest unit that carries text.  A unit of S destination
+  // rows reads at most S * ratio source rows plus the reach of the vertical filters (luma and chroma windows overlap)
+  int ovl_rows = 0;
+  for (int j = 0; j < n_jobs; j++) {
+    const DevJob &jb = jobs[j];
+    if (!jb.rz_ok || jb.bpp != bpp || jb.n_glyphs <= 0) continue;
+    const double ratio = (double)jb.H / jb.Hd;
+    const int rows = (int)std::ceil((jb.rz_seg_rows + 2) * ratio) + 2 * std::max(jb.vl.size, jb.vc.size) + (int)std::ceil(2 * ratio) + 8;
+    ovl_rows = std::max(ovl_rows, std::min(rows, jb.H));
+  }
   const int nry = rz_ring_rows(vl), nrc = rz_ring_rows(vc);
-  const RzSmem L = rz_smem(dwp, nry, nrc);
+  const RzSmem L = rz_smem(dwp, nry, nrc, ovl_rows);
   const int slot = staged * RZ_SUB * (RZ_BOXW * bpp + RZ_DEPB);
-  RzConfig c{0, slot, 0, dwp, taps <= 4 ? 4 : taps <= 6 ? 6 : 8, nry, nrc};
+  RzConfig c{0, slot, 0, dwp, taps <= 4 ? 4 : taps <= 6 ? 6 : 8, nry, nrc, ovl_rows};
   const int budget = (g_rz_optin > 0 ? g_rz_optin : 232448) - L.stage;
   const int ns = std::min(RZ_NS_MAX, budget / slot);
   if (ns >= 2) { c.ns = ns; c.smem = L.stage + ns * slot; }
@@ -791,8 +848,7 @@ static RzConfig rz_config(const DevJob *jobs, int n_jobs, int bpp) {
 
 // One segment height (destination rows) per pixel class: the vertical halo (about the longest vertical filter, in
 // source rows, per segment) against the one-unit tail of the persistent grid.  Unit numbering: a prefix sum over the
-// launch in which the jobs of the other class (and the jobs k_resize_tiles keeps) take no units.  Also lays the
-// overlay bitmaps of the jobs that carry text out in the launch's scratch.
+// launch in which the jobs of the other class (and the jobs k_resize_tiles keeps) take no units.
 void plan_resize_strips(DevJob *jobs, int n_jobs) {
   const int sms = g_rz_sms > 0 ? g_rz_sms : 148;
   for (int cls = 0; cls < 2; cls++) {
@@ -832,34 +888,10 @@ void plan_resize_strips(DevJob *jobs, int n_jobs) {
       base += jb.rz_units;
     }
   }
-  int64_t off = 0;
-  for (int j = 0; j < n_jobs; j++) {
-    DevJob &jb = jobs[j];
-    jb.rz_ovl_off = -1;
-    jb.rz_ovl_pitch = 0;
-    if (!jb.rz_ok || jb.n_glyphs <= 0) continue;
-    // a window reads up to RZ_BOXW - 1 columns past the frame's last one: the pitch covers them (they stay 0)
-    jb.rz_ovl_pitch = ((jb.W + RZ_BOXW + 31) >> 5) + 1;
-    jb.rz_ovl_off = off;
-    off += (int64_t)jb.rz_ovl_pitch * jb.H;
-    off = (off + 31) & ~(int64_t)31;
-  }
-}
-
-static size_t rz_overlay_bytes(const DevJob *jobs, int n_jobs) {
-  size_t words = 0;
-  for (int j = 0; j < n_jobs; j++)
-    if (jobs[j].rz_ok && jobs[j].rz_ovl_off >= 0) words = std::max(words, (size_t)jobs[j].rz_ovl_off + (size_t)jobs[j].rz_ovl_pitch * jobs[j].H);
-  return words * 4;
-}
-
-void resize_strips_free_scratch(RzScratch *scratch) {
-  if (scratch && scratch->ovl) cudaFree(scratch->ovl);
-  if (scratch) { scratch->ovl = nullptr; scratch->cap = 0; }
 }
 
 template <int BPP, int T>
-static cudaError_t rz_launch_one(int grid, const RzConfig &c, cudaStream_t st, const DevJob *jobs, int n_jobs, int total, uint32_t *ctr, const uint32_t *ovl, bool pdl) {
+static cudaError_t rz_launch_one(int grid, const RzConfig &c, cudaStream_t st, const DevJob *jobs, int n_jobs, int total, uint32_t *ctr) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(RZ_THREADS);
@@ -869,40 +901,13 @@ static cudaError_t rz_launch_one(int grid, const RzConfig &c, cudaStream_t st, c
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k_resize_strips<BPP, T>, jobs, n_jobs, total, ctr, ovl, c.ns, c.slot, c.dwp, c.nry, c.nrc);
+  cfg.numAttrs = g_rz_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_resize_strips<BPP, T>, jobs, n_jobs, total, ctr, c.ns, c.slot, c.dwp, c.nry, c.nrc, c.ovl_rows);
 }
 
-int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream, RzScratch *scratch) {
+int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_jobs, uint32_t *counters, uint64_t *seq, void *stream) {
   int launches = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int total_all = 0;
-  for (int j = 0; j < n_jobs; j++)
-    if (jobs_host[j].rz_ok) total_all += jobs_host[j].rz_units;
-  if (total_all == 0) return 0;
-  // text: the frames' overlay bitmaps are rebuilt ahead of the resize kernel (ordinary stream order: the kernel that
-  // reads them is then launched without the programmatic-overlap attribute)
-  const size_t ovl_bytes = rz_overlay_bytes(jobs_host, n_jobs);
-  const uint32_t *ovl = nullptr;
-  if (ovl_bytes > 0) {
-    if (!scratch) return -1;
-    if (scratch->cap < ovl_bytes) {
-      if (scratch->ovl) cudaFree(scratch->ovl);  // (synchronises: nothing in flight still reads it)
-      scratch->ovl = nullptr; scratch->cap = 0;
-      const size_t want = (ovl_bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
-      if (cudaMalloc((void **)&scratch->ovl, want) != cudaSuccess) { cudaGetLastError(); scratch->ovl = nullptr; return -1; }
-      scratch->cap = want;
-    }
-    if (cudaMemsetAsync(scratch->ovl, 0, ovl_bytes, st) != cudaSuccess) return -1;
-    int max_gl = 0;
-    for (int j = 0; j < n_jobs; j++)
-      if (jobs_host[j].rz_ok && jobs_host[j].rz_ovl_off >= 0) max_gl = std::max(max_gl, jobs_host[j].n_glyphs);
-    const dim3 grid((unsigned)std::min(std::max((max_gl + 7) / 8, 1), 4096), (unsigned)std::min(n_jobs, 1024));  // one glyph per warp
-    k_overlay_bits<<<grid, 256, 0, st>>>(jobs_dev, n_jobs, scratch->ovl);
-    if (cudaGetLastError() != cudaSuccess) return -1;
-    launches++;
-    ovl = scratch->ovl;
-  }
   for (int bpp = 3; bpp <= 4; bpp++) {
     int total = 0;
     for (int j = 0; j < n_jobs; j++)
@@ -912,10 +917,9 @@ int launch_resize_strips(const DevJob *jobs_dev, const DevJob *jobs_host, int n_
     if (c.ns < 2) return -1;
     const int grid = std::min(total, g_rz_sms);
     uint32_t *ctr = counters + 2 * ((*seq)++ % COUNTER_SLOTS);
-    const bool pdl = g_rz_pdl && ovl == nullptr;
     cudaError_t e;
-    if (bpp == 3) e = c.taps == 4 ? rz_launch_one<3, 4>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl) : c.taps == 6 ? rz_launch_one<3, 6>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl) : rz_launch_one<3, 8>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl);
-    else e = c.taps == 4 ? rz_launch_one<4, 4>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl) : c.taps == 6 ? rz_launch_one<4, 6>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl) : rz_launch_one<4, 8>(grid, c, st, jobs_dev, n_jobs, total, ctr, ovl, pdl);
+    if (bpp == 3) e = c.taps == 4 ? rz_launch_one<3, 4>(grid, c, st, jobs_dev, n_jobs, total, ctr) : c.taps == 6 ? rz_launch_one<3, 6>(grid, c, st, jobs_dev, n_jobs, total, ctr) : rz_launch_one<3, 8>(grid, c, st, jobs_dev, n_jobs, total, ctr);
+    else e = c.taps == 4 ? rz_launch_one<4, 4>(grid, c, st, jobs_dev, n_jobs, total, ctr) : c.taps == 6 ? rz_launch_one<4, 6>(grid, c, st, jobs_dev, n_jobs, total, ctr) : rz_launch_one<4, 8>(grid, c, st, jobs_dev, n_jobs, total, ctr);
     if (e != cudaSuccess) return -1;
     launches++;
   }

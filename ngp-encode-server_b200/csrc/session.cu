@@ -125,7 +125,6 @@ struct nes_gpu_session {
   HostAtlas atlas;
   uint32_t *d_atlas = nullptr;     // glyph bit masks (HostAtlas::mask)
   uint32_t *d_counters = nullptr;  // k_frame_strips work counters: COUNTER_SLOTS self re-arming pairs, handed out round-robin per launch
-  RzScratch rz_scratch;            // overlay bitmaps of k_resize_strips launches (grown on demand)
   std::map<std::tuple<int, int, int, int>, FilterSet> filters;
   // tensor maps of staged planes, keyed by (pointer, stride, width in bytes, rows, box bytes): a streaming
   // session cycles through a handful of ring buffers, so encoding happens once per buffer
@@ -622,13 +621,13 @@ int run_kernels(nes_gpu_session *s, const DevJob *d_jobs, const DevJob *h_jobs, 
   int l = 0;
   const int r0 = launch_frame_strips(d_jobs, h_jobs, n, s->d_counters, &s->strips_seq, st, 0, 0, glyphs_host);
   if (r0 > 0) l += r0;
-  const int r1 = launch_resize_strips(d_jobs, h_jobs, n, s->d_counters, &s->strips_seq, st, &s->rz_scratch);
+  const int r1 = launch_resize_strips(d_jobs, h_jobs, n, s->d_counters, &s->strips_seq, st);
   if (r1 > 0) l += r1;
   const int r = launch_resize_tiles(d_jobs, h_jobs, n, st);
   if (r > 0) l += r;
   const int r2 = launch_depth16(h_jobs, n, st);
   if (r2 > 0) l += r2;
-  if (r0 < 0 || r1 < 0 || r < 0 || r2 < 0) {  // a launch (or the overlay scratch allocation) failed: the frame was not converted
+  if (r0 < 0 || r1 < 0 || r < 0 || r2 < 0) {  // a launch failed: the frame was not converted
     if (s->err.empty()) s->err = "kernel launch failed";
     s->sticky = NES_ERR_CUDA;
   }
@@ -737,7 +736,6 @@ void nes_gpu_session_destroy(nes_gpu_session *s) {
   for (auto &kv : s->filters) { cudaFree(kv.second.blob); cudaFree((void *)kv.second.win_x); }
   cudaFree(s->d_atlas);
   cudaFree(s->d_counters);
-  resize_strips_free_scratch(&s->rz_scratch);
   if (s->st_in) cudaStreamDestroy(s->st_in);
   if (s->st_k) cudaStreamDestroy(s->st_k);
   if (s->st_out) cudaStreamDestroy(s->st_out);
@@ -1316,7 +1314,6 @@ struct nes_gpu_mux {
   int device = 0, max_batch = 64;
   cudaStream_t st_k = nullptr;
   uint32_t *d_counters = nullptr;
-  RzScratch rz_scratch;
   uint64_t strips_seq = 0;
   static constexpr int kTables = 4;
   BatchTables tables[kTables];
@@ -1369,7 +1366,7 @@ static void mux_dispatch(nes_gpu_mux *m, std::vector<std::pair<nes_gpu_session *
   int l = 0;
   if (status == NES_OK) {
     const int r0 = launch_frame_strips(bt.d_jobs, bt.h_jobs, n, m->d_counters, &m->strips_seq, m->st_k);
-    const int r1 = launch_resize_strips(bt.d_jobs, bt.h_jobs, n, m->d_counters, &m->strips_seq, m->st_k, &m->rz_scratch);
+    const int r1 = launch_resize_strips(bt.d_jobs, bt.h_jobs, n, m->d_counters, &m->strips_seq, m->st_k);
     const int r2 = launch_resize_tiles(bt.d_jobs, bt.h_jobs, n, m->st_k);
     const int r3 = launch_depth16(bt.h_jobs, n, m->st_k);
     if (r0 < 0 || r1 < 0 || r2 < 0 || r3 < 0) { status = NES_ERR_CUDA; m->err = "kernel launch failed"; }
@@ -1462,7 +1459,6 @@ void nes_gpu_mux_destroy(nes_gpu_mux *m) {
     if (bt.done) cudaEventDestroy(bt.done);
   }
   cudaFree(m->d_counters);
-  resize_strips_free_scratch(&m->rz_scratch);
   if (m->st_k) cudaStreamDestroy(m->st_k);
   cudaGetLastError();
   delete m;

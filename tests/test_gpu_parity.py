@@ -672,7 +672,7 @@ def _device_job(N, session, fmt, srcs, w, h, wd, hd):
 def test_batch_mixed_jobs(N, O, port, glyphs, session):
     """One batched call mixing what a multi-session server submits together: 3-byte and 4-byte
     pixels, 1 / 2 / 4 sources (one sub-stage slot size per launch), same-size and resized outputs
-    (composite + overlay + resize is one fused launch behind a small overlay-bitmap kernel), with and without text."""
+    (composite + overlay + resize is a single fused launch), with and without text."""
     rng = np.random.default_rng(77)
     text = [(O.POS_LEFT_TOP, b"mixed batch\nline two 0123456789"), (O.POS_CENTER, b"centre")]
     specs = [("rgb24", 1, 512, 96, 512, 96, None), ("rgba", 2, 512, 96, 512, 96, text), ("rgba", 1, 768, 64, 768, 64, None),
@@ -694,8 +694,7 @@ def test_batch_mixed_jobs(N, O, port, glyphs, session):
         jobs.append(_device_job(N, session, fmt, srcs, w, h, wd, hd) + (wd, hd, runs))
     before = session.launches
     session.convert_batch_device([j[0] for j in jobs], [j[6] for j in jobs], [j[1] for j in jobs], sync=True)
-    # two pixel-size classes x (same-size kernel, resize kernel) + the overlay bitmaps of the resized frames that carry text
-    assert session.launches - before == 5
+    assert session.launches - before == 4  # two pixel-size classes x (same-size kernel, resize kernel)
     for (fin, fo, (d_s, d_d), ptrs, wd, hd, runs), (want_s, want_d), spec in zip(jobs, wants, specs):
         sc, dp = N.FrameManager(N.FrameContext(wd, hd, "yuv420p")), N.FrameManager(N.FrameContext(wd, hd, "yuv420p"))
         session.d2h(sc.buffer, d_s); session.d2h(dp.buffer, d_d)
