@@ -446,7 +446,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
         __syncwarp();
 #pragma unroll 1
         for (int sub = 0; sub < RZ_SUBS; sub++) {
-          if (!round0) mbar_wait_sleep_a(smem_u32(&s_empty[q]), (uint32_t)(par ^ 1), 256u);
+          if (!round0) mbar_wait_hint_a(smem_u32(&s_empty[q]), (uint32_t)(par ^ 1), 2000u);
           const int ys = yc0 + sub * RZ_SUB;
           const bool wanted = ys < rb;
           if (wanted) {
@@ -485,7 +485,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
     const int vtid = tid - 32 * RZ_H_WARPS;
     constexpr int VT = 32 * RZ_V_WARPS;
     for (int j = 0;; j++) {
-      mbar_wait_sleep_a(hdone0 + (j & 1) * 8, (uint32_t)((j >> 1) & 1), 512u);
+      mbar_wait_hint_a(hdone0 + (j & 1) * 8, (uint32_t)((j >> 1) & 1), 2000u);
       const RzCtx &c = *(const RzCtx *)(smem + L.ctx + (j & (RZ_NCTX - 1)) * RZ_CTX_BYTES);
       const int last = c.last;
       const int yc0 = c.yc0, dw = c.dw, dcw = c.dcw;
@@ -682,7 +682,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
       // ---- text overlay of the unit: one bit per pixel of its source window (nothing is written to the staged rows)
       if (c.first && c.unit_text) unit_overlay(jobs[c.job], s_ovl, wx0, min(c.lr0, c.cr0), max(c.lr1, c.cr1), s_hits, s_nhits);
       // the ring rows this chunk overwrites were last read by the vertical pass of chunk j - 2
-      if (j >= 2) mbar_wait_sleep_a(vdone0 + (j & 1) * 8, (uint32_t)(((j - 2) >> 1) & 1), 128u);
+      if (j >= 2) mbar_wait_hint_a(vdone0 + (j & 1) * 8, (uint32_t)(((j - 2) >> 1) & 1), 2000u);
 
       // ---- per source row: composite -> overlay bits -> 14-bit planes (row buffer) -> horizontal pass -> rings ----------
       const uint32_t ky0 = c.ky[0], ky1 = c.ky[1], ku0 = c.ku[0], ku1 = c.ku[1], kv0 = c.kv[0], kv1 = c.kv[1];

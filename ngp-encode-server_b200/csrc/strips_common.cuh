@@ -34,7 +34,7 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// the same, letting the hardware keep the warp suspended for up to ~hint_ns before the try returns (fewer polls)
+// the same with a suspend-time hint (SASS: NANOSLEEP.SYNCS between tries -- the warp is woken by the barrier's update)
 __device__ __forceinline__ void mbar_wait_hint_a(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
   asm volatile(
       "{\n"
@@ -45,20 +45,6 @@ __device__ __forceinline__ void mbar_wait_hint_a(uint32_t bar, uint32_t parity, 
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(bar), "r"(parity), "r"(hint_ns) : "memory");
-}
-// the same with a back-off between polls: a warp that waits long (an idle role of a warp-specialised CTA) must not
-// take issue slots from the warps that work
-__device__ __forceinline__ void mbar_wait_sleep_a(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "nanosleep.u32 %2;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity), "r"(sleep_ns) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
