@@ -394,12 +394,12 @@ class Harness:
             ver["port_note"] = repr(e)[:120]
 
         # ---- single-frame launches: what one streaming session without batching sees --------------------------
-        if full:
+        if True:
             singles = [s.batch_prepare([fins_dev[f]], [runs_list[f]], [fouts_dev[0][f]]) for f in range(B)]
             for b in singles:
                 s.batch_run(b)
             torch.cuda.synchronize()
-            reps = max(1, int(np.ceil(2000 / B)))
+            reps = max(1, int(np.ceil((2000 if full else 300) / B)))
             e0.record(stream)
             for _ in range(reps):
                 for b in singles:
@@ -412,7 +412,7 @@ class Harness:
             for p in prep1:
                 s.run_batch(p)
             torch.cuda.synchronize()
-            reps = max(1, int(np.ceil(1000 / B)))
+            reps = max(1, int(np.ceil((1000 if full else 300) / B)))
             e0.record(stream)
             p0 = time.perf_counter()
             for _ in range(reps):
@@ -574,7 +574,11 @@ class Harness:
         t0 = time.time()
         p0 = time.perf_counter()
         go.set()
-        time.sleep(0.3)  # ramp: every session has frames in flight
+        # ramp: until every session has been through both of its frame slots twice (the first submits of a session allocate its
+        # device buffers -- cudaMalloc synchronises the device -- which is start-up, not the steady state this measures)
+        ramp_to = time.perf_counter() + 15.0
+        while min(counts) < 4 * max(1, len(sess) // n_threads) and time.perf_counter() < ramp_to and not stop.is_set():
+            time.sleep(0.05)
         c0, p1 = sum(counts), time.perf_counter()
         time.sleep(seconds)
         c1, p2 = sum(counts), time.perf_counter()
@@ -725,7 +729,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
     n.lib()
-    sampler = ClockSampler(local) if rank == 0 else None  # one nvidia-smi poller per box, not per rank
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("NES_BENCH_NO_SAMPLER")) else None  # one nvidia-smi poller per box, not per rank
     H = Harness(n, torch, dist, rank, world, local, sampler, args)
     main_res = H.measure(args.workload, args.steps, warmup, full=True)
 
@@ -748,7 +752,8 @@ def main():
             try:
                 r = H.measure(name, max(5, min(args.steps, 40)), 3, full=False)
                 extra[name] = {k: r[k] for k in ("value", "unit", "ms_per_step", "frames_per_step", "frames_per_launch", "roofline", "e2e", "verified",
-                                                 "p50_frame_latency_ms", "gpu_launches", "sessions") if k in r}
+                                                 "p50_frame_latency_ms", "gpu_launches", "sessions", "single_frame_launch_fps", "single_frame_api_fps",
+                                                 "single_frame_api_host_us") if k in r}
                 extra[name]["config"] = workload_config(n.synth, name)
             except Exception as e:  # noqa: BLE001
                 extra[name] = {"error": repr(e)[:300]}

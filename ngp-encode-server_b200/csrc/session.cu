@@ -110,12 +110,16 @@ struct BatchTables {
 
 struct nes_gpu_mux;
 static int mux_enqueue(nes_gpu_mux *m, nes_gpu_session *s, int slot_index);
+static void mux_forget(nes_gpu_mux *m, nes_gpu_session *s);
 static void mux_wait_dispatched(nes_gpu_mux *m, nes_gpu_session *s, int slot_index);
 
 struct nes_gpu_session {
   nes_gpu_cfg cfg{};
   std::mutex mu;
   cudaStream_t st_in = nullptr, st_k = nullptr, st_out = nullptr;
+  // the streams the session created (st_in / st_out point at the mux's pooled copy streams while it is attached: a device
+  // has a handful of hardware queues, and hundreds of streams waiting on each other's events serialise on them)
+  cudaStream_t own_in = nullptr, own_out = nullptr;
   std::vector<Slot> slots;
   BatchTables batch[kBatchRing];
   uint64_t batch_seq = 0;
@@ -685,9 +689,11 @@ int nes_gpu_session_create(const nes_gpu_cfg *cfg, nes_gpu_session **out) {
   auto fail = [&](int st) { nes_gpu_session_destroy(s); return st; };
   if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(NES_ERR_CUDA);
   if (kernels_init() != 0) return fail(NES_ERR_CUDA);
-  if (cudaStreamCreateWithFlags(&s->st_in, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&s->own_in, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
+  s->st_in = s->own_in;
   if (cudaStreamCreateWithFlags(&s->st_k, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
-  if (cudaStreamCreateWithFlags(&s->st_out, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&s->own_out, cudaStreamNonBlocking) != cudaSuccess) return fail(NES_ERR_CUDA);
+  s->st_out = s->own_out;
   if (cudaMalloc((void **)&s->d_counters, 2 * COUNTER_SLOTS * sizeof(uint32_t)) != cudaSuccess) return fail(NES_ERR_CUDA);
   if (cudaMemset(s->d_counters, 0, 2 * COUNTER_SLOTS * sizeof(uint32_t)) != cudaSuccess) return fail(NES_ERR_CUDA);
   s->slots.resize((size_t)s->cfg.ring_depth);
@@ -715,6 +721,9 @@ void nes_gpu_session_destroy(nes_gpu_session *s) {
   if (s->st_in) cudaStreamSynchronize(s->st_in);
   if (s->st_k) cudaStreamSynchronize(s->st_k);
   if (s->st_out) cudaStreamSynchronize(s->st_out);
+  if (s->mux) mux_forget(s->mux, s);  // back on its own streams, off the mux's list
+  if (s->st_in) cudaStreamSynchronize(s->st_in);
+  if (s->st_out) cudaStreamSynchronize(s->st_out);
   for (Slot &sl : s->slots) {
     cudaFree(sl.d_in); cudaFree(sl.d_out);
     cudaFreeHost(sl.h_in); cudaFreeHost(sl.h_out);
@@ -736,9 +745,9 @@ void nes_gpu_session_destroy(nes_gpu_session *s) {
   for (auto &kv : s->filters) { cudaFree(kv.second.blob); cudaFree((void *)kv.second.win_x); }
   cudaFree(s->d_atlas);
   cudaFree(s->d_counters);
-  if (s->st_in) cudaStreamDestroy(s->st_in);
+  if (s->own_in) cudaStreamDestroy(s->own_in);
   if (s->st_k) cudaStreamDestroy(s->st_k);
-  if (s->st_out) cudaStreamDestroy(s->st_out);
+  if (s->own_out) cudaStreamDestroy(s->own_out);
   cudaGetLastError();
   delete s;
 }
@@ -1315,6 +1324,12 @@ struct nes_gpu_mux {
   cudaStream_t st_k = nullptr;
   uint32_t *d_counters = nullptr;
   uint64_t strips_seq = 0;
+  // copy streams shared by the attached sessions (session i uploads on st_up[i % kCopyStreams], downloads on st_down[...])
+  static constexpr int kCopyStreams = 4;
+  cudaStream_t st_up[kCopyStreams] = {}, st_down[kCopyStreams] = {};
+  std::mutex att_mu;
+  std::vector<nes_gpu_session *> attached;
+  uint64_t attach_seq = 0;
   static constexpr int kTables = 4;
   BatchTables tables[kTables];
   uint64_t table_seq = 0;
@@ -1396,6 +1411,14 @@ static void mux_dispatch(nes_gpu_mux *m, std::vector<std::pair<nes_gpu_session *
   m->done_cv.notify_all();
 }
 
+// The session leaves the mux (its own destruction, or the mux's): back on the streams it created.
+static void mux_forget(nes_gpu_mux *m, nes_gpu_session *s) {
+  std::lock_guard<std::mutex> lk(m->att_mu);
+  m->attached.erase(std::remove(m->attached.begin(), m->attached.end(), s), m->attached.end());
+  s->st_in = s->own_in; s->st_out = s->own_out;
+  s->mux = nullptr;
+}
+
 static void mux_worker(nes_gpu_mux *m) {
   cudaSetDevice(m->device);
   std::vector<std::pair<nes_gpu_session *, int>> batch;
@@ -1424,7 +1447,10 @@ int nes_gpu_mux_create(int device, int max_batch, nes_gpu_mux **out) {
   if (!m) return NES_ERR_NO_MEMORY;
   m->device = device;
   m->max_batch = max_batch < 1 ? 64 : std::min(max_batch, kMaxBatch);
-  bool ok = cudaSetDevice(device) == cudaSuccess && kernels_init() == 0 && cudaStreamCreateWithFlags(&m->st_k, cudaStreamNonBlocking) == cudaSuccess &&
+  bool ok = cudaSetDevice(device) == cudaSuccess && kernels_init() == 0 && cudaStreamCreateWithFlags(&m->st_k, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < nes_gpu_mux::kCopyStreams; i++)
+    ok = ok && cudaStreamCreateWithFlags(&m->st_up[i], cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&m->st_down[i], cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok &&
             cudaMalloc((void **)&m->d_counters, 2 * COUNTER_SLOTS * sizeof(uint32_t)) == cudaSuccess &&
             cudaMemset(m->d_counters, 0, 2 * COUNTER_SLOTS * sizeof(uint32_t)) == cudaSuccess;
   for (BatchTables &bt : m->tables) {
@@ -1454,12 +1480,31 @@ void nes_gpu_mux_destroy(nes_gpu_mux *m) {
   }
   cudaSetDevice(m->device);
   if (m->st_k) cudaStreamSynchronize(m->st_k);
+  for (int i = 0; i < nes_gpu_mux::kCopyStreams; i++) {
+    if (m->st_up[i]) cudaStreamSynchronize(m->st_up[i]);
+    if (m->st_down[i]) cudaStreamSynchronize(m->st_down[i]);
+  }
+  // sessions that are still attached go back to their own streams (they stay usable, un-multiplexed)
+  for (;;) {
+    nes_gpu_session *s = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(m->att_mu);
+      if (!m->attached.empty()) s = m->attached.back();
+    }
+    if (!s) break;
+    std::lock_guard<std::mutex> lk(s->mu);
+    mux_forget(m, s);
+  }
   for (BatchTables &bt : m->tables) {
     cudaFreeHost(bt.h_jobs); cudaFree(bt.d_jobs);
     if (bt.done) cudaEventDestroy(bt.done);
   }
   cudaFree(m->d_counters);
   if (m->st_k) cudaStreamDestroy(m->st_k);
+  for (int i = 0; i < nes_gpu_mux::kCopyStreams; i++) {
+    if (m->st_up[i]) cudaStreamDestroy(m->st_up[i]);
+    if (m->st_down[i]) cudaStreamDestroy(m->st_down[i]);
+  }
   cudaGetLastError();
   delete m;
 }
@@ -1470,7 +1515,14 @@ int nes_gpu_mux_attach(nes_gpu_mux *m, nes_gpu_session *s) {
   if (s->cfg.device != m->device) return NES_ERR_INVALID_ARG;
   for (const Slot &sl : s->slots)
     if (sl.busy) return NES_ERR_BUSY;
+  if (s->mux == m) return NES_OK;
+  if (s->mux) mux_forget(s->mux, s);
+  std::lock_guard<std::mutex> lk2(m->att_mu);
+  const uint64_t i = m->attach_seq++;
   s->mux = m;
+  s->st_in = m->st_up[i % nes_gpu_mux::kCopyStreams];
+  s->st_out = m->st_down[i % nes_gpu_mux::kCopyStreams];
+  m->attached.push_back(s);
   return NES_OK;
 }
 
