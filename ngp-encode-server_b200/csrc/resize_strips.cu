@@ -321,7 +321,8 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
 
   if (tid == 0) {
     for (int i = 0; i < RZ_NS_MAX; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], RZ_SUB); }
-    for (int i = 0; i < 2; i++) { mbar_init(&s_hdone[i], RZ_H_WARPS); mbar_init(&s_vdone[i], RZ_V_WARPS); }
+    // (every thread of a role arrives itself: the hand-over is then a plain per-thread happens-before, which is also what compute-sanitizer's racecheck can follow)
+    for (int i = 0; i < 2; i++) { mbar_init(&s_hdone[i], 32 * RZ_H_WARPS); mbar_init(&s_vdone[i], 32 * RZ_V_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -611,8 +612,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
           }
         }
       }
-      __syncwarp();  // every lane is done with the rings and the context of chunk j
-      if (lane == 0) mbar_arrive_a(vdone0 + (j & 1) * 8);
+      mbar_arrive_a(vdone0 + (j & 1) * 8);  // this thread is done with the rings and the context of chunk j
       if (last) break;
     }
     return;
@@ -778,7 +778,7 @@ k_resize_strips(const DevJob *__restrict__ jobs, int n_jobs, int total_units, ui
         if (lane == 0) mbar_arrive_a(empty0 + q[i] * 8);
       }
     }
-    if (lane == 0) mbar_arrive_a(hdone0 + (j & 1) * 8);  // (after the __syncwarp above: this warp's ring rows of chunk j are written)
+    mbar_arrive_a(hdone0 + (j & 1) * 8);  // this thread's ring samples of chunk j are written
     if (last) break;
     qc += RZ_SUBS;
     while (qc >= ns) { qc -= ns; parc ^= 1; }
