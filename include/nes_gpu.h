@@ -337,9 +337,10 @@ NES_API int nes_ingest_release(nes_ingest_ring *r, int slot);
  * BASELINE config 4 (64 concurrent sessions sharded over the GPUs; the reference is one process per session,
  * main.cpp:133-171, one process_frame_thread per eye, :274-282).  Create one mux per GPU and attach that GPU's
  * sessions: nes_gpu_submit on an attached session stages the frame on the caller's thread (descriptor, H2D copies on
- * the session's own stream) and hands it to the mux's dispatcher thread, which gathers whatever frames are ready --
- * it never waits for a batch to fill -- into one descriptor table and one kernel launch, then enqueues every frame's
- * download on its session's stream.  nes_gpu_wait / nes_gpu_convert work as before.  Destroy the sessions first. */
+ * one of the mux's pooled copy streams) and hands it to the mux's dispatcher thread, which gathers whatever frames are
+ * ready -- it never waits for a batch to fill -- into one descriptor table and one kernel launch, then enqueues every
+ * frame's download.  nes_gpu_wait / nes_gpu_convert work as before.  A destroyed session detaches itself; destroying
+ * the mux hands the sessions still attached back to their own streams (they stay usable, un-multiplexed). */
 typedef struct nes_gpu_mux nes_gpu_mux;
 typedef struct nes_mux_stats {
   uint64_t frames;      /* frames dispatched                                             */

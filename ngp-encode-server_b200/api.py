@@ -543,7 +543,7 @@ class Mux:
         return self.L.nes_gpu_mux_error(self.h).decode()
 
     def close(self):
-        """Destroy the attached sessions first."""
+        """Sessions still attached go back to their own streams (either order of destruction is fine)."""
         if self.h:
             self.L.nes_gpu_mux_destroy(self.h)
             self.h = C.c_void_p()

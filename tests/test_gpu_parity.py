@@ -574,6 +574,43 @@ def test_mux_many_sessions(N, O, port, glyphs):
         mux.close()
 
 
+def test_mux_destroyed_before_its_sessions(N, O, port, glyphs):
+    """Either order of destruction: a session whose mux is gone is back on its own streams and converts on its own;
+    a session destroyed first leaves the mux's list (the mux then closes cleanly)."""
+    w, h = 320, 200
+    mux = N.Mux(device=0, max_batch=8)
+    s1 = N.Session(device=0, max_width=w, max_height=h, max_sources=1, ring_depth=2)
+    s2 = N.Session(device=0, max_width=w, max_height=h, max_sources=1, ring_depth=2)
+    try:
+        for s in (s1, s2):
+            s.atlas_set(glyphs.metrics, glyphs.bitmaps)
+            mux.attach(s)
+        wl = dict(w=w, h=h, fmt="rgb24", n_src=1)
+
+        def convert_and_check(s, f):
+            srcs = N.synth.make_sources(wl, f)
+            runs = O.reference_strings(index=f)
+            want = O.expected_frame(srcs, "rgb24", runs, w, h, port, glyphs)
+            sc = N.FrameManager(N.FrameContext(w, h, "yuv420p"), session=s)
+            dp = N.FrameManager(N.FrameContext(w, h, "yuv420p"), session=s)
+            keep = [(np.ascontiguousarray(a).reshape(-1), np.ascontiguousarray(d).reshape(-1)) for a, d in srcs]
+            fin = N.Session.frame_in("rgb24", w, h, [(a, d, 0, 0) for a, d in keep])
+            s.wait(s.submit(fin, runs, N.api._frame_out(sc, dp)))
+            assert sc.cropped() == want[0].cropped() and dp.cropped() == want[1].cropped()
+
+        convert_and_check(s1, 1)
+        convert_and_check(s2, 2)
+        assert mux.stats()["frames"] == 2
+        s2.close()           # a session goes first ...
+        convert_and_check(s1, 3)
+        mux.close()          # ... then the mux, with s1 still attached
+        convert_and_check(s1, 4)  # s1 is un-multiplexed now
+    finally:
+        s1.close()
+        s2.close()
+        mux.close()
+
+
 def test_reference_encode_cpp_text_runs(N, O, port, glyphs, tmp_path):
     """The reference's OWN process_frame_thread + send_frame_thread text (extracted from /root/reference in the build
     container into the git-ignored tests/cpp/_ref/, which travels to the GPU box like oracle/_ref) run against the shim on the GPU: one frame goes through the four overlays, convert_frame()
