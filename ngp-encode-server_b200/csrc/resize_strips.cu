@@ -841,7 +841,9 @@ static RzConfig rz_config(const DevJob *jobs, int n_jobs, int bpp) {
   const int slot = staged * RZ_SUB * (RZ_BOXW * bpp + RZ_DEPB);
   RzConfig c{0, slot, 0, dwp, taps <= 4 ? 4 : taps <= 6 ? 6 : 8, nry, nrc, ovl_rows};
   const int budget = (g_rz_optin > 0 ? g_rz_optin : 232448) - L.stage;
-  const int ns = std::min(RZ_NS_MAX, budget / slot);
+  // NES_RZ_NS (tests): cap the sub-stage ring, e.g. 2 or 3 slots for a 4-sub-stage chunk (what a launch with little shared memory left gets)
+  static const int ns_cap = [] { const char *v = getenv("NES_RZ_NS"); const int x = v ? atoi(v) : RZ_NS_MAX; return std::min(std::max(x, 2), RZ_NS_MAX); }();
+  const int ns = std::min(ns_cap, budget / slot);
   if (ns >= 2) { c.ns = ns; c.smem = L.stage + ns * slot; }
   return c;
 }

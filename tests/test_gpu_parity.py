@@ -232,6 +232,20 @@ def test_resize_composite_overlay_config5_small(N, O, port, glyphs, session):
     assert dp.cropped() == want_d.cropped()
 
 
+@pytest.mark.parametrize("ns", [2, 3, 5])
+def test_resize_with_shallow_substage_rings(ns):
+    """k_resize_strips walks a chunk of 4 sub-stages through a ring of `ns` slots (2 ... 8, whatever shared memory is left after the
+    rings); the slot / parity arithmetic of the three warp roles must hold for every ns, also when a chunk wraps the ring more
+    than once.  NES_RZ_NS is read once per process, so the resize tests are re-run in a child process per value."""
+    import subprocess
+    import sys
+    env = dict(os.environ, NES_RZ_NS=str(ns))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "test_resize_vs_oracle or test_resize_composite_overlay_config5_small or test_nv12_output or test_batch_mixed_jobs"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+
+
 # ------------------------------------------------------------------ API behaviour
 def test_errors(N, session):
     rgb = np.zeros(64 * 32 * 3, np.uint8)
