@@ -859,25 +859,35 @@ void plan_resize_strips(DevJob *jobs, int n_jobs) {
     for (int j = 0; j < n_jobs; j++) any = any || (jobs[j].rz_ok && jobs[j].bpp == bpp);
     int best_s = 32;
     if (any) {
+      // Candidates: the heights that cut a frame into k equal segments (multiples of 16).  Units of a launch cost about the same
+      // and are handed out dynamically, so the launch takes ceil(units / CTAs) rounds of one unit: source rows of the segment +
+      // the vertical halo and the ragged last chunk + what a unit costs before its first row (filter registers, overlay bits,
+      // pipeline fill), in source rows.
       const int grid = sms;
+      int hd_max = 0;
+      for (int j = 0; j < n_jobs; j++)
+        if (jobs[j].rz_ok && jobs[j].bpp == bpp) hd_max = std::max(hd_max, jobs[j].Hd);
       double best_cost = 1e30;
-      for (int S = 16; S <= 512; S *= 2) {
-        double work = 0, unit_max = 0;
+      for (int k = 1; k <= std::max(1, hd_max / 16); k++) {
+        const int S = std::max(16, ((hd_max + k - 1) / k + 15) & ~15);
+        if (k > 1 && S == std::max(16, ((hd_max + k - 2) / (k - 1) + 15) & ~15)) continue;  // same height as the previous k
+        double unit_max = 0;
         long units = 0;
         for (int j = 0; j < n_jobs; j++) {
           const DevJob &jb = jobs[j];
           if (!jb.rz_ok || jb.bpp != bpp) continue;
           const int strips = (jb.Wd + jb.rz_dw - 1) / jb.rz_dw, segs = (jb.Hd + S - 1) / S;
           const double ratio = (double)jb.H / jb.Hd;
-          const double halo = std::max(jb.vl.size, jb.vc.size) + RZ_CH / 2;  // + the ragged last chunk
+          const double halo = std::max(jb.vl.size, jb.vc.size) + RZ_CH / 2;
           units += (long)strips * segs;
-          work += (double)strips * (jb.H + segs * halo);
-          unit_max = std::max(unit_max, S * ratio + halo);
+          unit_max = std::max(unit_max, std::min(S, jb.Hd) * ratio + halo + 24.0);
         }
-        const double cost = units <= grid ? unit_max : work / grid + 0.7 * unit_max;
+        const double cost = (double)((units + grid - 1) / grid) * unit_max;
         if (cost < best_cost - 1e-9) { best_cost = cost; best_s = S; }
       }
     }
+    static const int seg_override = [] { const char *v = getenv("NES_RZ_SEG"); return v ? atoi(v) : 0; }();  // experiments: fixed segment height
+    if (seg_override >= 16) best_s = seg_override;
     int base = 0;
     for (int j = 0; j < n_jobs; j++) {
       DevJob &jb = jobs[j];
