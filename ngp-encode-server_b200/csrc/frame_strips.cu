@@ -797,13 +797,17 @@ void plan_frame_strips(DevJob *jobs, int n_jobs, bool text_first) {
         if (jb.general || jb.bpp != 3 + cls) continue;
         const int strips = (jb.W + STRIP_W - 1) / STRIP_W, segs = (jb.H + S - 1) / S;
         units += (long)strips * segs;
-        work += (double)strips * (jb.H + segs * 3.6);  // halo rows cost the chroma half of phase A
+        work += (double)strips * (jb.H + segs * 6.2);  // what a segment costs beyond its rows (halo rows, pipeline fill), in rows: fitted on B200
       }
       if (units == 0) break;
-      const double unit_cost = S + 3.6;
-      const double cost = units <= grid ? unit_cost : work / grid + 0.7 * unit_cost;
+      const double unit_cost = S + 6.2;
+      // more units than CTAs: the work per CTA plus a small share of one unit for the ragged end -- consecutive launches overlap
+      // (programmatic dependent launch), so the tail of a launch is mostly filled by the next one
+      const double cost = units <= grid ? unit_cost : work / grid + 0.1 * unit_cost;
       if (cost < best_cost - 1e-9) { best_cost = cost; best_s = S; }
     }
+    static const int seg_override = [] { const char *v = getenv("NES_STRIPS_SEG"); return v ? atoi(v) : 0; }();  // experiments: fixed segment height
+    if (seg_override >= s_min) best_s = s_min + (seg_override - s_min) / ch * ch;
     int base[2] = {0, 0};
     for (int j = 0; j < n_jobs; j++) {
       DevJob &jb = jobs[j];
