@@ -868,7 +868,7 @@ void plan_resize_strips(DevJob *jobs, int n_jobs) {
       for (int j = 0; j < n_jobs; j++)
         if (jobs[j].rz_ok && jobs[j].bpp == bpp) hd_max = std::max(hd_max, jobs[j].Hd);
       double best_cost = 1e30;
-      for (int k = 1; k <= std::max(1, hd_max / 16); k++) {
+      for (int k = 1; k <= std::max(1, hd_max / 32); k++) {  // (segments under 32 rows never pay: a unit costs ~50 rows before its first one)
         const int S = std::max(16, ((hd_max + k - 1) / k + 15) & ~15);
         if (k > 1 && S == std::max(16, ((hd_max + k - 2) / (k - 1) + 15) & ~15)) continue;  // same height as the previous k
         double unit_max = 0;
